@@ -1,0 +1,148 @@
+"""Deterministic synthetic inputs and weights for the G/D hot path.
+
+Everything is drawn from ``numpy.random.RandomState`` (bit-stable across numpy/torch versions and
+machines), so the golden fixtures under ``tests/golden`` can be regenerated and re-checked anywhere.
+Value ranges follow what the reference's data pipeline produces:
+
+* captions sorted by decreasing length, T = longest (``attngan/datasets.py:35-36``),
+* bounding boxes as (x, y, w, h) fractions with ``-1`` marking an empty slot
+  (``attngan/datasets.py:107-109``), labels 0..79 and 80 for "no object" one-hot over 81,
+* theta / theta^-1 as in ``attngan/miscc/utils.py:16-49``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+MAX_OBJECTS = 3
+N_LABELS = 81
+
+
+def transformation_matrix(bbox: np.ndarray) -> np.ndarray:
+    """bbox (N,4) x,y,w,h -> theta (N,2,3): crops the box out of the image.
+    Follows ``attngan/miscc/utils.py:34-49`` (fp32 arithmetic)."""
+    bbox = bbox.astype(np.float32)
+    x, y, w, h = bbox[:, 0], bbox[:, 1], bbox[:, 2], bbox[:, 3]
+    th = np.zeros((bbox.shape[0], 2, 3), np.float32)
+    th[:, 0, 0] = w
+    th[:, 0, 2] = np.float32(2) * ((x + np.float32(0.5) * w) - np.float32(0.5))
+    th[:, 1, 1] = h
+    th[:, 1, 2] = np.float32(2) * ((y + np.float32(0.5) * h) - np.float32(0.5))
+    return th
+
+
+def transformation_matrix_inverse(bbox: np.ndarray) -> np.ndarray:
+    """bbox (N,4) -> theta^-1 (N,2,3): places a full canvas into the box.
+    Follows ``attngan/miscc/utils.py:16-31``; an empty slot (-1,-1,-1,-1) yields
+    [[-1,0,-4],[0,-1,-4]] whose sampling grid lies fully outside the image => exact zeros."""
+    bbox = bbox.astype(np.float32)
+    x, y, w, h = bbox[:, 0], bbox[:, 1], bbox[:, 2], bbox[:, 3]
+    sx = np.float32(1.0) / w
+    sy = np.float32(1.0) / h
+    th = np.zeros((bbox.shape[0], 2, 3), np.float32)
+    th[:, 0, 0] = sx
+    th[:, 0, 2] = np.float32(2) * sx * (np.float32(0.5) - (x + np.float32(0.5) * w))
+    th[:, 1, 1] = sy
+    th[:, 1, 2] = np.float32(2) * sy * (np.float32(0.5) - (y + np.float32(0.5) * h))
+    return th
+
+
+def bboxes_and_labels(rng: np.random.RandomState, B: int, max_objects: int = MAX_OBJECTS,
+                      n_labels: int = N_LABELS, always_valid: bool = False):
+    """Random layout: per sample k in {0..max_objects} valid boxes (first k slots), rest empty."""
+    bbox = -np.ones((B, max_objects, 4), np.float32)
+    label = np.full((B, max_objects), n_labels - 1, np.int64)
+    for b in range(B):
+        k = max_objects if always_valid else int(rng.randint(0, max_objects + 1))
+        for s in range(k):
+            w, h = rng.uniform(0.15, 0.6, size=2)
+            x = rng.uniform(0.0, 0.999 - w)
+            y = rng.uniform(0.0, 0.999 - h)
+            bbox[b, s] = (x, y, w, h)
+            label[b, s] = int(rng.randint(0, n_labels - 1))
+    onehot = np.zeros((B, max_objects, n_labels), np.float32)
+    for b in range(B):
+        for s in range(max_objects):
+            onehot[b, s, label[b, s]] = 1.0
+    flat = bbox.reshape(-1, 4)
+    theta = transformation_matrix(flat).reshape(B, max_objects, 2, 3)
+    theta_inv = transformation_matrix_inverse(flat).reshape(B, max_objects, 2, 3)
+    return bbox, label, onehot, theta, theta_inv
+
+
+def attngan_batch(B: int, T: int = 18, nef: int = 256, nz: int = 100, seed: int = 1234,
+                  sizes=(64, 128, 256)) -> dict:
+    """One synthetic AttnGAN training batch (config 5 of BASELINE.json when called with defaults
+    and B=32). Returns CPU torch tensors."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    out["noise"] = rng.standard_normal((B, nz)).astype(np.float32)
+    out["sent_emb"] = np.tanh(rng.standard_normal((B, nef))).astype(np.float32)
+    out["words_embs"] = np.tanh(rng.standard_normal((B, nef, T))).astype(np.float32)
+    lo = min(5, T)
+    lens = np.sort(rng.randint(lo, T + 1, size=B))[::-1].copy()
+    lens[0] = T
+    out["cap_lens"] = lens.astype(np.int64)
+    out["mask"] = (np.arange(T)[None, :] >= lens[:, None])
+    out["imgs"] = [rng.uniform(-1, 1, size=(B, 3, s, s)).astype(np.float32) for s in sizes]
+    bbox, label, onehot, theta, theta_inv = bboxes_and_labels(rng, B)
+    out["bbox"], out["label"], out["label_one_hot"] = bbox, label, onehot
+    out["transf_matrices"], out["transf_matrices_inv"] = theta, theta_inv
+    out["eps"] = rng.standard_normal((B, 100)).astype(np.float32)  # CA_NET reparametrisation draw
+    out["class_ids"] = np.arange(B)
+    res = {}
+    for k, v in out.items():
+        if isinstance(v, list):
+            res[k] = [torch.from_numpy(a) for a in v]
+        elif k == "class_ids":
+            res[k] = v
+        else:
+            res[k] = torch.from_numpy(np.ascontiguousarray(v))
+    return res
+
+
+def fill_state_dict(sd: dict, seed: int) -> dict:
+    """Deterministic, version-independent weights for a ``state_dict`` (keys/shapes from the
+    reference classes). Conv/Linear ~ N(0, 1/fan_in) so activations stay O(1) through the depth
+    (comparable to the orthogonal init of ``attngan/miscc/utils.py:321-331``); BatchNorm gamma ~
+    N(1, 0.02) as in the reference, beta/bias small but non-zero so bias paths are exercised."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        shape = tuple(v.shape)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros(shape, dtype=torch.long)
+        elif k.endswith("running_mean"):
+            out[k] = torch.zeros(shape, dtype=torch.float32)
+        elif k.endswith("running_var"):
+            out[k] = torch.ones(shape, dtype=torch.float32)
+        elif k.endswith("weight") and len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            out[k] = torch.from_numpy((rng.standard_normal(shape) / np.sqrt(fan_in)).astype(np.float32))
+        elif k.endswith("weight"):
+            out[k] = torch.from_numpy((1.0 + 0.02 * rng.standard_normal(shape)).astype(np.float32))
+        elif k.endswith("bias"):
+            out[k] = torch.from_numpy((0.02 * rng.standard_normal(shape)).astype(np.float32))
+        else:
+            raise KeyError("unexpected state_dict entry %s" % k)
+    return out
+
+
+class StandInEncoder:
+    """A tiny fixed, differentiable stand-in for the frozen DAMSM image encoder (Inception-v3,
+    ``attngan/model.py:207-313``), used so the DAMSM branch of ``generator_loss``
+    (``attngan/miscc/losses.py:205-224``) can be exercised without the 22.5 M-parameter network
+    (SURVEY.md section 8(f) row f1 -- the real encoder is a later scope row).
+    ``img (B,3,S,S) -> (region_features (B,nef,17,17), cnn_code (B,nef))``."""
+
+    def __init__(self, nef: int, seed: int = 7, device="cpu"):
+        rng = np.random.RandomState(seed)
+        self.w_feat = torch.from_numpy(rng.standard_normal((nef, 3, 1, 1)).astype(np.float32)).to(device)
+        self.w_code = torch.from_numpy(rng.standard_normal((nef, 3 * 16)).astype(np.float32) * 0.25).to(device)
+
+    def __call__(self, img):
+        import torch.nn.functional as F
+        feat = F.conv2d(F.adaptive_avg_pool2d(img, 17), self.w_feat)
+        code = F.linear(F.adaptive_avg_pool2d(img, 4).reshape(img.shape[0], -1), self.w_code)
+        return feat, code

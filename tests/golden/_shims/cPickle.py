@@ -1,0 +1,1 @@
+from pickle import *  # py2 cPickle stand-in (golden harness only)

@@ -1,0 +1,148 @@
+"""Pin the oracle (oracle/attngan_oracle.py) against vectors produced by executing the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from mog_b200 import synth
+from oracle import attngan_oracle as O
+
+TOL = 2e-5  # fp32 CPU vs fp32 CPU; differences are only op-ordering (e.g. x+0 canvas adds)
+
+
+def _tiny_cfg(c):
+    return O.Cfg(GF_DIM=c["GF_DIM"], DF_DIM=c["DF_DIM"], Z_DIM=c["Z_DIM"], R_NUM=c["R_NUM"],
+                 EMBEDDING_DIM=c["EMBEDDING_DIM"])
+
+
+def _build(keys, seed):
+    shapes = {k: torch.empty(s) for k, s in keys.items()}
+    return O.leafify(synth.fill_state_dict(shapes, seed))
+
+
+@pytest.fixture(scope="module")
+def keys():
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "attngan_state_dict_keys.json")) as f:
+        return json.load(f)
+
+
+def test_theta_matches_reference():
+    G, _ = gu.load("stn_cases")
+    bbox = gu.full(G, "bbox").numpy()
+    gu.check(torch.from_numpy(synth.transformation_matrix(bbox)), G["theta_ref"], 1e-7, "theta")
+    gu.check(torch.from_numpy(synth.transformation_matrix_inverse(bbox)), G["theta_inv_ref"], 1e-7, "theta_inv")
+
+
+@pytest.mark.parametrize("tag", ["scatter16", "crop64to16", "scatter15to16"])
+def test_stn(tag):
+    G, _ = gu.load("stn_cases")
+    x = gu.full(G, tag + "/x").requires_grad_(True)
+    y = O.stn(x, gu.full(G, tag + "/theta"), G[tag + "/y"]["shape"])
+    gu.check(y, G[tag + "/y"], 1e-6, tag)
+    y.backward(gu.full(G, tag + "/g"))
+    gu.check(x.grad, G[tag + "/dx"], 1e-6, tag + " dx")
+    if tag == "scatter16":  # empty slot (bbox -1): exact zeros
+        assert float(y[1].detach().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["b3", "b4"])
+def test_global_attention(tag):
+    G, _ = gu.load("attention_cases")
+    h = gu.full(G, tag + "/h").requires_grad_(True)
+    ctx = gu.full(G, tag + "/ctx").requires_grad_(True)
+    w = gu.full(G, tag + "/w").requires_grad_(True)
+    mask = gu.full(G, tag + "/mask").bool()
+    wc, attn = O.global_attention(h, ctx, mask, {"a.conv_context.weight": w}, "a")
+    gu.check(wc, G[tag + "/wc"], 1e-6)
+    gu.check(attn, G[tag + "/attn"], 1e-6)
+    wc.backward(gu.full(G, tag + "/g"))
+    gu.check(h.grad, G[tag + "/dh"], 1e-5)
+    gu.check(ctx.grad, G[tag + "/dctx"], 1e-5)
+    gu.check(w.grad, G[tag + "/dw"], 1e-5)
+
+
+def test_damsm_losses():
+    G, _ = gu.load("attention_cases")
+    cfg = O.Cfg()
+    feat = gu.full(G, "damsm/feat").requires_grad_(True)
+    code = gu.full(G, "damsm/code").requires_grad_(True)
+    words, sent = gu.full(G, "damsm/words"), gu.full(G, "damsm/sent")
+    lens = gu.full(G, "damsm/lens").long()
+    B = feat.shape[0]
+    labels = torch.arange(B)
+    w0, w1 = O.words_loss(feat, words, labels, lens, np.arange(B), B, cfg)
+    s0, s1 = O.sent_loss(code, sent, labels, np.arange(B), B, cfg)
+    for k, v in {"w0": w0, "w1": w1, "s0": s0, "s1": s1}.items():
+        gu.check(v, G["damsm/" + k], 1e-5, k)
+    (w0 + w1 + s0 + s1).backward()
+    gu.check(feat.grad, G["damsm/dfeat"], 1e-5)
+    gu.check(code.grad, G["damsm/dcode"], 1e-5)
+
+
+def test_attngan_step_matches_reference(keys):
+    """G forward, 3 D losses + grads, full G loss (adversarial + DAMSM via stand-in + KL) + grads,
+    BatchNorm running statistics -- all against the executed reference."""
+    G, meta = gu.load("attngan_tiny_step")
+    c, seed = meta["cfg"], meta["seed"]
+    cfg = _tiny_cfg(c)
+    batch = synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed)
+    PG = _build(keys["tiny"]["G_NET"], seed + 1)
+    PDs = [_build(keys["tiny"]["D_NET%d" % (64 << i)], seed + 2 + i) for i in range(3)]
+    eps = gu.full(G, "G/eps")
+    B = c["B"]
+    real, fake = torch.ones(B), torch.zeros(B)
+    tm, tmi, oh = batch["transf_matrices"], batch["transf_matrices_inv"], batch["label_one_hot"]
+    imgs, atts, mu, logvar = O.g_net(PG, cfg, batch["noise"], batch["sent_emb"], batch["words_embs"],
+                                     batch["mask"], tmi, oh, eps=eps)
+    for i in range(3):
+        gu.check(imgs[i], G["G/fake%d" % i], TOL, "fake%d" % i)
+    for i in range(2):
+        gu.check(atts[i], G["G/att%d" % i], TOL, "att%d" % i)
+    gu.check(mu, G["G/mu"], TOL)
+    gu.check(logvar, G["G/logvar"], TOL)
+    for i, PD in enumerate(PDs):
+        kw = dict(label=oh, theta=tm, theta_inv=tmi) if i == 0 else {}
+        errD = O.discriminator_loss(i, PD, cfg, batch["imgs"][i], imgs[i], batch["sent_emb"], real, fake, **kw)
+        gu.check(errD, G["D%d/errD" % i], TOL, "errD%d" % i)
+        names = [k for k, p in PD.items() if p.requires_grad]
+        grads = torch.autograd.grad(errD, [PD[k] for k in names])
+        for k, g in zip(names, grads):
+            gu.check(g, G["D%d/grad/%s" % (i, k)], 5e-5, "D%d grad %s" % (i, k))
+        for k, v in PD.items():
+            if "running" in k:
+                gu.check(v, G["D%d/buf_after_dstep/%s" % (i, k)], TOL, k)
+    enc = synth.StandInEncoder(c["EMBEDDING_DIM"])
+    adv = O.generator_gan_loss(PDs, cfg, imgs, batch["sent_emb"], real, oh, tm, tmi)
+    feat, code = enc(imgs[-1])
+    labels = torch.arange(B)
+    w0, w1 = O.words_loss(feat, batch["words_embs"], labels, batch["cap_lens"], batch["class_ids"], B, cfg)
+    s0, s1 = O.sent_loss(code, batch["sent_emb"], labels, batch["class_ids"], B, cfg)
+    total = adv + (w0 + w1) * cfg.LAMBDA + (s0 + s1) * cfg.LAMBDA
+    kl = O.kl_loss(mu, logvar)
+    gu.check(total, G["G/errG_total"], TOL, "errG_total")
+    gu.check(kl, G["G/kl"], TOL, "kl")
+    names = [k for k, p in PG.items() if p.requires_grad]
+    grads = torch.autograd.grad(total + kl, [PG[k] for k in names])
+    for k, g in zip(names, grads):
+        gu.check(g, G["G/grad/%s" % k], 2e-4, "G grad %s" % k)
+    for k, v in PG.items():
+        if "running" in k:
+            gu.check(v, G["G/buf/%s" % k], TOL, k)
+
+
+def test_attngan_gd_only_step(keys):
+    """oracle.gd_step (the G+D-only step the bench times) against the executed reference."""
+    G, meta = gu.load("attngan_tiny_gd")
+    c, seed = meta["cfg"], meta["seed"]
+    cfg = _tiny_cfg(c)
+    batch = synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed)
+    PG = _build(keys["tiny"]["G_NET"], seed + 1)
+    PDs = [_build(keys["tiny"]["D_NET%d" % (64 << i)], seed + 2 + i) for i in range(3)]
+    out = O.gd_step(PG, PDs, cfg, batch, eps=gu.full(G, "G/eps"))
+    gu.check(out["errG"], G["G/errG_adv"], TOL)
+    gu.check(out["kl"], G["G/kl"], TOL)
+    for k, p in PG.items():
+        if p.requires_grad:
+            gu.check(p.grad, G["G/grad/%s" % k], 2e-4, "G grad %s" % k)
