@@ -1,0 +1,161 @@
+/*
+ * mog.h -- C ABI of libmog.so, the sm_100a implementation of the generator / discriminator
+ * forward+backward hot path of tohinz/multiple-objects-gan (AttnGAN variant first).
+ *
+ * The reference has no native/FFI layer: the path is a set of torch library calls issued from
+ * code/coco/attngan/{model.py,GlobalAttention.py,miscc/losses.py}.  Each entry point below names
+ * the reference call site(s) it replaces ("replaces:").  All tensors are caller-owned device
+ * buffers; activations are NHWC fp32 (a logically-NCHW torch tensor in channels_last memory
+ * format is exactly that), matrices are row-major.  Every function enqueues work on `stream`
+ * (a cudaStream_t passed as void*), never synchronises, never allocates, and returns 0 or a
+ * negative MOG_ERR_* code; mog_last_error() gives the message of the calling thread's last
+ * failure.  There is no CPU fallback.
+ */
+#ifndef MOG_H_
+#define MOG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOG_VERSION 100
+
+enum {
+  MOG_OK = 0,
+  MOG_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, inconsistent shapes */
+  MOG_ERR_UNSUPPORTED = -2,  /* shape / mode not implemented by the selected kernel */
+  MOG_ERR_WORKSPACE = -3,    /* workspace too small */
+  MOG_ERR_CUDA = -4          /* a CUDA call or launch failed */
+};
+
+/* activation / epilogue codes */
+enum {
+  MOG_ACT_NONE = 0,
+  MOG_ACT_RELU = 1,
+  MOG_ACT_LRELU = 2, /* negative slope 0.2 (model.py:93,579,589) */
+  MOG_ACT_GLU = 3,   /* x[:, :C] * sigmoid(x[:, C:]) (model.py:24-32): 2C channels in, C out */
+  MOG_ACT_TANH = 4,  /* model.py:470 */
+  MOG_ACT_SIGMOID = 5
+};
+
+/* operand precision of the convolution kernels */
+enum {
+  MOG_PREC_FP32 = 0,   /* CUDA-core FFMA implicit GEMM, fp32 operands and accumulate            */
+  MOG_PREC_BF16X3 = 1, /* tcgen05: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate in TMEM   */
+  MOG_PREC_BF16 = 2    /* tcgen05: single-pass bf16 operands, fp32 accumulate in TMEM           */
+};
+
+typedef struct MogConvDesc {
+  int32_t N, H, W, Cin;  /* input tensor NHWC (before the optional fused upsample)               */
+  int32_t Cout, KH, KW;  /* filter                                                               */
+  int32_t stride, pad;
+  int32_t up2x;          /* 1: the conv reads nearest-neighbour 2x upsampled input (upBlock)     */
+  int32_t act;           /* fused epilogue: MOG_ACT_NONE / LRELU / TANH (bias added first)       */
+  int32_t precision;     /* MOG_PREC_*                                                           */
+} MogConvDesc;
+
+int mog_version(void);
+const char* mog_last_error(void);
+
+/* ---- layout ---------------------------------------------------------------------------- */
+/* replaces: nothing (the reference is NCHW throughout); boundary helpers for NCHW callers.  */
+int mog_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, void* stream);
+int mog_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, void* stream);
+/* OIHW fp32 -> GEMM B operand [KH*KW*Cin][Cout] (forward) */
+int mog_pack_weight_fwd(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW, void* stream);
+/* OIHW fp32 -> GEMM B operand [KH*KW*Cout][Cin] (data gradient) */
+int mog_pack_weight_dgrad(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW, void* stream);
+
+/* ---- convolution ----------------------------------------------------------------------- */
+/* replaces: nn.Conv2d forward incl. a preceding nn.Upsample(2,'nearest') (model.py:41-55,
+ * 587-609,626,664-677; GlobalAttention.py:25-28) and nn.Linear (H=W=KH=KW=1; model.py:324,
+ * 365,371).  y: [N,Ho,Wo,Cout]; bias may be NULL. */
+int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo);
+size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which /*0 fwd, 1 dgrad, 2 wgrad*/);
+int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const float* w_packed_fwd, const float* bias,
+                   float* y, void* workspace, size_t ws_bytes, void* stream);
+/* replaces: autograd of the above w.r.t. the input.  dy: [N,Ho,Wo,Cout] (already multiplied by
+ * the epilogue derivative, see mog_act_bwd), dx: [N,H,W,Cin]. */
+int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const float* w_packed_dgrad, float* dx,
+                     void* workspace, size_t ws_bytes, void* stream);
+/* replaces: autograd w.r.t. the weight; writes dw in OIHW (state_dict layout), deterministic
+ * split reduction through the workspace.  dbias (may be NULL): [Cout]. */
+int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const float* dy, float* dw_oihw, float* dbias,
+                     void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- BatchNorm (train mode) + activation ------------------------------------------------ */
+/* x is [S*M][C] (S segments of M rows; the object pathway calls the same BN once per object
+ * with separate statistics, model.py:393-401,685-693).
+ * replaces: nn.BatchNorm2d/1d train-mode forward (model.py:53,62,72,75,96,100,366,372,...). */
+int mog_bn_stats(const float* x, int S, int M, int C, double* sum /*[S][C]*/, double* sqsum /*[S][C]*/, void* stream);
+/* Finalises statistics: mean, invstd [S][C]; scale = gamma*invstd, shift = beta - mean*scale;
+ * running stats updated once per segment in order (momentum, unbiased variance) when not NULL. */
+int mog_bn_finalize(const double* sum, const double* sqsum, int S, int M, int C, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* y = act(x*scale + shift) (+ residual).  scale/shift may be NULL (plain activation).  For
+ * MOG_ACT_GLU x has C channels and y (and residual) C/2.
+ * replaces: BN apply + GLU / ReLU / LeakyReLU / residual add (model.py:24-32,54,63,73,80,...). */
+int mog_affine_act_fwd(const float* x, const float* scale, const float* shift, const float* residual,
+                       float* y, int S, int M, int C, int act, void* stream);
+/* Backward of BN(train)+act: pass 1 reduces dgamma=sum(dz*xhat), dbeta=sum(dz) per (segment,
+ * channel) in double; pass 2 writes dx.  dy: [S*M][C or C/2].  With mean == invstd ==
+ * dgamma_seg == dbeta_seg == NULL, mog_bn_act_bwd_apply is the backward of a plain activation
+ * of the pre-activation x (dx = dy * act'(x); used for GLU without BN, model.py:328). */
+int mog_bn_act_bwd_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, int S, int M, int C, int act,
+                          double* dgamma_seg /*[S][C]*/, double* dbeta_seg /*[S][C]*/, void* stream);
+int mog_bn_act_bwd_apply(const float* x, const float* dy, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, const double* dgamma_seg,
+                         const double* dbeta_seg, int S, int M, int C, int act, float* dx,
+                         float* dgamma /*[C], summed over segments*/, float* dbeta, void* stream);
+/* dz = dy * act'(.) given the activation OUTPUT y (LRELU / RELU / TANH / SIGMOID). */
+int mog_act_bwd(const float* dy, const float* y, float* dz, size_t n, int act, void* stream);
+
+/* ---- small elementwise helpers ----------------------------------------------------------- */
+/* 2x2 sum pooling: backward of the nearest 2x upsample fused into mog_conv2d_fwd. */
+int mog_sumpool2x2(const float* src /*[N,2H,2W,C]*/, float* dst /*[N,H,W,C]*/, int N, int H, int W, int C, void* stream);
+
+/* ---- spatial transformer (bbox crop / scatter) ------------------------------------------- */
+/* Bilinear sampling with an affine grid, zero padding, align_corners=0|1.
+ * replaces: stn() = F.affine_grid + F.grid_sample (model.py:17-21) and the per-object loops
+ * around it (model.py:107-112, 393-401, 685-693).
+ *   mode 0 "scatter-sum": x [S*B,Hi,Wi,C] (segment-major), theta [B,S,2,3] -> y [B,Ho,Wo,C] = sum_s stn(x[s*B+b], theta[b,s])
+ *   mode 1 "crop":        x [B,Hi,Wi,C], theta [B,S,2,3] -> y [S*B,Ho,Wo,Cy]; channels [0,C) sampled,
+ *                         channels [C,Cy) filled with extra[b,s,:] (label planes, model.py:686-689; may be NULL, Cy==C) */
+int mog_stn_fwd(const float* x, const float* theta, const float* extra, float* y, int mode, int B, int S,
+                int Hi, int Wi, int C, int Ho, int Wo, int Cy, int align_corners, void* stream);
+/* Input gradient of the above (gather form, deterministic; theta must be axis-aligned, i.e.
+ * theta[0][1]==theta[1][0]==0 as produced by miscc/utils.py:16-49). dy has Cy channels per pixel. */
+int mog_stn_bwd(const float* dy, const float* theta, float* dx, int mode, int B, int S,
+                int Hi, int Wi, int C, int Ho, int Wo, int Cy, int align_corners, void* stream);
+
+/* ---- word attention ----------------------------------------------------------------------- */
+/* replaces: GlobalAttentionGeneral.forward after the 1x1 conv (GlobalAttention.py:95-123):
+ * bmm -> mask -> softmax over words -> bmm.  h [B,Q,D] (NHWC pixels), src [B,T,D] (NHWC conv_context
+ * output), mask [B,T] uint8 or NULL.  mask_quirk=1 reproduces the reference's tiled mask
+ * (row (b*Q+q) uses mask[(b*Q+q) % B], GlobalAttention.py:104-108); 0 = per-sample mask.
+ * out [B,Q,D]; attn (may be NULL) [B,T,Q] as returned by the reference. */
+int mog_word_attention_fwd(const float* h, const float* src, const uint8_t* mask, float* out, float* attn,
+                           int B, int Q, int D, int T, int mask_quirk, void* stream);
+/* dh [B,Q,D]; dsrc [B,T,D] (must be zero-initialised by the caller; accumulated atomically). */
+int mog_word_attention_bwd(const float* h, const float* src, const uint8_t* mask, const float* dout,
+                           float* dh, float* dsrc, int B, int Q, int D, int T, int mask_quirk, void* stream);
+
+/* ---- loss heads --------------------------------------------------------------------------- */
+/* loss[0] (+)= weight * mean_i BCE(sigmoid(z_i), target_i) with torch's log clamp at -100;
+ * prob (may be NULL) receives sigmoid(z).  replaces: nn.Sigmoid + nn.BCELoss
+ * (model.py:627, miscc/losses.py:156-171,195-200). */
+int mog_sigmoid_bce_fwd(const float* z, const float* target /*[n]*/, float weight, int n, float* prob, float* loss,
+                        int accumulate, void* stream);
+/* dz_i = gscale[0] * weight * dBCE/dz_i / n */
+int mog_sigmoid_bce_bwd(const float* z, const float* target /*[n]*/, float weight, int n, const float* gscale,
+                        float* dz, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOG_H_ */

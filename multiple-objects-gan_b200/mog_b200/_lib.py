@@ -1,0 +1,90 @@
+"""ctypes binding of libmog.so (the C ABI declared in include/mog.h).
+
+The library is mandatory: there is no PyTorch/CPU fallback for any op on the hot path.  A
+missing or unloadable ``libmog.so`` raises ``RuntimeError`` at first use (build it with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C multiple-objects-gan_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmog.so")
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GLU, ACT_TANH, ACT_SIGMOID = range(6)
+PREC_FP32, PREC_BF16X3, PREC_BF16 = range(3)
+PREC_NAMES = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+
+class MogConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "up2x", "act", "precision")]
+
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_sz = C.c_size_t
+_dp = C.POINTER(MogConvDesc)
+
+# name -> (restype, argtypes); must list every symbol of include/mog.h (checked by tests)
+SIGNATURES = {
+    "mog_version": (_i, []),
+    "mog_last_error": (C.c_char_p, []),
+    "mog_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mog_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mog_pack_weight_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mog_pack_weight_dgrad": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mog_conv_out_hw": (_i, [_dp, C.POINTER(_i), C.POINTER(_i)]),
+    "mog_conv_workspace_bytes": (_sz, [_dp, _i]),
+    "mog_conv2d_fwd": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
+    "mog_conv2d_dgrad": (_i, [_dp, _p, _p, _p, _p, _sz, _p]),
+    "mog_conv2d_wgrad": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
+    "mog_bn_stats": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "mog_bn_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "mog_affine_act_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "mog_bn_act_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "mog_bn_act_bwd_apply": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mog_act_bwd": (_i, [_p, _p, _p, _sz, _i, _p]),
+    "mog_sumpool2x2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "mog_stn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_stn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_word_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mog_word_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mog_sigmoid_bce_fwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _p]),
+    "mog_sigmoid_bce_bwd": (_i, [_p, _p, _f, _i, _p, _p, _p]),
+}
+
+_lib = None
+launches = 0  # number of libmog entry-point calls that enqueue kernels (bench.py reports it)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libmog.so not found at %s -- the CUDA library is mandatory (no CPU fallback). "
+                "Build it: python -c 'import __graft_entry__ as g; g.build()'" % LIB_PATH)
+        try:
+            L = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise RuntimeError("cannot load %s: %s" % (LIB_PATH, e))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise RuntimeError(mog_last_error()) on failure."""
+    global launches
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, L.mog_last_error().decode()))
+    launches += 1
+    return rc

@@ -1,0 +1,417 @@
+"""torch.autograd.Function wrappers over the libmog C ABI.
+
+All activation tensors handled here are contiguous fp32 CUDA tensors in **NHWC** order
+(``[N, H, W, C]``; 2-D ``[N, C]`` for the fully-connected parts).  PyTorch supplies device
+memory, streams and the autograd tape only -- every computation is a libmog kernel.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GLU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, MogConvDesc,
+                   PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_NAMES, call)
+
+import ctypes as C
+
+_default_precision = PREC_NAMES[os.environ.get("MOG_PRECISION", "fp32")]
+
+
+def set_precision(name: str):
+    """Operand precision of the convolution kernels: 'fp32' | 'bf16x3' | 'bf16'."""
+    global _default_precision
+    _default_precision = PREC_NAMES[name]
+
+
+def get_precision() -> int:
+    return _default_precision
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError("%s: libmog ops need CUDA tensors (no CPU fallback); got %s" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s: expected float32, got %s" % (name, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("%s: expected a contiguous tensor" % name)
+
+
+# ---------------------------------------------------------------------------------------------
+# layout helpers (API boundary: the reference's tensors are NCHW)
+# ---------------------------------------------------------------------------------------------
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor -> contiguous [N,H,W,C].  Zero-copy when x already is channels_last."""
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    x = x.contiguous()
+    _chk(x, "to_nhwc")
+    N, Cc, H, W = x.shape
+    out = torch.empty((N, H, W, Cc), device=x.device, dtype=x.dtype)
+    call("mog_nchw_to_nhwc", x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream())
+    return out
+
+
+def to_nchw_view(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous [N,H,W,C] -> logical NCHW view (channels_last strides, no copy)."""
+    return x.permute(0, 3, 1, 2)
+
+
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_nchw_view(g.contiguous())
+
+
+def nhwc(x):
+    """Differentiable NCHW -> NHWC (a free autograd-tracked view when x is channels_last)."""
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    return _ToNHWC.apply(x) if x.requires_grad else to_nhwc(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution / linear
+# ---------------------------------------------------------------------------------------------
+def _packed(weight: torch.Tensor, which: str) -> torch.Tensor:
+    """Pack an OIHW parameter into the GEMM B operand; cached on the tensor per version."""
+    cache = getattr(weight, "_mog_pack", None)
+    ver = weight._version
+    if cache is None or cache.get("ver") != ver or cache.get("ptr") != weight.data_ptr():
+        cache = {"ver": ver, "ptr": weight.data_ptr()}
+        try:
+            weight._mog_pack = cache
+        except Exception:
+            pass
+    if which not in cache:
+        w = weight.detach()
+        if w.dim() == 2:
+            w = w.reshape(w.shape[0], w.shape[1], 1, 1)
+        w = w.contiguous()
+        _chk(w, "weight")
+        Co, Ci, KH, KW = w.shape
+        out = torch.empty(KH * KW * Ci * Co, device=w.device, dtype=torch.float32)
+        fn = "mog_pack_weight_fwd" if which == "fwd" else "mog_pack_weight_dgrad"
+        call(fn, w.data_ptr(), out.data_ptr(), Co, Ci, KH, KW, _stream())
+        cache[which] = out
+    return cache[which]
+
+
+def _desc(x_shape, w_shape, stride, pad, up2x, act, precision):
+    N, H, W, Ci = x_shape
+    Co, Ci2, KH, KW = w_shape
+    if Ci != Ci2:
+        raise RuntimeError("conv: input has %d channels, weight expects %d" % (Ci, Ci2))
+    d = MogConvDesc(N, H, W, Ci, Co, KH, KW, stride, pad, int(up2x), act, precision)
+    ho, wo = C.c_int(), C.c_int()
+    call("mog_conv_out_hw", C.byref(d), C.byref(ho), C.byref(wo))
+    return d, ho.value, wo.value
+
+
+def _workspace(d, which, device):
+    n = _lib.lib().mog_conv_workspace_bytes(C.byref(d), which)
+    if n == 0:
+        return None, 0
+    ws = torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
+    return ws, n
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = act(conv(up2x?(x), w) + b), NHWC.  replaces nn.Conv2d (+ nn.Upsample) of model.py."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, up2x, act, precision):
+        _chk(x, "conv input")
+        w4 = weight if weight.dim() == 4 else weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
+        d, Ho, Wo = _desc(x.shape, w4.shape, stride, pad, up2x, act, precision)
+        y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
+        ws, nws = _workspace(d, 0, x.device)
+        b = None if bias is None else bias.detach().contiguous()
+        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _packed(weight, "fwd").data_ptr(), _ptr(b),
+             y.data_ptr(), _ptr(ws), nws, _stream())
+        ctx.cfg = (stride, pad, up2x, act, precision)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        stride, pad, up2x, act, precision = ctx.cfg
+        dy = dy.contiguous()
+        w4 = weight if weight.dim() == 4 else weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
+        d, Ho, Wo = _desc(x.shape, w4.shape, stride, pad, up2x, ACT_NONE, precision)
+        st = _stream()
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, st)
+            dy = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ws, nws = _workspace(d, 1, x.device)
+            call("mog_conv2d_dgrad", C.byref(d), dy.data_ptr(), _packed(weight, "dgrad").data_ptr(),
+                 dx.data_ptr(), _ptr(ws), nws, st)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty(w4.shape, device=x.device, dtype=torch.float32)
+            if ctx.has_bias:
+                db = torch.empty(d.Cout, device=x.device, dtype=torch.float32)
+            ws, nws = _workspace(d, 2, x.device)
+            call("mog_conv2d_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db),
+                 _ptr(ws), nws, st)
+            dw = dw.reshape(weight.shape)
+        return dx, dw, db, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, up2x=False, act=ACT_NONE, precision=None):
+    if precision is None:
+        precision = _default_precision
+    return Conv2dFn.apply(x, weight, bias, stride, pad, bool(up2x), act, precision)
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, precision=None):
+    """x [N, F] -> [N, O] through the same implicit-GEMM kernels (H=W=KH=KW=1)."""
+    N, Fi = x.shape
+    y = conv2d(x.reshape(N, 1, 1, Fi), weight, bias, 1, 0, False, act, precision)
+    return y.reshape(N, -1)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm (train) + activation (+ residual)
+# ---------------------------------------------------------------------------------------------
+class BnActFn(torch.autograd.Function):
+    """y = act(BN_train(x)) (+ residual) over rows [S*M, C] with per-segment statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, S, act, momentum, eps):
+        _chk(x, "bn input")
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        if rows % S:
+            raise RuntimeError("bn: %d rows not divisible by %d segments" % (rows, S))
+        M = rows // S
+        dev = x.device
+        st = _stream()
+        stats = torch.empty((2, S, Cc), device=dev, dtype=torch.float64)
+        call("mog_bn_stats", x.data_ptr(), S, M, Cc, stats[0].data_ptr(), stats[1].data_ptr(), st)
+        mis = torch.empty((4, S, Cc), device=dev, dtype=torch.float32)  # mean, invstd, scale, shift
+        g = gamma.detach().contiguous()
+        b = beta.detach().contiguous()
+        call("mog_bn_finalize", stats[0].data_ptr(), stats[1].data_ptr(), S, M, Cc, g.data_ptr(), b.data_ptr(),
+             eps, momentum, _ptr(running_mean), _ptr(running_var), mis[0].data_ptr(), mis[1].data_ptr(),
+             mis[2].data_ptr(), mis[3].data_ptr(), st)
+        Co = Cc // 2 if act == ACT_GLU else Cc
+        y = torch.empty(x.shape[:-1] + (Co,), device=dev, dtype=torch.float32)
+        if residual is not None:
+            _chk(residual, "bn residual")
+        call("mog_affine_act_fwd", x.data_ptr(), mis[2].data_ptr(), mis[3].data_ptr(), _ptr(residual),
+             y.data_ptr(), S, M, Cc, act, st)
+        ctx.cfg = (S, M, Cc, act)
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, g, b, mis)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, b, mis = ctx.saved_tensors
+        S, M, Cc, act = ctx.cfg
+        dy = dy.contiguous()
+        st = _stream()
+        dev = x.device
+        red = torch.empty((2, S, Cc), device=dev, dtype=torch.float64)
+        call("mog_bn_act_bwd_reduce", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
+             g.data_ptr(), b.data_ptr(), S, M, Cc, act, red[0].data_ptr(), red[1].data_ptr(), st)
+        dx = torch.empty_like(x)
+        dgb = torch.empty((2, Cc), device=dev, dtype=torch.float32)
+        call("mog_bn_act_bwd_apply", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
+             g.data_ptr(), b.data_ptr(), red[0].data_ptr(), red[1].data_ptr(), S, M, Cc, act, dx.data_ptr(),
+             dgb[0].data_ptr(), dgb[1].data_ptr(), st)
+        dres = dy if ctx.has_res else None
+        return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None
+
+
+def bn_act(x, bn, act=ACT_NONE, residual=None, segments=1):
+    """Apply a train-mode ``nn.BatchNorm*d``-compatible module ``bn`` (weight, bias,
+    running_mean, running_var, num_batches_tracked, momentum, eps) followed by ``act``."""
+    if not bn.training:
+        raise RuntimeError("libmog implements the training path (batch statistics) only")
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += segments
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, segments, act,
+                         float(bn.momentum), float(bn.eps))
+
+
+# ---------------------------------------------------------------------------------------------
+# spatial transformer
+# ---------------------------------------------------------------------------------------------
+class StnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, theta, extra, mode, B, S, Ho, Wo, align):
+        _chk(x, "stn input")
+        theta = theta.contiguous()
+        _chk(theta, "stn theta")
+        n_in, Hi, Wi, Cc = x.shape
+        if theta.shape != (B, S, 2, 3):
+            raise RuntimeError("stn: theta must be [B,S,2,3], got %s" % (tuple(theta.shape),))
+        if n_in != (S * B if mode == 0 else B):
+            raise RuntimeError("stn: input batch %d inconsistent with mode %d, B=%d, S=%d" % (n_in, mode, B, S))
+        Cy = Cc
+        if extra is not None:
+            extra = extra.contiguous()
+            _chk(extra, "stn extra")
+            Cy = Cc + extra.shape[-1]
+        n_out = B if mode == 0 else S * B
+        y = torch.empty((n_out, Ho, Wo, Cy), device=x.device, dtype=torch.float32)
+        call("mog_stn_fwd", x.data_ptr(), theta.data_ptr(), _ptr(extra), y.data_ptr(), mode, B, S, Hi, Wi, Cc,
+             Ho, Wo, Cy, int(align), _stream())
+        ctx.cfg = (mode, B, S, Hi, Wi, Cc, Ho, Wo, Cy, int(align))
+        ctx.save_for_backward(theta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (theta,) = ctx.saved_tensors
+        mode, B, S, Hi, Wi, Cc, Ho, Wo, Cy, align = ctx.cfg
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dy = dy.contiguous()
+            n_in = S * B if mode == 0 else B
+            dx = torch.empty((n_in, Hi, Wi, Cc), device=dy.device, dtype=torch.float32)
+            call("mog_stn_bwd", dy.data_ptr(), theta.data_ptr(), dx.data_ptr(), mode, B, S, Hi, Wi, Cc, Ho, Wo,
+                 Cy, align, _stream())
+        return dx, None, None, None, None, None, None, None, None
+
+
+def stn_scatter_sum(x, theta, B, S, out_hw, align_corners=False):
+    """x [S*B,Hi,Wi,C] (segment-major), theta [B,S,2,3] -> [B,Ho,Wo,C] = sum_s stn(x[s*B+b], theta[b,s])."""
+    return StnFn.apply(x, theta, None, 0, B, S, out_hw[0], out_hw[1], align_corners)
+
+
+def stn_crop(x, theta, S, out_hw, extra=None, align_corners=False):
+    """x [B,Hi,Wi,C], theta [B,S,2,3] -> [S*B,Ho,Wo,C(+E)]; ``extra`` [B,S,E] is broadcast into
+    the trailing channels (the label planes of D_NET64's object pathway)."""
+    return StnFn.apply(x, theta, extra, 1, x.shape[0], S, out_hw[0], out_hw[1], align_corners)
+
+
+# ---------------------------------------------------------------------------------------------
+# word attention
+# ---------------------------------------------------------------------------------------------
+class WordAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, src, mask, quirk, want_attn):
+        _chk(h, "attention h")
+        _chk(src, "attention src")
+        B, Q, D = h.shape
+        T = src.shape[1]
+        out = torch.empty_like(h)
+        attn = torch.empty((B, T, Q), device=h.device, dtype=torch.float32) if want_attn else None
+        m = None
+        if mask is not None:
+            m = mask.to(torch.uint8).contiguous()
+        call("mog_word_attention_fwd", h.data_ptr(), src.data_ptr(), _ptr(m), out.data_ptr(), _ptr(attn),
+             B, Q, D, T, int(quirk), _stream())
+        ctx.cfg = (B, Q, D, T, int(quirk))
+        ctx.save_for_backward(h, src, m)
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+            return out, attn
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        h, src, m = ctx.saved_tensors
+        B, Q, D, T, quirk = ctx.cfg
+        dout = dout.contiguous()
+        dh = torch.empty_like(h)
+        dsrc = torch.zeros_like(src)
+        call("mog_word_attention_bwd", h.data_ptr(), src.data_ptr(), _ptr(m), dout.data_ptr(), dh.data_ptr(),
+             dsrc.data_ptr(), B, Q, D, T, quirk, _stream())
+        return dh, dsrc, None, None, None
+
+
+def word_attention(h, src, mask=None, mask_quirk=True, want_attn=True):
+    """h [B,Q,D], src [B,T,D] -> (weighted context [B,Q,D], attn [B,T,Q] or None)."""
+    return WordAttnFn.apply(h, src, mask, mask_quirk, want_attn)
+
+
+# ---------------------------------------------------------------------------------------------
+# sigmoid + BCE head
+# ---------------------------------------------------------------------------------------------
+class SigmoidBceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, target, weight):
+        z = z.contiguous()
+        _chk(z, "bce logits")
+        target = target.detach().to(torch.float32).contiguous()
+        _chk(target, "bce target")
+        if target.numel() != z.numel():
+            raise RuntimeError("bce: %d logits vs %d targets" % (z.numel(), target.numel()))
+        loss = torch.empty(1, device=z.device, dtype=torch.float32)
+        call("mog_sigmoid_bce_fwd", z.data_ptr(), target.data_ptr(), float(weight), z.numel(), None,
+             loss.data_ptr(), 0, _stream())
+        ctx.weight = float(weight)
+        ctx.save_for_backward(z, target)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        z, target = ctx.saved_tensors
+        g = g.contiguous().reshape(1)
+        dz = torch.empty_like(z)
+        call("mog_sigmoid_bce_bwd", z.data_ptr(), target.data_ptr(), ctx.weight, z.numel(), g.data_ptr(),
+             dz.data_ptr(), _stream())
+        return dz, None, None
+
+
+def sigmoid_bce(z, target, weight: float = 1.0):
+    """weight * mean BCE(sigmoid(z), target)   (nn.Sigmoid + nn.BCELoss of the reference heads)."""
+    return SigmoidBceFn.apply(z, target, weight)
+
+
+# ---------------------------------------------------------------------------------------------
+# plain activation (no BatchNorm), e.g. the GLU of CA_NET (model.py:328)
+# ---------------------------------------------------------------------------------------------
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        _chk(x, "act input")
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        Co = Cc // 2 if act == ACT_GLU else Cc
+        y = torch.empty(x.shape[:-1] + (Co,), device=x.device, dtype=torch.float32)
+        call("mog_affine_act_fwd", x.data_ptr(), None, None, None, y.data_ptr(), 1, rows, Cc, act, _stream())
+        ctx.act = act
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        dx = torch.empty_like(x)
+        call("mog_bn_act_bwd_apply", x.data_ptr(), dy.data_ptr(), None, None, None, None, None, None, 1, rows, Cc,
+             ctx.act, dx.data_ptr(), None, None, _stream())
+        return dx, None
+
+
+def activation(x, act):
+    return ActFn.apply(x, act)

@@ -280,5 +280,5 @@ if __name__ == "__main__":
     for i, cls in enumerate([M.D_NET64, M.D_NET128, M.D_NET256]):
         kfull["D_NET%d" % (64 << i)] = {k: list(v.shape) for k, v in cls().state_dict().items()}
     with open(os.path.join(HERE, "attngan_state_dict_keys.json"), "w") as f:
-        json.dump({"tiny": keys, "config5": kfull}, f, indent=0, sort_keys=True)
+        json.dump({"tiny": keys, "config5": kfull}, f, indent=0)  # insertion order = parameter order
     print("done")

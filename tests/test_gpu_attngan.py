@@ -1,0 +1,155 @@
+"""Network-level parity of the libmog AttnGAN modules (G_NET, D_NET64/128/256, losses) against
+(a) golden vectors produced by executing the unmodified reference and (b) the CPU oracle on a
+second seed.  Run on the B200 box: -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from mog_b200 import synth
+from oracle import attngan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# fp32 CUDA-core path vs fp32 CPU reference: summation order only.  Gradients of deep nets
+# accumulate a little more.
+OUT_TOL = 5e-5
+GRAD_TOL = 5e-4
+
+
+def _set_cfg(c):
+    from mog_b200.attngan.miscc.config import cfg, reset_cfg
+    reset_cfg()
+    cfg.GAN.GF_DIM, cfg.GAN.DF_DIM, cfg.GAN.Z_DIM = c["GF_DIM"], c["DF_DIM"], c["Z_DIM"]
+    cfg.GAN.R_NUM, cfg.TEXT.EMBEDDING_DIM, cfg.TEXT.WORDS_NUM = c["R_NUM"], c["EMBEDDING_DIM"], c["T"]
+    cfg.TRAIN.BATCH_SIZE = c["B"]
+    return cfg
+
+
+def _build(c, seed):
+    from mog_b200.attngan import model as M
+    _set_cfg(c)
+    netG = M.G_NET()
+    netsD = [M.D_NET64(), M.D_NET128(), M.D_NET256()]
+    netG.load_state_dict(synth.fill_state_dict(netG.state_dict(), seed + 1))
+    for i, d in enumerate(netsD):
+        d.load_state_dict(synth.fill_state_dict(d.state_dict(), seed + 2 + i))
+    return netG.cuda().train(), [d.cuda().train() for d in netsD]
+
+
+def _dev(batch):
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, list):
+            out[k] = [t.cuda() for t in v]
+        elif torch.is_tensor(v):
+            out[k] = v.cuda()
+        else:
+            out[k] = v
+    return out
+
+
+def test_attngan_step_vs_reference_golden():
+    """G forward, 3 discriminator losses + all D gradients + BN running stats against the
+    reference run (tests/golden/attngan_tiny_step), then G adversarial+KL gradients
+    (tests/golden/attngan_tiny_gd)."""
+    from mog_b200.attngan.miscc import losses as L
+    G, meta = gu.load("attngan_tiny_step")
+    G2, _ = gu.load("attngan_tiny_gd")
+    c, seed = meta["cfg"], meta["seed"]
+    netG, netsD = _build(c, seed)
+    b = _dev(synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed))
+    eps = gu.full(G, "G/eps").cuda()
+    B = c["B"]
+    real, fake = torch.ones(B, device="cuda"), torch.zeros(B, device="cuda")
+    tm, tmi, oh = b["transf_matrices"], b["transf_matrices_inv"], b["label_one_hot"]
+    imgs, atts, mu, logvar = netG(b["noise"], b["sent_emb"], b["words_embs"], b["mask"], tmi, oh, eps=eps)
+    for i in range(3):
+        gu.check(imgs[i], G["G/fake%d" % i], OUT_TOL, "fake%d" % i)
+    for i in range(2):
+        gu.check(atts[i], G["G/att%d" % i], OUT_TOL, "att%d" % i)
+    gu.check(mu, G["G/mu"], OUT_TOL, "mu")
+    gu.check(logvar, G["G/logvar"], OUT_TOL, "logvar")
+    for i, netD in enumerate(netsD):
+        netD.zero_grad()
+        kw = dict(local_labels=oh, transf_matrices=tm, transf_matrices_inv=tmi) if i == 0 else {}
+        errD = L.discriminator_loss(netD, b["imgs"][i], imgs[i], b["sent_emb"], real, fake, [0], **kw)
+        errD.backward()
+        gu.check(errD, G["D%d/errD" % i], OUT_TOL, "errD%d" % i)
+        for k, p in netD.named_parameters():
+            gu.check(p.grad, G["D%d/grad/%s" % (i, k)], GRAD_TOL, "D%d grad %s" % (i, k))
+        for k, v in netD.state_dict().items():
+            if "running" in k:
+                gu.check(v, G["D%d/buf_after_dstep/%s" % (i, k)], OUT_TOL, k)
+    # generator step, adversarial + KL (no DAMSM), D weights frozen (their wgrad is skipped)
+    for d in netsD:
+        for p in d.parameters():
+            p.requires_grad_(False)
+    netG.zero_grad()
+    errG, _ = L.generator_loss(netsD, None, imgs, real, b["words_embs"], b["sent_emb"], None, b["cap_lens"],
+                               b["class_ids"], [0], local_labels=oh, transf_matrices=tm, transf_matrices_inv=tmi)
+    kl = L.KL_loss(mu, logvar)
+    gu.check(errG, G2["G/errG_adv"], OUT_TOL, "errG")
+    gu.check(kl, G2["G/kl"], OUT_TOL, "kl")
+    (errG + kl).backward()
+    for k, p in netG.named_parameters():
+        gu.check(p.grad, G2["G/grad/%s" % k], GRAD_TOL, "G grad %s" % k)
+
+
+def test_attngan_step_vs_oracle_second_seed():
+    """Same step on different data/weights (odd batch, different T) against the CPU oracle."""
+    from mog_b200.attngan.miscc import losses as L
+    c = dict(GF_DIM=8, DF_DIM=8, Z_DIM=16, R_NUM=1, EMBEDDING_DIM=24, T=9, B=3)
+    seed = 321
+    netG, netsD = _build(c, seed)
+    cfgo = O.Cfg(GF_DIM=8, DF_DIM=8, Z_DIM=16, R_NUM=1, EMBEDDING_DIM=24)
+    PG = O.leafify(netG.state_dict())
+    PDs = [O.leafify(d.state_dict()) for d in netsD]
+    batch = synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed)
+    ref = O.gd_step(PG, PDs, cfgo, batch)
+    b = _dev(batch)
+    B = c["B"]
+    real, fake = torch.ones(B, device="cuda"), torch.zeros(B, device="cuda")
+    tm, tmi, oh = b["transf_matrices"], b["transf_matrices_inv"], b["label_one_hot"]
+    imgs, _, mu, logvar = netG(b["noise"], b["sent_emb"], b["words_embs"], b["mask"], tmi, oh, eps=b["eps"])
+    for i in range(3):
+        assert gu.rel_l2(imgs[i].detach().cpu().numpy(), ref["fake_imgs"][i].numpy()) < OUT_TOL
+    for i, netD in enumerate(netsD):
+        kw = dict(local_labels=oh, transf_matrices=tm, transf_matrices_inv=tmi) if i == 0 else {}
+        errD = L.discriminator_loss(netD, b["imgs"][i], imgs[i], b["sent_emb"], real, fake, [0], **kw)
+        errD.backward()
+        assert abs(float(errD) - float(ref["errD"][i])) < 1e-4 * abs(float(ref["errD"][i]))
+        for k, p in netD.named_parameters():
+            assert gu.rel_l2(p.grad.cpu().numpy(), PDs[i][k].grad.numpy()) < GRAD_TOL, k
+    for d in netsD:
+        for p in d.parameters():
+            p.requires_grad_(False)
+    errG, _ = L.generator_loss(netsD, None, imgs, real, b["words_embs"], b["sent_emb"], None, b["cap_lens"],
+                               b["class_ids"], [0], local_labels=oh, transf_matrices=tm, transf_matrices_inv=tmi)
+    (errG + L.KL_loss(mu, logvar)).backward()
+    assert abs(float(errG) - float(ref["errG"])) < 1e-4 * abs(float(ref["errG"]))
+    for k, p in netG.named_parameters():
+        assert gu.rel_l2(p.grad.cpu().numpy(), PG[k].grad.numpy()) < GRAD_TOL, k
+
+
+def test_public_api_shapes_and_reference_signatures():
+    """Reference-facing surface: NCHW in/out, COND/UNCOND heads return probabilities."""
+    c = dict(GF_DIM=8, DF_DIM=8, Z_DIM=16, R_NUM=1, EMBEDDING_DIM=24, T=9, B=2)
+    netG, netsD = _build(c, 5)
+    b = _dev(synth.attngan_batch(2, T=9, nef=24, nz=16, seed=5))
+    imgs, atts, mu, logvar = netG(b["noise"], b["sent_emb"], b["words_embs"], b["mask"],
+                                  b["transf_matrices_inv"], b["label_one_hot"])
+    assert [tuple(i.shape) for i in imgs] == [(2, 3, 64, 64), (2, 3, 128, 128), (2, 3, 256, 256)]
+    assert [tuple(a.shape) for a in atts] == [(2, 9, 64, 64), (2, 9, 128, 128)]
+    assert mu.shape == (2, 100) and logvar.shape == (2, 100)
+    f = netsD[0](b["imgs"][0], b["label_one_hot"], b["transf_matrices"], b["transf_matrices_inv"])
+    assert tuple(f.shape) == (2, 64, 4, 4)
+    # NCHW-contiguous input (as a torch DataLoader would deliver) is converted, not rejected
+    f2 = netsD[2](b["imgs"][2].contiguous())
+    assert tuple(f2.shape) == (2, 64, 4, 4)
+    p = netsD[0].COND_DNET(f, b["sent_emb"])
+    q = netsD[0].UNCOND_DNET(f)
+    assert p.shape == (2,) and q.shape == (2,) and float(p.min()) > 0 and float(p.max()) < 1
