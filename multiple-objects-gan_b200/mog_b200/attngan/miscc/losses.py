@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import torch
 
-from .. import ops
+from ... import ops
 from .config import cfg
 
 
