@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of one COCO-AttnGAN 256x256 G+D training step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mog|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one synthetic batch (config 5 of BASELINE.json:
+B=32/GPU, T=18, GF 48, DF 96, R_NUM 3): G_NET forward; D_NET64/128/256 loss + backward + Adam;
+generator adversarial + KL loss, backward through the three discriminators and G, Adam, EMA
+(code/coco/attngan/trainer.py:294-342).  The DAMSM term (Inception-v3 image encoder) is a later
+scope row and is NOT part of the step; `config.workload` says so.
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same
+through the public trainer API with pinned-host inputs copied in and the losses read back every
+step; `roofline` = the dominant convolution kernel timed alone with CUDA events; `cpu_baseline`
+= the oracle (CPU port of the reference) on a bounded sample.  `--impl reference` times that CPU
+port alone, with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "multiple-objects-gan_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CFG5 = dict(GF_DIM=48, DF_DIM=96, Z_DIM=100, R_NUM=3, EMBEDDING_DIM=256, T=18)
+# forward GMAC per image from SURVEY.md section 8(a.1)/8(d) (hook-counted on the reference modules),
+# G+D-only step: G fwd 25.09; D step fwd 18.70 + bwd 36.86; G step D fwd 9.18 + D dgrad 9.18 + G bwd 50.18
+GMAC_PER_IMAGE_GD = 149.2
+WORKLOAD = "attngan256-coco-config5 G+D step (G fwd; 3x D loss+bwd+Adam; G adv+KL loss+bwd+Adam+EMA); no DAMSM/Inception"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def set_cfg():
+    from mog_b200.attngan.miscc.config import cfg, reset_cfg
+    reset_cfg()
+    cfg.GAN.GF_DIM, cfg.GAN.DF_DIM, cfg.GAN.Z_DIM, cfg.GAN.R_NUM = CFG5["GF_DIM"], CFG5["DF_DIM"], CFG5["Z_DIM"], CFG5["R_NUM"]
+    cfg.TEXT.EMBEDDING_DIM, cfg.TEXT.WORDS_NUM = CFG5["EMBEDDING_DIM"], CFG5["T"]
+    cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2, cfg.TRAIN.SMOOTH.GAMMA3, cfg.TRAIN.SMOOTH.LAMBDA = 4.0, 5.0, 10.0, 50.0
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle port of the reference on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, batch):
+    from mog_b200 import synth
+    from oracle import attngan_oracle as O
+    from mog_b200.attngan import model as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    set_cfg()
+    torch.manual_seed(1234)
+    # parameter shapes from the host-side modules (never moved to a device here); N(0, 1/fan_in) fill
+    sdG = synth.fill_state_dict(M.G_NET().state_dict(), 1)
+    sdDs = [synth.fill_state_dict(c().state_dict(), 2 + i) for i, c in enumerate((M.D_NET64, M.D_NET128, M.D_NET256))]
+    PG, PDs = O.leafify(sdG), [O.leafify(s) for s in sdDs]
+    ocfg = O.Cfg(**{k: v for k, v in CFG5.items() if k != "T"})
+    b = synth.attngan_batch(batch, T=CFG5["T"], nef=CFG5["EMBEDDING_DIM"], nz=CFG5["Z_DIM"], seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.gd_step(PG, PDs, ocfg, b)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return {"value": batch * len(times) / tot, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "oracle/attngan_oracle.gd_step (torch CPU fp32 port of the reference step, fwd+bwd, no "
+                      "optimiser) at config 5, batch %d, %d warm-up + %d timed steps" % (batch, warmup, len(times)),
+            "ms_per_step": 1e3 * tot / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, args.ref_batch)
+    line = {"impl": "reference", "metric": "images/sec (G+D fwd+bwd) COCO-AttnGAN 256^2", "value": r["value"],
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": args.ref_batch, "device": "cpu"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# libmog arm
+# --------------------------------------------------------------------------------------------
+def run_mog(args):
+    import __graft_entry__ as ge
+    from mog_b200 import _lib, ops, parallel, synth
+    from mog_b200.attngan.miscc.utils import weights_init
+    from mog_b200.attngan.trainer import condGANTrainer
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the libmog path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    ws = parallel.init_from_env("nccl")
+    rank = parallel.rank()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        ge.build()
+    if ws > 1:
+        dist.barrier()
+    cfg = set_cfg()
+    ops.set_precision(args.precision)
+    cfg.TRAIN.BATCH_SIZE = args.batch
+    B, K, W = args.batch, args.steps, args.warmup
+
+    torch.manual_seed(1234)
+    tr = condGANTrainer("", None, 0, None)
+    _, _, netG, netsD, _ = tr.build_models()   # weights_init (orthogonal) on device, broadcast from rank 0
+    optG, optDs = tr.define_optimizers(netG, netsD)
+    st = tr.make_step_state(netG, netsD, optG, optDs)
+
+    host = synth.attngan_batch(B, T=CFG5["T"], nef=CFG5["EMBEDDING_DIM"], nz=CFG5["Z_DIM"], seed=1234 + rank)
+    keys = ["sent_emb", "words_embs", "mask", "transf_matrices", "transf_matrices_inv", "label_one_hot", "noise"]
+    pinned = {k: host[k].pin_memory() for k in keys}
+    pinned_imgs = [t.pin_memory() for t in host["imgs"]]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values()) + \
+        sum(t.numel() * t.element_size() for t in pinned_imgs)
+
+    def upload():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        imgs = [t.to(dev, non_blocking=True) for t in pinned_imgs]
+        return d, imgs
+
+    d, imgs = upload()
+
+    def step(d, imgs, fresh_noise=True):
+        return tr.train_step(st, imgs, d["sent_emb"], d["words_embs"], d["mask"], d["transf_matrices"],
+                             d["transf_matrices_inv"], d["label_one_hot"], host["cap_lens"], host["class_ids"],
+                             noise=None if fresh_noise else d["noise"])
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        """n calls bracketed by barrier+sync, CUDA events on the launching stream; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if ws > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(W):
+        step(d, imgs)
+    n0 = _lib.launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(lambda: step(d, imgs), K)
+    launches = _lib.launch_count() - n0
+    clocks = cs.summary()
+    value = ws * B * K / (ms / 1e3)
+
+    # ---- end to end: pinned host inputs copied in, losses read back, every step
+    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dd, ii = upload()
+        eD, eG, kl = step(dd, ii)
+        loss_host.copy_(torch.stack((eD, eG, kl)), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    e2e_value = ws * B * K / (ms_e2e / 1e3)
+
+    line = None
+    roof = cpu = None
+    if rank == 0:
+        roof = roofline_probe(dev, args, B)
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        # free the device-side state first? not needed: the CPU leg only touches host memory
+        cpu = cpu_reference_run(1, 1, args.ref_batch)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        pk, src = peaks()
+        line = {"metric": "images/sec (G+D fwd+bwd) COCO-AttnGAN 256^2", "value": value, "unit": "images/s",
+                "n_gpus": ws, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (3-pass split, fp32-equivalent) + fp32 accumulate",
+                          "bf16": "bf16 operands, fp32 accumulate"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": ws * B, "words": CFG5["T"],
+                           "parallelism": "dp%d (NCCL grad all-reduce per net)" % ws,
+                           "precision": args.precision, "l2": "working set per step (>5 GB) exceeds the 126 MB L2; no flush needed",
+                           "optimizer": "torch Adam + EMA inside the timed region",
+                           "algorithmic_gflop_per_image": 2 * GMAC_PER_IMAGE_GD,
+                           "step_tflops_achieved": 2 * GMAC_PER_IMAGE_GD * 1e9 * value / 1e12},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K},
+                "roofline": roof, "cpu_baseline": cpu, "peaks": src}
+        print(json.dumps(line))
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_probe(dev, args, B):
+    """The dominant kernel timed alone: the largest conv launch of the step, G.h_net3.upsample
+    (nearest x2 + conv3x3 96->96 at 256x256; implicit GEMM M=B*65536, N=96, K=864 -- SURVEY 8(a.1)),
+    forward, through the same ops.conv2d entry the model uses."""
+    from mog_b200 import ops
+    pk, src = peaks()
+    x = torch.randn(B, 128, 128, 96, device=dev)
+    w = torch.randn(96, 96, 3, 3, device=dev) * 0.03
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            ops.conv2d(x, w, None, 1, 1, True, 0)
+        times = []
+        for _ in range(5):
+            flush.zero_()                      # evict L2 between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            ops.conv2d(x, w, None, 1, 1, True, 0)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    flops = 2.0 * B * 256 * 256 * 96 * 864
+    achieved = flops / (ms / 1e3) / 1e12
+    peak = pk["bf16_tflops"]
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "conv fwd G.h_net3.upsample (up2x + 3x3, 96->96 @256^2), precision=%s" % args.precision,
+            "ms_per_launch": ms, "peak_source": src + " bf16 burst (kernel timed alone)",
+            "algorithmic_flops_per_launch": flops}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mog", choices=["mog", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
+    ap.add_argument("--precision", default=os.environ.get("MOG_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "mog":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_mog(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,8 @@ typedef struct MogConvDesc {
 
 int mog_version(void);
 const char* mog_last_error(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
+unsigned long long mog_launch_count(void);
 
 /* ---- layout ---------------------------------------------------------------------------- */
 /* replaces: nothing (the reference is NCHW throughout); boundary helpers for NCHW callers.  */

@@ -13,7 +13,11 @@ namespace mog {
 char* err_buf();
 int fail(int code, const char* fmt, ...);
 
+// number of kernels launched by this library since load (mog_launch_count)
+void count_launch();
+
 inline int check_launch(const char* what) {
+  count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

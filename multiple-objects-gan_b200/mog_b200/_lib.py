@@ -32,6 +32,7 @@ _dp = C.POINTER(MogConvDesc)
 SIGNATURES = {
     "mog_version": (_i, []),
     "mog_last_error": (C.c_char_p, []),
+    "mog_launch_count": (C.c_ulonglong, []),
     "mog_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mog_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mog_pack_weight_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
@@ -57,7 +58,6 @@ SIGNATURES = {
 }
 
 _lib = None
-launches = 0  # number of libmog entry-point calls that enqueue kernels (bench.py reports it)
 
 
 def lib():
@@ -79,12 +79,15 @@ def lib():
     return _lib
 
 
+def launch_count() -> int:
+    """Kernels launched by libmog since load (counted inside the library)."""
+    return int(lib().mog_launch_count())
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise RuntimeError(mog_last_error()) on failure."""
-    global launches
     L = lib()
     rc = getattr(L, name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, L.mog_last_error().decode()))
-    launches += 1
     return rc
