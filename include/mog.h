@@ -66,10 +66,13 @@ unsigned long long mog_launch_count(void);
 /* replaces: nothing (the reference is NCHW throughout); boundary helpers for NCHW callers.  */
 int mog_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, void* stream);
 int mog_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, void* stream);
-/* OIHW fp32 -> GEMM B operand [KH*KW*Cin][Cout] (forward) */
-int mog_pack_weight_fwd(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW, void* stream);
-/* OIHW fp32 -> GEMM B operand [KH*KW*Cout][Cin] (data gradient) */
-int mog_pack_weight_dgrad(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW, void* stream);
+/* Packs an OIHW fp32 weight (state_dict layout) into the GEMM B operand of the forward conv
+ * (which = 0) or of the data gradient (which = 1) for the kernel selected by d->precision:
+ * fp32 [K][N] for the CUDA-core path; bf16 hi(/lo) planes [Npad][Kpad], K-major, one block per
+ * stride phase for the tcgen05 path.  The buffer is opaque; size it with mog_packed_weight_bytes.
+ * Re-pack after every optimiser step (weights changed). */
+size_t mog_packed_weight_bytes(const MogConvDesc* d, int which);
+int mog_pack_weight(const MogConvDesc* d, int which, const float* w_oihw, void* w_packed, void* stream);
 
 /* ---- convolution ----------------------------------------------------------------------- */
 /* replaces: nn.Conv2d forward incl. a preceding nn.Upsample(2,'nearest') (model.py:41-55,
@@ -77,11 +80,11 @@ int mog_pack_weight_dgrad(const float* w_oihw, float* w_packed, int Cout, int Ci
  * 365,371).  y: [N,Ho,Wo,Cout]; bias may be NULL. */
 int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo);
 size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which /*0 fwd, 1 dgrad, 2 wgrad*/);
-int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const float* w_packed_fwd, const float* bias,
+int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* w_packed_fwd, const float* bias,
                    float* y, void* workspace, size_t ws_bytes, void* stream);
 /* replaces: autograd of the above w.r.t. the input.  dy: [N,Ho,Wo,Cout] (already multiplied by
  * the epilogue derivative, see mog_act_bwd), dx: [N,H,W,Cin]. */
-int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const float* w_packed_dgrad, float* dx,
+int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* w_packed_dgrad, float* dx,
                      void* workspace, size_t ws_bytes, void* stream);
 /* replaces: autograd w.r.t. the weight; writes dw in OIHW (state_dict layout), deterministic
  * split reduction through the workspace.  dbias (may be NULL): [Cout]. */

@@ -1,48 +1,45 @@
-// conv.cu -- C-ABI entry points of the convolution family; builds the gather-GEMM problems and
-// dispatches on MogConvDesc.precision.
+// conv.cu -- C-ABI entry points of the convolution family.  Builds the gather-GEMM problems
+// (forward: one; data gradient: one per stride phase) and dispatches on MogConvDesc.precision:
+// MOG_PREC_FP32 -> CUDA-core kernels (conv_ffma.cu); MOG_PREC_BF16X3 / MOG_PREC_BF16 -> tcgen05
+// kernels (conv_tc.cu, conv_tc_wgrad.cu) whenever the shape is eligible (gathered channel count
+// a multiple of 8), else the exact CUDA-core kernel.
 #include "conv_common.cuh"
 
 using namespace mog;
+
+namespace mog {
+// conv_ffma.cu
+__global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KHW);
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KHW);
+}  // namespace mog
 
 static int validate(const MogConvDesc* d, const char* who) {
   MOG_REQUIRE(d, "%s: null descriptor", who);
   MOG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "%s: non-positive dims", who);
   MOG_REQUIRE(d->KH > 0 && d->KW > 0 && d->KH <= 8 && d->KW <= 8 && d->KH * d->KW <= 64, "%s: filter %dx%d unsupported", who, d->KH, d->KW);
-  MOG_REQUIRE(d->stride >= 1 && d->pad >= 0, "%s: bad stride/pad", who);
+  MOG_REQUIRE(d->stride >= 1 && d->stride <= 8 && d->pad >= 0, "%s: bad stride/pad", who);
   MOG_REQUIRE(d->up2x == 0 || d->up2x == 1, "%s: up2x must be 0/1", who);
+  MOG_REQUIRE(d->precision >= MOG_PREC_FP32 && d->precision <= MOG_PREC_BF16, "%s: unknown precision %d", who, d->precision);
   int HL = d->H << d->up2x, WL = d->W << d->up2x;
   MOG_REQUIRE(HL + 2 * d->pad >= d->KH && WL + 2 * d->pad >= d->KW, "%s: filter larger than padded input", who);
   return MOG_OK;
 }
 
-extern "C" int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
-  int rc = validate(d, "mog_conv_out_hw");
-  if (rc) return rc;
+static void out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
   int HL = d->H << d->up2x, WL = d->W << d->up2x;
-  if (Ho) *Ho = (HL + 2 * d->pad - d->KH) / d->stride + 1;
-  if (Wo) *Wo = (WL + 2 * d->pad - d->KW) / d->stride + 1;
-  return MOG_OK;
+  *Ho = (HL + 2 * d->pad - d->KH) / d->stride + 1;
+  *Wo = (WL + 2 * d->pad - d->KW) / d->stride + 1;
 }
 
-extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
-  if (validate(d, "mog_conv_workspace_bytes")) return 0;
-  int Ho, Wo;
-  mog_conv_out_hw(d, &Ho, &Wo);
-  if (which == 1) return d->up2x ? (size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cin * sizeof(float) : 0;
-  if (which == 2) return (size_t)wgrad_splits(*d, Ho, Wo) * d->KH * d->KW * d->Cin * d->Cout * sizeof(float);
-  return 0;
-}
+static int passes_of(const MogConvDesc* d) { return d->precision == MOG_PREC_BF16X3 ? 3 : 1; }
+static bool tc_fwd(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_gather_eligible(d->Cin, d->Cout); }
+static bool tc_dgrad(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_gather_eligible(d->Cout, d->Cin); }
 
-extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const float* w, const float* bias, float* y,
-                              void* workspace, size_t ws_bytes, void* stream) {
-  int rc = validate(d, "mog_conv2d_fwd");
-  if (rc) return rc;
-  MOG_REQUIRE(x && w && y, "mog_conv2d_fwd: null tensor");
-  (void)workspace; (void)ws_bytes;
+// ---- problem builders -----------------------------------------------------------------------
+static IGemmParams fwd_problem(const MogConvDesc* d) {
   int Ho, Wo;
-  mog_conv_out_hw(d, &Ho, &Wo);
+  out_hw(d, &Ho, &Wo);
   IGemmParams p{};
-  p.src = x; p.wmat = w; p.bias = bias; p.dst = y;
   p.N = d->N; p.Hs = d->H; p.Ws = d->W; p.Cs = d->Cin; p.up2x = d->up2x;
   p.Hr = Ho; p.Wr = Wo; p.rs = d->stride;
   p.nth = d->KH; p.ntw = d->KW;
@@ -53,53 +50,151 @@ extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const float*
   p.act = d->act;
   p.M = (long long)d->N * Ho * Wo;
   p.K = d->KH * d->KW * d->Cin;
-  if (d->precision != MOG_PREC_FP32) return fail(MOG_ERR_UNSUPPORTED, "mog_conv2d_fwd: precision %d not built", d->precision);
+  return p;
+}
+
+// One gather-GEMM per stride phase: input pixels (hi, wi) with hi%s==ph, wi%s==pw only see the taps
+// kh with (ph + pad - kh) % s == 0, at dy row hi/s + (ph + pad - kh)/s.  Returns false for an
+// empty phase (no rows).
+static bool dgrad_problem(const MogConvDesc* d, int ph, int pw, IGemmParams* out) {
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  const int HL = d->H << d->up2x, WL = d->W << d->up2x;
+  const int s = d->stride;
+  IGemmParams p{};
+  p.N = d->N; p.Hs = Ho; p.Ws = Wo; p.Cs = d->Cout; p.up2x = 0;
+  p.Hr = (HL - ph + s - 1) / s; p.Wr = (WL - pw + s - 1) / s; p.rs = 1;
+  if (p.Hr <= 0 || p.Wr <= 0) return false;
+  int nth = 0, ntw = 0, khs[8], kws[8];
+  for (int kh = 0; kh < d->KH; ++kh)
+    if (((ph + d->pad - kh) % s + s) % s == 0) { khs[nth] = kh; p.off_h[nth] = (ph + d->pad - kh) / s; ++nth; }
+  for (int kw = 0; kw < d->KW; ++kw)
+    if (((pw + d->pad - kw) % s + s) % s == 0) { kws[ntw] = kw; p.off_w[ntw] = (pw + d->pad - kw) / s; ++ntw; }
+  if (nth == 0 || ntw == 0) { nth = 0; ntw = 1; }  // no tap reaches this phase: K = 0, zeros are written
+  p.nth = nth; p.ntw = ntw;
+  for (int a = 0; a < nth; ++a)
+    for (int b = 0; b < ntw; ++b) p.tapw[a * ntw + b] = khs[a] * d->KW + kws[b];
+  p.Cd = d->Cin; p.Hd = HL; p.Wd = WL; p.dsh = s; p.doh = ph; p.dsw = s; p.dow = pw;
+  p.act = MOG_ACT_NONE;
+  p.M = (long long)d->N * p.Hr * p.Wr;
+  p.K = nth * ntw * d->Cout;
+  *out = p;
+  return true;
+}
+
+static size_t tc_bytes(int ntaps, int Cs, int Cd, int passes) { return tc_packed_bytes(ntaps, Cs, Cd, passes); }
+
+static bool tc_wgrad(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_wgrad_eligible(*d); }
+
+// ---- public API ---------------------------------------------------------------------------------
+extern "C" int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
+  int rc = validate(d, "mog_conv_out_hw");
+  if (rc) return rc;
+  int a, b;
+  out_hw(d, &a, &b);
+  if (Ho) *Ho = a;
+  if (Wo) *Wo = b;
+  return MOG_OK;
+}
+
+extern "C" size_t mog_packed_weight_bytes(const MogConvDesc* d, int which) {
+  if (validate(d, "mog_packed_weight_bytes")) return 0;
+  const size_t dense = (size_t)d->KH * d->KW * d->Cin * d->Cout * sizeof(float);
+  if (which == 0) return tc_fwd(d) ? tc_bytes(d->KH * d->KW, d->Cin, d->Cout, passes_of(d)) : dense;
+  if (which == 1) {
+    if (!tc_dgrad(d)) return dense;
+    size_t tot = 0;
+    for (int ph = 0; ph < d->stride; ++ph)
+      for (int pw = 0; pw < d->stride; ++pw) {
+        IGemmParams p;
+        if (!dgrad_problem(d, ph, pw, &p)) continue;
+        tot += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+      }
+    return tot;
+  }
+  return 0;
+}
+
+extern "C" int mog_pack_weight(const MogConvDesc* d, int which, const float* w, void* out, void* stream) {
+  int rc = validate(d, "mog_pack_weight");
+  if (rc) return rc;
+  MOG_REQUIRE(w && out && (which == 0 || which == 1), "mog_pack_weight: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const size_t total = (size_t)d->Cout * d->Cin * d->KH * d->KW;
+  const unsigned blocks = (unsigned)ceil_div_ll((long long)total, 256);
+  if (which == 0) {
+    if (!tc_fwd(d)) {
+      pack_fwd_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
+      return check_launch("pack_fwd_kernel");
+    }
+    int taps[64];
+    for (int i = 0; i < d->KH * d->KW; ++i) taps[i] = i;
+    return tc_pack(w, out, d->Cout, d->Cin, d->KH, d->KW, 0, d->KH * d->KW, taps, passes_of(d), st);
+  }
+  if (!tc_dgrad(d)) {
+    pack_dgrad_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
+    return check_launch("pack_dgrad_kernel");
+  }
+  unsigned char* o = static_cast<unsigned char*>(out);
+  for (int ph = 0; ph < d->stride; ++ph)
+    for (int pw = 0; pw < d->stride; ++pw) {
+      IGemmParams p;
+      if (!dgrad_problem(d, ph, pw, &p)) continue;
+      rc = tc_pack(w, o, d->Cout, d->Cin, d->KH, d->KW, 1, p.nth * p.ntw, p.tapw, passes_of(d), st);
+      if (rc) return rc;
+      o += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+    }
+  return MOG_OK;
+}
+
+extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
+  if (validate(d, "mog_conv_workspace_bytes")) return 0;
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  if (which == 1) return d->up2x ? (size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cin * sizeof(float) : 0;
+  if (which == 2) return tc_wgrad(d) ? tc_wgrad_workspace_bytes(*d, Ho, Wo) : wgrad_ffma_workspace_bytes(*d, Ho, Wo);
+  return 0;
+}
+
+extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* w, const float* bias, float* y,
+                              void* workspace, size_t ws_bytes, void* stream) {
+  int rc = validate(d, "mog_conv2d_fwd");
+  if (rc) return rc;
+  MOG_REQUIRE(x && w && y, "mog_conv2d_fwd: null tensor");
+  (void)workspace; (void)ws_bytes;
+  IGemmParams p = fwd_problem(d);
+  p.src = x; p.bias = bias; p.dst = y;
+  if (tc_fwd(d)) return launch_igemm_tc(p, w, passes_of(d), as_stream(stream));
+  p.wmat = static_cast<const float*>(w);
   return launch_igemm_ffma(p, as_stream(stream));
 }
 
-extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const float* wt, float* dx, void* workspace,
+extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* wt, float* dx, void* workspace,
                                 size_t ws_bytes, void* stream) {
   int rc = validate(d, "mog_conv2d_dgrad");
   if (rc) return rc;
   MOG_REQUIRE(dy && wt && dx, "mog_conv2d_dgrad: null tensor");
-  if (d->precision != MOG_PREC_FP32) return fail(MOG_ERR_UNSUPPORTED, "mog_conv2d_dgrad: precision %d not built", d->precision);
-  int Ho, Wo;
-  mog_conv_out_hw(d, &Ho, &Wo);
-  const int HL = d->H << d->up2x, WL = d->W << d->up2x;  // logical input grid of the conv
   float* target = dx;
   if (d->up2x) {
     size_t need = mog_conv_workspace_bytes(d, 1);
     if (!workspace || ws_bytes < need) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_dgrad: workspace %zu < %zu", ws_bytes, need);
     target = static_cast<float*>(workspace);
   }
-  const int s = d->stride;
   cudaStream_t st = as_stream(stream);
-  // one gather-GEMM per stride phase: input pixels (hi, wi) with hi%s==ph, wi%s==pw only see the
-  // taps kh with (ph + pad - kh) % s == 0, at dy row hi/s + (ph + pad - kh)/s.
-  for (int ph = 0; ph < s; ++ph) {
-    for (int pw = 0; pw < s; ++pw) {
-      IGemmParams p{};
-      p.src = dy; p.wmat = wt; p.bias = nullptr; p.dst = target;
-      p.N = d->N; p.Hs = Ho; p.Ws = Wo; p.Cs = d->Cout; p.up2x = 0;
-      p.Hr = (HL - ph + s - 1) / s; p.Wr = (WL - pw + s - 1) / s; p.rs = 1;
-      if (p.Hr <= 0 || p.Wr <= 0) continue;
-      int nth = 0, ntw = 0, khs[8], kws[8];
-      for (int kh = 0; kh < d->KH; ++kh)
-        if (((ph + d->pad - kh) % s + s) % s == 0) { khs[nth] = kh; p.off_h[nth] = (ph + d->pad - kh) / s; ++nth; }
-      for (int kw = 0; kw < d->KW; ++kw)
-        if (((pw + d->pad - kw) % s + s) % s == 0) { kws[ntw] = kw; p.off_w[ntw] = (pw + d->pad - kw) / s; ++ntw; }
-      p.nth = nth; p.ntw = ntw;
-      for (int a = 0; a < nth; ++a)
-        for (int b = 0; b < ntw; ++b) p.tapw[a * ntw + b] = khs[a] * d->KW + kws[b];
-      p.Cd = d->Cin; p.Hd = HL; p.Wd = WL; p.dsh = s; p.doh = ph; p.dsw = s; p.dow = pw;
-      p.act = MOG_ACT_NONE;
-      p.M = (long long)d->N * p.Hr * p.Wr;
-      p.K = nth * ntw * d->Cout;
-      if (p.K == 0) {
-        // no tap reaches this phase: gradient is zero there. Handled by a K=0 GEMM (writes zeros).
-        p.nth = 0; p.ntw = 1;
+  const bool use_tc = tc_dgrad(d);
+  const unsigned char* wp = static_cast<const unsigned char*>(wt);
+  for (int ph = 0; ph < d->stride; ++ph) {
+    for (int pw = 0; pw < d->stride; ++pw) {
+      IGemmParams p;
+      if (!dgrad_problem(d, ph, pw, &p)) continue;
+      p.src = dy; p.bias = nullptr; p.dst = target;
+      if (use_tc) {
+        rc = launch_igemm_tc(p, wp, passes_of(d), st);
+        wp += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+      } else {
+        p.wmat = static_cast<const float*>(wt);
+        rc = launch_igemm_ffma(p, st);
       }
-      rc = launch_igemm_ffma(p, st);
       if (rc) return rc;
     }
   }
@@ -112,13 +207,19 @@ extern "C" int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const floa
   int rc = validate(d, "mog_conv2d_wgrad");
   if (rc) return rc;
   MOG_REQUIRE(x && dy && dw, "mog_conv2d_wgrad: null tensor");
-  if (d->precision != MOG_PREC_FP32) return fail(MOG_ERR_UNSUPPORTED, "mog_conv2d_wgrad: precision %d not built", d->precision);
   int Ho, Wo;
-  mog_conv_out_hw(d, &Ho, &Wo);
+  out_hw(d, &Ho, &Wo);
   size_t need = mog_conv_workspace_bytes(d, 2);
   if (!workspace || ws_bytes < need) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_wgrad: workspace %zu < %zu", ws_bytes, need);
   cudaStream_t st = as_stream(stream);
-  rc = launch_wgrad_ffma(*d, Ho, Wo, x, dy, dw, static_cast<float*>(workspace), st);
+  int splits = 1;
+  float* ws = static_cast<float*>(workspace);
+  if (tc_wgrad(d))
+    rc = launch_wgrad_tc(*d, Ho, Wo, x, dy, ws, passes_of(d), &splits, st);
+  else
+    rc = launch_wgrad_ffma_partial(*d, Ho, Wo, x, dy, ws, &splits, st);
+  if (rc) return rc;
+  rc = launch_wgrad_reduce(ws, dw, splits, d->KH * d->KW * d->Cin, d->Cout, d->Cin, d->KH * d->KW, st);
   if (rc) return rc;
   if (dbias) return launch_colsum(dy, dbias, (long long)d->N * Ho * Wo, d->Cout, st);
   return MOG_OK;

@@ -27,10 +27,24 @@ struct IGemmParams {
 };
 
 int launch_igemm_ffma(const IGemmParams& p, cudaStream_t st);
-int launch_wgrad_ffma(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* dw,
-                      float* ws, cudaStream_t st);
-int wgrad_splits(const MogConvDesc& d, int Ho, int Wo);
+int launch_wgrad_ffma_partial(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws,
+                              int* splits_out, cudaStream_t st);
+size_t wgrad_ffma_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
+int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int KHW, cudaStream_t st);
 int launch_colsum(const float* x, float* out, long long M, int C, cudaStream_t st);
 int launch_sumpool(const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st);
+
+// tcgen05 path (conv_tc.cu, conv_tc_wgrad.cu)
+namespace tc { struct TcWeightLayout; }
+bool tc_gather_eligible(int Cs, int Cd);
+int tc_bn_for(int Cd);
+int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
+            const int* taps, int passes, cudaStream_t st);
+size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes);
+int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, cudaStream_t st);
+bool tc_wgrad_eligible(const MogConvDesc& d);
+size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
+int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws, int passes,
+                    int* splits_out, cudaStream_t st);
 
 }  // namespace mog

@@ -428,8 +428,8 @@ int wgrad_splits(const MogConvDesc& d, int Ho, int Wo) {
   return (int)s;
 }
 
-int launch_wgrad_ffma(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* dw,
-                      float* ws, cudaStream_t st) {
+int launch_wgrad_ffma_partial(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws,
+                              int* splits_out, cudaStream_t st) {
   WgradParams p;
   p.x = x; p.dy = dy; p.ws = ws;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.up2x = d.up2x;
@@ -446,11 +446,17 @@ int launch_wgrad_ffma(const MogConvDesc& d, int Ho, int Wo, const float* x, cons
     wgrad_kernel<4><<<grid, NT, 0, st>>>(p);
   else
     wgrad_kernel<1><<<grid, NT, 0, st>>>(p);
-  int rc = check_launch("wgrad_kernel");
-  if (rc) return rc;
-  size_t total = (size_t)p.K * d.Cout;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(ws, dw, splits, p.K, d.Cout,
-                                                                                      d.Cin, d.KH * d.KW);
+  *splits_out = splits;
+  return check_launch("wgrad_kernel");
+}
+
+size_t wgrad_ffma_workspace_bytes(const MogConvDesc& d, int Ho, int Wo) {
+  return (size_t)wgrad_splits(d, Ho, Wo) * d.KH * d.KW * d.Cin * d.Cout * sizeof(float);
+}
+
+int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int KHW, cudaStream_t st) {
+  size_t total = (size_t)K * Cout;
+  wgrad_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(ws, dw, splits, K, Cout, Cin, KHW);
   return check_launch("wgrad_reduce_kernel");
 }
 
@@ -463,19 +469,6 @@ extern "C" int mog_sumpool2x2(const float* src, float* dst, int N, int H, int W,
   size_t total = (size_t)N * H * W * C;
   sumpool2x2_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, as_stream(stream)>>>(src, dst, N, H, W, C);
   return check_launch("sumpool2x2_kernel");
-}
-
-extern "C" int mog_pack_weight_fwd(const float* w, float* out, int Cout, int Cin, int KH, int KW, void* stream) {
-  MOG_REQUIRE(w && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "mog_pack_weight_fwd: bad argument");
-  size_t total = (size_t)Cout * Cin * KH * KW;
-  pack_fwd_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, as_stream(stream)>>>(w, out, Cout, Cin, KH * KW);
-  return check_launch("pack_fwd_kernel");
-}
-extern "C" int mog_pack_weight_dgrad(const float* w, float* out, int Cout, int Cin, int KH, int KW, void* stream) {
-  MOG_REQUIRE(w && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "mog_pack_weight_dgrad: bad argument");
-  size_t total = (size_t)Cout * Cin * KH * KW;
-  pack_dgrad_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, as_stream(stream)>>>(w, out, Cout, Cin, KH * KW);
-  return check_launch("pack_dgrad_kernel");
 }
 
 namespace mog {

@@ -1,0 +1,344 @@
+// conv_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a.
+//
+//   D[M x N] = A[M x K] * B[K x N]      M = output pixels (gathered rows), N = output channels,
+//                                        K = taps x input channels
+//
+// * A is never materialised: producer warps gather the fp32 NHWC pixels of each (tap, channel
+//   chunk), split them on the fly into bf16 hi (+ lo for the 3-pass mode) and store them into
+//   shared memory in the canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte atoms).
+//   Nearest-2x upsampling, stride, padding and the per-phase tap subsets of the data gradient
+//   are all just index arithmetic of the gather (IGemmParams).
+// * B (weights) is pre-packed once per optimiser step into bf16 hi/lo planes [N][K] (K-major),
+//   copied by the producers into the same swizzled layout.
+// * One elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16 per instruction, fp32
+//   accumulator in TMEM).  MOG_PREC_BF16X3 issues three MMAs per k-step
+//   (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo) into the same accumulator: fp32-equivalent products
+//   (~2^-16 relative) at one third of the bf16 rate; MOG_PREC_BF16 issues only the first.
+// * mbarrier pipeline: full[s] (128 producer arrivals) / empty[s] (tcgen05.commit) over `stages`
+//   shared-memory stages; accum barrier (tcgen05.commit) hands the TMEM tile to the epilogue.
+// * Epilogue: the 4 producer warps read their TMEM lane quarter with tcgen05.ld (32x32b.x16),
+//   add bias / apply the activation and store fp32 NHWC rows.
+//
+// The weight gradient (reduction over pixels, both operands MN-major) is in conv_tc_wgrad.cu.
+#include <cuda_bf16.h>
+
+#include "conv_common.cuh"
+#include "tc_common.cuh"
+
+namespace mog {
+namespace tc {
+
+struct TcParams {
+  IGemmParams g;
+  const __nv_bfloat16* Bhi;  // [Npad][Kpad]
+  const __nv_bfloat16* Blo;  // [Npad][Kpad] (3-pass mode) or nullptr
+  int Kpad;
+  int BN;
+  int passes;
+  int stages;
+  int tmem_cols;
+};
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  if (act == MOG_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  if (act == MOG_ACT_TANH) return tanhf(v);
+  if (act == MOG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MOG_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte aligned base (SWIZZLE_128B atoms)
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const IGemmParams& g = p.g;
+  const int nplanes = p.passes == 3 ? 2 : 1;
+  const int a_plane = BM * 128;        // bytes of one A plane (128 rows x 64 bf16)
+  const int b_plane = p.BN * 128;      // bytes of one B plane
+  const int stage_bytes = nplanes * (a_plane + b_plane);
+  unsigned char* bar_base = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* accum = empty + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+  }
+  if (t == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], NPROD);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int nk = p.Kpad / BK;
+
+  if (warp < 4) {
+    // ===================== producers: gather + split + swizzled store ======================
+    const int r = t;  // this thread's tile row
+    const long long m = m0 + r;
+    const bool row_ok = m < g.M;
+    int rn = 0, h0 = 0, w0 = 0;
+    if (row_ok) {
+      int rw = (int)(m % g.Wr);
+      long long q = m / g.Wr;
+      int rh = (int)(q % g.Hr);
+      rn = (int)(q / g.Hr);
+      h0 = rh * g.rs;
+      w0 = rw * g.rs;
+    }
+    const int HL = g.Hs << g.up2x, WL = g.Ws << g.up2x;
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const int rx = r & 7;
+    // running decode of k -> (tap, channel); chunks of 8 channels never straddle a tap (Cs % 8 == 0)
+    int c = 0, th = 0, tw = 0;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % p.stages;
+      const uint32_t ph = (uint32_t)((kc / p.stages) & 1);
+      mbar_wait(&empty[s], ph ^ 1u);
+      unsigned char* st = smem + (size_t)s * stage_bytes;
+      unsigned char* a_hi = st;
+      unsigned char* a_lo = st + a_plane;                 // valid only when nplanes == 2
+      unsigned char* b_hi = st + nplanes * a_plane;
+      unsigned char* b_lo = b_hi + b_plane;
+      // ---- A: 8 chunks of 8 channels for this row
+      float4 v[8][2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j][1] = v[j][0];
+        if (row_ok && th < g.nth) {
+          const int sh = h0 + g.off_h[th], sw = w0 + g.off_w[tw];
+          if (sh >= 0 && sh < HL && sw >= 0 && sw < WL) {
+            const size_t off = (((size_t)rn * g.Hs + (sh >> g.up2x)) * g.Ws + (sw >> g.up2x)) * g.Cs + c;
+            const float4* sp = reinterpret_cast<const float4*>(g.src + off);
+            v[j][0] = __ldg(sp);
+            v[j][1] = __ldg(sp + 1);
+          }
+        }
+        c += 8;
+        if (c >= g.Cs) {
+          c = 0;
+          if (++tw == g.ntw) { tw = 0; ++th; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          hi[e] = *reinterpret_cast<uint32_t*>(&h2);
+          if (nplanes == 2) {
+            float2 hf = __bfloat1622float2(h2);
+            __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+            lo[e] = *reinterpret_cast<uint32_t*>(&l2);
+          }
+        }
+        const uint32_t off = row_off + (uint32_t)((j ^ rx) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (nplanes == 2) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      // ---- B: BN rows x 8 chunks per plane, already bf16
+      const size_t kbase = (size_t)kc * BK;
+      for (int i = t; i < p.BN * 8; i += NPROD) {
+        const int row = i >> 3, ch = i & 7;
+        const size_t goff = (size_t)(n0 + row) * p.Kpad + kbase + ch * 8;
+        const uint32_t soff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
+        *reinterpret_cast<uint4*>(b_hi + soff) = __ldg(reinterpret_cast<const uint4*>(p.Bhi + goff));
+        if (nplanes == 2) *reinterpret_cast<uint4*>(b_lo + soff) = __ldg(reinterpret_cast<const uint4*>(p.Blo + goff));
+      }
+      fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full[s]);
+    }
+
+    // ===================== epilogue: TMEM -> registers -> global ===========================
+    mbar_wait(accum, 0);
+    tcgen05_fence_after();
+    float* dptr = nullptr;
+    if (row_ok) {
+      int rw = (int)(m % g.Wr);
+      long long q = m / g.Wr;
+      int rh = (int)(q % g.Hr);
+      size_t pix = ((size_t)rn * g.Hd + (rh * g.dsh + g.doh)) * g.Wd + (rw * g.dsw + g.dow);
+      dptr = g.dst + pix * g.Cd + n0;
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(taddr + (uint32_t)c0, acc);
+      if (row_ok) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float b = (g.bias && n0 + c0 + j < g.Cd) ? __ldg(g.bias + n0 + c0 + j) : 0.f;
+          o[j] = epi_act(__uint_as_float(acc[j]) + b, g.act);
+        }
+        if (((g.Cd & 3) == 0) && n0 + c0 + 15 < g.Cd) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dptr + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < g.Cd) dptr[c0 + j] = o[j];
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer (warp 4) ==============================================
+    const uint32_t idesc = make_idesc_bf16(BM, p.BN);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % p.stages;
+      const uint32_t ph = (uint32_t)((kc / p.stages) & 1);
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + a_plane;
+        const uint32_t b_hi = st + nplanes * a_plane, b_lo = b_hi + b_plane;
+        for (int pass = 0; pass < p.passes; ++pass) {
+          const uint32_t ab = pass == 1 ? a_lo : a_hi;   // 0: hi*hi   1: lo*hi   2: hi*lo
+          const uint32_t bb = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t da = make_desc_sw128(ab + k16 * 32);
+            const uint64_t db = make_desc_sw128(bb + k16 * 32);
+            umma_bf16(tmem_base, da, db, idesc, (kc | pass | k16) != 0);
+          }
+        }
+        umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+        if (kc == nk - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 OIHW -> bf16 hi/lo planes [Npad][Kpad], k = local_tap * Cs + c
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* w;  // OIHW
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;  // may be null
+  int Cout, Cin, KHW;
+  int transpose;  // 0: n = co, c = ci (forward)    1: n = ci, c = co (data gradient)
+  int ntaps;
+  int taps[64];
+  int Nreal, Npad, Cs, K, Kpad;
+};
+
+__global__ void pack_tc_kernel(const PackArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)a.Npad * a.Kpad;
+  if (idx >= total) return;
+  int k = (int)(idx % a.Kpad);
+  int n = (int)(idx / a.Kpad);
+  float v = 0.f;
+  if (n < a.Nreal && k < a.K) {
+    int tl = k / a.Cs, c = k - tl * a.Cs;
+    int tap = a.taps[tl];
+    int co = a.transpose ? c : n, ci = a.transpose ? n : c;
+    v = a.w[((size_t)co * a.Cin + ci) * a.KHW + tap];
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  a.hi[idx] = h;
+  if (a.lo) a.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+using namespace tc;
+
+int tc_bn_for(int Cd) {
+  int cpad = ceil_div(Cd, 16) * 16;
+  int tiles = ceil_div(cpad, 256);
+  int bn = ceil_div(ceil_div(cpad, tiles), 16) * 16;
+  return bn;
+}
+
+bool tc_gather_eligible(int Cs, int Cd) { return (Cs % 8) == 0 && Cd >= 1; }
+
+// layout of the packed buffer of one gather-GEMM problem (K = ntaps * Cs, N = Cd)
+TcWeightLayout tc_weight_layout(int ntaps, int Cs, int Cd, int passes) {
+  TcWeightLayout L;
+  L.BN = tc_bn_for(Cd);
+  L.ntiles = ceil_div(Cd, L.BN);
+  L.Npad = L.ntiles * L.BN;
+  L.K = ntaps * Cs;
+  L.Kpad = ceil_div(L.K > 0 ? L.K : 1, BK) * BK;
+  L.plane_elems = (size_t)L.Npad * L.Kpad;
+  L.planes = passes == 3 ? 2 : 1;
+  return L;
+}
+
+size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes) {
+  TcWeightLayout L = tc_weight_layout(ntaps, Cs, Cd, passes);
+  size_t b = L.plane_elems * L.planes * 2;
+  return (b + 255) / 256 * 256;  // keep every phase 256-byte aligned
+}
+
+int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
+            const int* taps, int passes, cudaStream_t st) {
+  const int Cs = transpose ? Cout : Cin, Cd = transpose ? Cin : Cout;
+  TcWeightLayout L = tc_weight_layout(ntaps, Cs, Cd, passes);
+  PackArgs a;
+  a.w = w_oihw;
+  a.hi = static_cast<__nv_bfloat16*>(out);
+  a.lo = L.planes == 2 ? a.hi + L.plane_elems : nullptr;
+  a.Cout = Cout; a.Cin = Cin; a.KHW = KH * KW; a.transpose = transpose; a.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) a.taps[i] = taps[i];
+  a.Nreal = Cd; a.Npad = L.Npad; a.Cs = Cs; a.K = L.K; a.Kpad = L.Kpad;
+  pack_tc_kernel<<<(unsigned)ceil_div_ll((long long)L.plane_elems, 256), 256, 0, st>>>(a);
+  return check_launch("pack_tc_kernel");
+}
+
+int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, cudaStream_t st) {
+  TcWeightLayout L = tc_weight_layout(g.nth * g.ntw, g.Cs, g.Cd, passes);
+  TcParams p;
+  p.g = g;
+  p.Bhi = static_cast<const __nv_bfloat16*>(packed);
+  p.Blo = L.planes == 2 ? p.Bhi + L.plane_elems : nullptr;
+  p.Kpad = L.Kpad;
+  p.BN = L.BN;
+  p.passes = passes;
+  const int stage_bytes = L.planes * (BM * 128 + L.BN * 128);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < L.BN) cols *= 2;
+  p.tmem_cols = cols;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(MOG_ERR_CUDA, "conv_tc_kernel smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div_ll(g.M, BM), (unsigned)L.ntiles);
+  conv_tc_kernel<<<grid, NTHREADS, smem, st>>>(p);
+  return check_launch("conv_tc_kernel");
+}
+
+}  // namespace mog

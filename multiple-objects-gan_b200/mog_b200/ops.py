@@ -90,8 +90,9 @@ def nhwc(x):
 # ---------------------------------------------------------------------------------------------
 # convolution / linear
 # ---------------------------------------------------------------------------------------------
-def _packed(weight: torch.Tensor, which: str) -> torch.Tensor:
-    """Pack an OIHW parameter into the GEMM B operand; cached on the tensor per version."""
+def _packed(weight: torch.Tensor, which: str, d: MogConvDesc) -> torch.Tensor:
+    """Pack an OIHW parameter into the GEMM B operand of the kernel selected by ``d`` (fp32 matrix or
+    bf16 hi/lo planes per stride phase); cached on the tensor per (version, conv geometry)."""
     cache = getattr(weight, "_mog_pack", None)
     ver = weight._version
     if cache is None or cache.get("ver") != ver or cache.get("ptr") != weight.data_ptr():
@@ -100,18 +101,20 @@ def _packed(weight: torch.Tensor, which: str) -> torch.Tensor:
             weight._mog_pack = cache
         except Exception:
             pass
-    if which not in cache:
+    # the dgrad packing depends on stride/pad (phase tap subsets) and, with odd sizes, on H/W parity
+    key = (which, d.precision, d.stride, d.pad, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
+    if key not in cache:
         w = weight.detach()
         if w.dim() == 2:
             w = w.reshape(w.shape[0], w.shape[1], 1, 1)
         w = w.contiguous()
         _chk(w, "weight")
-        Co, Ci, KH, KW = w.shape
-        out = torch.empty(KH * KW * Ci * Co, device=w.device, dtype=torch.float32)
-        fn = "mog_pack_weight_fwd" if which == "fwd" else "mog_pack_weight_dgrad"
-        call(fn, w.data_ptr(), out.data_ptr(), Co, Ci, KH, KW, _stream())
-        cache[which] = out
-    return cache[which]
+        wi = 0 if which == "fwd" else 1
+        n = _lib.lib().mog_packed_weight_bytes(C.byref(d), wi)
+        out = torch.empty((n + 3) // 4, device=w.device, dtype=torch.float32)
+        call("mog_pack_weight", C.byref(d), wi, w.data_ptr(), out.data_ptr(), _stream())
+        cache[key] = out
+    return cache[key]
 
 
 def _desc(x_shape, w_shape, stride, pad, up2x, act, precision):
@@ -144,7 +147,7 @@ class Conv2dFn(torch.autograd.Function):
         y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
         ws, nws = _workspace(d, 0, x.device)
         b = None if bias is None else bias.detach().contiguous()
-        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _packed(weight, "fwd").data_ptr(), _ptr(b),
+        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _packed(weight, "fwd", d).data_ptr(), _ptr(b),
              y.data_ptr(), _ptr(ws), nws, _stream())
         ctx.cfg = (stride, pad, up2x, act, precision)
         ctx.has_bias = bias is not None
@@ -167,7 +170,7 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             ws, nws = _workspace(d, 1, x.device)
-            call("mog_conv2d_dgrad", C.byref(d), dy.data_ptr(), _packed(weight, "dgrad").data_ptr(),
+            call("mog_conv2d_dgrad", C.byref(d), dy.data_ptr(), _packed(weight, "dgrad", d).data_ptr(),
                  dx.data_ptr(), _ptr(ws), nws, st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty(w4.shape, device=x.device, dtype=torch.float32)

@@ -1,0 +1,150 @@
+"""tcgen05 convolution kernels (MOG_PREC_BF16X3 / MOG_PREC_BF16) against torch CPU fp32.
+Tolerances: the 3-pass bf16 split keeps ~16 mantissa bits per product (a_hi*w_hi + a_lo*w_hi +
+a_hi*w_lo, fp32 accumulate) -> rel-L2 <= 5e-5 per conv; single-pass bf16 -> <= 1e-2.
+Run on the B200 box: -m gpu."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_util as gu
+from mog_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16x3": 5e-5, "bf16": 1e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+TC_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, up2x, bias, act
+    (2, 16, 16, 96, 192, 3, 1, 1, False, False, 0),   # ResBlock conv C->2C   (K=864: 13.5 k-chunks, tap-straddling chunks)
+    (2, 16, 16, 96, 96, 3, 1, 1, True, False, 0),     # upBlock, fused nearest x2 (M = 2*32*32 = 16 tiles)
+    (3, 8, 8, 16, 32, 3, 1, 1, False, False, 0),      # small channels, BN=32, K=144 (tail chunk zero-filled)
+    (2, 16, 16, 96, 192, 4, 2, 1, False, False, 0),   # downBlock 4x4/s2: dgrad in 4 stride phases
+    (2, 8, 8, 384, 384, 4, 2, 1, False, False, 2),    # two N tiles of 192, LeakyReLU epilogue, M=32 rows (partial tile)
+    (3, 16, 16, 88, 40, 4, 1, 1, False, False, 0),    # 16 -> 15 (D_NET64.local-like, Cin%8==0), Cout=40 -> BN=48
+    (2, 16, 16, 104, 56, 3, 2, 1, False, False, 2),   # 3x3/s2 (bbox_net-like): phases with 1,2,2,4 taps
+    (4, 4, 4, 64, 8, 4, 4, 0, False, True, 5),        # 4x4/s4 head + bias + sigmoid, Cout=8 -> BN=16
+    (2, 32, 32, 48, 3, 3, 1, 1, False, False, 4),     # GET_IMAGE_G: Cout=3 (fwd on tensor cores, dgrad falls back: Cs=3)
+    (6, 1, 1, 248, 512, 1, 1, 0, False, False, 0),    # Linear 248 -> 512, M=6 rows
+    (2, 6, 1, 32, 8, 1, 1, 0, False, False, 0),       # conv_context 1x1
+    (1, 4, 4, 768, 1536, 4, 2, 1, False, False, 0),   # D_NET256 deep layer: K=12288, 6 N tiles of 256, M=4
+    (2, 4, 4, 1024, 768, 3, 1, 1, False, False, 0),   # COND_DNET.jointConv
+    (1, 40, 40, 8, 8, 3, 1, 1, True, False, 0),       # up2x, Cin=8: every chunk is its own tap
+]
+
+
+def _torch_conv(x, w, b, stride, pad, up2x, act):
+    if up2x:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    y = F.conv2d(x, w, b, stride, pad)
+    if act == 2:
+        y = F.leaky_relu(y, 0.2)
+    elif act == 4:
+        y = torch.tanh(y)
+    elif act == 5:
+        y = torch.sigmoid(y)
+    return y
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(str(int(v)) for v in c))
+def test_conv_tc(case, prec):
+    from mog_b200 import ops
+    from mog_b200._lib import PREC_NAMES
+    N, H, W, Ci, Co, k, s, p, up, has_b, act = case
+    x = rnd(N, Ci, H, W, seed=1).requires_grad_(True)
+    w = rnd(Co, Ci, k, k, seed=2, scale=1.0 / np.sqrt(Ci * k * k)).requires_grad_(True)
+    b = rnd(Co, seed=3, scale=0.1).requires_grad_(True) if has_b else None
+    y_ref = _torch_conv(x, w, b, s, p, up, act)
+    g = rnd(*y_ref.shape, seed=4)
+    y_ref.backward(g)
+    xd = x.detach().cuda().permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    wd = w.detach().cuda().requires_grad_(True)
+    bd = b.detach().cuda().requires_grad_(True) if has_b else None
+    y = ops.conv2d(xd, wd, bd, s, p, up, act, precision=PREC_NAMES[prec])
+    torch.cuda.synchronize()
+    tol = TOL[prec]
+    assert rel(y.permute(0, 3, 1, 2), y_ref) < tol, "fwd"
+    if prec == "bf16" and act in (2,):
+        tol = 6e-2  # LeakyReLU' flips where the bf16 pre-activation changes sign near zero
+    y.backward(g.cuda().permute(0, 2, 3, 1).contiguous())
+    torch.cuda.synchronize()
+    assert rel(xd.grad.permute(0, 3, 1, 2), x.grad) < tol, "dgrad"
+    assert rel(wd.grad, w.grad) < tol, "wgrad"
+    if has_b:
+        assert rel(bd.grad, b.grad) < 1e-5
+
+
+def test_wgrad_many_splits():
+    """Reduction over 2*128*128 pixels split across many CTAs, deterministic two-stage reduce."""
+    from mog_b200 import ops
+    from mog_b200._lib import PREC_NAMES
+    x = rnd(2, 16, 128, 128, seed=1).requires_grad_(True)
+    w = rnd(24, 16, 3, 3, seed=2, scale=0.1).requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, 1, 1)
+    g = rnd(*y_ref.shape, seed=3)
+    y_ref.backward(g)
+    outs = []
+    for _ in range(2):
+        xd = x.detach().cuda().permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+        wd = w.detach().cuda().requires_grad_(True)
+        y = ops.conv2d(xd, wd, None, 1, 1, precision=PREC_NAMES["bf16x3"])
+        y.backward(g.cuda().permute(0, 2, 3, 1).contiguous())
+        outs.append(wd.grad.clone())
+    assert rel(outs[0], w.grad) < 5e-5
+    assert torch.equal(outs[0], outs[1]), "wgrad must be run-to-run deterministic"
+
+
+def test_attngan_step_bf16x3_vs_reference_golden():
+    """The whole G/D step with every eligible conv on the tensor cores (3-pass split) against the
+    reference-generated golden vectors: images <= 2e-4, gradients <= 3e-3 rel-L2 (north star: 1e-3
+    on outputs)."""
+    from mog_b200 import ops
+    from mog_b200.attngan.miscc import losses as L
+    import test_gpu_attngan as T
+    G, meta = gu.load("attngan_tiny_step")
+    G2, _ = gu.load("attngan_tiny_gd")
+    c, seed = meta["cfg"], meta["seed"]
+    ops.set_precision("bf16x3")
+    try:
+        netG, netsD = T._build(c, seed)
+        b = T._dev(synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed))
+        eps = gu.full(G, "G/eps").cuda()
+        B = c["B"]
+        real, fake = torch.ones(B, device="cuda"), torch.zeros(B, device="cuda")
+        tm, tmi, oh = b["transf_matrices"], b["transf_matrices_inv"], b["label_one_hot"]
+        imgs, atts, mu, logvar = netG(b["noise"], b["sent_emb"], b["words_embs"], b["mask"], tmi, oh, eps=eps)
+        for i in range(3):
+            gu.check(imgs[i], G["G/fake%d" % i], 2e-4, "fake%d" % i)
+        for i, netD in enumerate(netsD):
+            netD.zero_grad()
+            kw = dict(local_labels=oh, transf_matrices=tm, transf_matrices_inv=tmi) if i == 0 else {}
+            errD = L.discriminator_loss(netD, b["imgs"][i], imgs[i], b["sent_emb"], real, fake, [0], **kw)
+            errD.backward()
+            gu.check(errD, G["D%d/errD" % i], 2e-4, "errD%d" % i)
+            for k, p in netD.named_parameters():
+                gu.check(p.grad, G["D%d/grad/%s" % (i, k)], 3e-3, "D%d grad %s" % (i, k))
+        for d in netsD:
+            for p in d.parameters():
+                p.requires_grad_(False)
+        netG.zero_grad()
+        errG, _ = L.generator_loss(netsD, None, imgs, real, b["words_embs"], b["sent_emb"], None, b["cap_lens"],
+                                   b["class_ids"], [0], local_labels=oh, transf_matrices=tm, transf_matrices_inv=tmi)
+        kl = L.KL_loss(mu, logvar)
+        gu.check(errG, G2["G/errG_adv"], 2e-4, "errG")
+        (errG + kl).backward()
+        for k, p in netG.named_parameters():
+            gu.check(p.grad, G2["G/grad/%s" % k], 3e-3, "G grad %s" % k)
+    finally:
+        ops.set_precision("fp32")
