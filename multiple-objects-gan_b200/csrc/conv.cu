@@ -86,6 +86,24 @@ static size_t tc_bytes(int ntaps, int Cs, int Cd, int passes) { return tc_packed
 
 static bool tc_wgrad(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_wgrad_eligible(*d); }
 
+// dgrad workspace = [hi-res gradient of the fused upsample][split-K partials of the largest phase]
+static size_t dgrad_up_bytes(const MogConvDesc* d) {
+  size_t b = d->up2x ? (size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cin * sizeof(float) : 0;
+  return (b + 255) / 256 * 256;
+}
+static size_t dgrad_split_bytes(const MogConvDesc* d) {
+  if (!tc_dgrad(d)) return 0;
+  size_t mx = 0;
+  for (int ph = 0; ph < d->stride; ++ph)
+    for (int pw = 0; pw < d->stride; ++pw) {
+      IGemmParams p;
+      if (!dgrad_problem(d, ph, pw, &p)) continue;
+      size_t b = tc_igemm_workspace_bytes(p.M, p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+      if (b > mx) mx = b;
+    }
+  return mx;
+}
+
 // ---- public API ---------------------------------------------------------------------------------
 extern "C" int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
   int rc = validate(d, "mog_conv_out_hw");
@@ -151,7 +169,11 @@ extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   if (validate(d, "mog_conv_workspace_bytes")) return 0;
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
-  if (which == 1) return d->up2x ? (size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cin * sizeof(float) : 0;
+  if (which == 0) {
+    if (!tc_fwd(d)) return 0;
+    return tc_igemm_workspace_bytes((long long)d->N * Ho * Wo, d->KH * d->KW, d->Cin, d->Cout, passes_of(d));
+  }
+  if (which == 1) return dgrad_up_bytes(d) + dgrad_split_bytes(d);
   if (which == 2) return tc_wgrad(d) ? tc_wgrad_workspace_bytes(*d, Ho, Wo) : wgrad_ffma_workspace_bytes(*d, Ho, Wo);
   return 0;
 }
@@ -161,10 +183,9 @@ extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* 
   int rc = validate(d, "mog_conv2d_fwd");
   if (rc) return rc;
   MOG_REQUIRE(x && w && y, "mog_conv2d_fwd: null tensor");
-  (void)workspace; (void)ws_bytes;
   IGemmParams p = fwd_problem(d);
   p.src = x; p.bias = bias; p.dst = y;
-  if (tc_fwd(d)) return launch_igemm_tc(p, w, passes_of(d), as_stream(stream));
+  if (tc_fwd(d)) return launch_igemm_tc(p, w, passes_of(d), workspace, ws_bytes, as_stream(stream));
   p.wmat = static_cast<const float*>(w);
   return launch_igemm_ffma(p, as_stream(stream));
 }
@@ -175,11 +196,11 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
   if (rc) return rc;
   MOG_REQUIRE(dy && wt && dx, "mog_conv2d_dgrad: null tensor");
   float* target = dx;
-  if (d->up2x) {
-    size_t need = mog_conv_workspace_bytes(d, 1);
-    if (!workspace || ws_bytes < need) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_dgrad: workspace %zu < %zu", ws_bytes, need);
-    target = static_cast<float*>(workspace);
-  }
+  const size_t need = mog_conv_workspace_bytes(d, 1);
+  if (need && (!workspace || ws_bytes < need)) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_dgrad: workspace %zu < %zu", ws_bytes, need);
+  if (d->up2x) target = static_cast<float*>(workspace);
+  unsigned char* split_ws = workspace ? static_cast<unsigned char*>(workspace) + dgrad_up_bytes(d) : nullptr;
+  const size_t split_bytes = need - dgrad_up_bytes(d);
   cudaStream_t st = as_stream(stream);
   const bool use_tc = tc_dgrad(d);
   const unsigned char* wp = static_cast<const unsigned char*>(wt);
@@ -189,7 +210,7 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
       if (!dgrad_problem(d, ph, pw, &p)) continue;
       p.src = dy; p.bias = nullptr; p.dst = target;
       if (use_tc) {
-        rc = launch_igemm_tc(p, wp, passes_of(d), st);
+        rc = launch_igemm_tc(p, wp, passes_of(d), split_ws, split_bytes, st);
         wp += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
       } else {
         p.wmat = static_cast<const float*>(wt);

@@ -41,7 +41,9 @@ int tc_bn_for(int Cd);
 int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
             const int* taps, int passes, cudaStream_t st);
 size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes);
-int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, cudaStream_t st);
+int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* workspace, size_t ws_bytes,
+                    cudaStream_t st);
+size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int passes);
 bool tc_wgrad_eligible(const MogConvDesc& d);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
 int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws, int passes,

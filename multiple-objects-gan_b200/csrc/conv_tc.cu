@@ -3,21 +3,25 @@
 //   D[M x N] = A[M x K] * B[K x N]      M = output pixels (gathered rows), N = output channels,
 //                                        K = taps x input channels
 //
-// * A is never materialised: producer warps gather the fp32 NHWC pixels of each (tap, channel
+// * A is never materialised: 8 producer warps gather the fp32 NHWC pixels of each (tap, channel
 //   chunk), split them on the fly into bf16 hi (+ lo for the 3-pass mode) and store them into
 //   shared memory in the canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte atoms).
 //   Nearest-2x upsampling, stride, padding and the per-phase tap subsets of the data gradient
 //   are all just index arithmetic of the gather (IGemmParams).
 // * B (weights) is pre-packed once per optimiser step into bf16 hi/lo planes [N][K] (K-major),
-//   copied by the producers into the same swizzled layout.
+//   copied by the producers into the same swizzled layout (all loads of a stage issued before
+//   the first store, so a stage costs one memory round trip).
 // * One elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16 per instruction, fp32
 //   accumulator in TMEM).  MOG_PREC_BF16X3 issues three MMAs per k-step
 //   (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo) into the same accumulator: fp32-equivalent products
-//   (~2^-16 relative) at one third of the bf16 rate; MOG_PREC_BF16 issues only the first.
-// * mbarrier pipeline: full[s] (128 producer arrivals) / empty[s] (tcgen05.commit) over `stages`
+//   at one third of the bf16 rate; MOG_PREC_BF16 issues only the first.
+// * mbarrier pipeline: full[s] (256 producer arrivals) / empty[s] (tcgen05.commit) over `stages`
 //   shared-memory stages; accum barrier (tcgen05.commit) hands the TMEM tile to the epilogue.
-// * Epilogue: the 4 producer warps read their TMEM lane quarter with tcgen05.ld (32x32b.x16),
-//   add bias / apply the activation and store fp32 NHWC rows.
+// * Split-K (grid.z) for problems whose M x N tiling cannot fill 148 SMs (the deep discriminator
+//   layers: M = 512, K up to 27648): fp32 partial tiles go to a workspace and a deterministic
+//   reduce kernel applies bias/activation and scatters to the NHWC destination.
+// * Epilogue: the 8 producer warps read TMEM with tcgen05.ld (32x32b.x16; warp w and w+4 share a
+//   lane quarter and split the columns), add bias / apply the activation, store fp32 NHWC rows.
 //
 // The weight gradient (reduction over pixels, both operands MN-major) is in conv_tc_wgrad.cu.
 #include <cuda_bf16.h>
@@ -28,15 +32,21 @@
 namespace mog {
 namespace tc {
 
+constexpr int CPROD = 256;             // producer threads (8 warps)
+constexpr int CTHREADS = CPROD + 32;   // + MMA warp (warp 8)
+
 struct TcParams {
   IGemmParams g;
   const __nv_bfloat16* Bhi;  // [Npad][Kpad]
   const __nv_bfloat16* Blo;  // [Npad][Kpad] (3-pass mode) or nullptr
+  float* partial;            // split-K workspace [splits][M][Cd] or nullptr
   int Kpad;
   int BN;
   int passes;
   int stages;
   int tmem_cols;
+  int splits;      // grid.z
+  int kc_per_split;
 };
 
 __device__ __forceinline__ float epi_act(float v, int act) {
@@ -47,7 +57,7 @@ __device__ __forceinline__ float epi_act(float v, int act) {
   return v;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned base (SWIZZLE_128B atoms)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -63,12 +73,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
   uint64_t* accum = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
 
-  if (warp == 4) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-  }
+  if (warp == 8) tmem_alloc(tmem_slot, p.tmem_cols);
   if (t == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], NPROD);
+      mbar_init(&full[s], CPROD);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum, 1);
@@ -81,18 +89,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
 
   const long long m0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * p.BN;
-  const int nk = p.Kpad / BK;
+  const int nk_total = p.Kpad / BK;
+  const int kc_begin = blockIdx.z * p.kc_per_split;
+  int kc_end = kc_begin + p.kc_per_split;
+  if (kc_end > nk_total) kc_end = nk_total;
+  const int nk = kc_end - kc_begin;   // >= 1 by construction
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== producers: gather + split + swizzled store ======================
-    const int r = t;  // this thread's tile row
+    const int r = t & 127;   // tile row
+    const int half = t >> 7; // which 4 of the 8 channel chunks of a k-chunk
     const long long m = m0 + r;
     const bool row_ok = m < g.M;
-    int rn = 0, h0 = 0, w0 = 0;
+    int rn = 0, h0 = 0, w0 = 0, rh = 0, rw = 0;
     if (row_ok) {
-      int rw = (int)(m % g.Wr);
+      rw = (int)(m % g.Wr);
       long long q = m / g.Wr;
-      int rh = (int)(q % g.Hr);
+      rh = (int)(q % g.Hr);
       rn = (int)(q / g.Hr);
       h0 = rh * g.rs;
       w0 = rw * g.rs;
@@ -101,20 +114,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const int rx = r & 7;
     // running decode of k -> (tap, channel); chunks of 8 channels never straddle a tap (Cs % 8 == 0)
-    int c = 0, th = 0, tw = 0;
-    for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc % p.stages;
-      const uint32_t ph = (uint32_t)((kc / p.stages) & 1);
+    int c, th, tw;
+    {
+      const long long k0 = (long long)kc_begin * BK + half * 32;
+      int tap = (int)(k0 / g.Cs);
+      c = (int)(k0 - (long long)tap * g.Cs);
+      th = tap / g.ntw;
+      tw = tap - th * g.ntw;
+    }
+    const int nB = p.BN * 8;   // 16-byte chunks of one B plane per stage
+    for (int it = 0; it < nk; ++it) {
+      const int kc = kc_begin + it;
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)((it / p.stages) & 1);
       mbar_wait(&empty[s], ph ^ 1u);
       unsigned char* st = smem + (size_t)s * stage_bytes;
       unsigned char* a_hi = st;
       unsigned char* a_lo = st + a_plane;                 // valid only when nplanes == 2
       unsigned char* b_hi = st + nplanes * a_plane;
       unsigned char* b_lo = b_hi + b_plane;
-      // ---- A: 8 chunks of 8 channels for this row
-      float4 v[8][2];
+      // ---- issue all global loads of this stage first: A (4 chunks of 8 fp32) ...
+      float4 v[4][2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         v[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
         v[j][1] = v[j][0];
         if (row_ok && th < g.nth) {
@@ -132,8 +154,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
           if (++tw == g.ntw) { tw = 0; ++th; }
         }
       }
+      // skip the other half's 4 chunks
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
+        c += 8;
+        if (c >= g.Cs) {
+          c = 0;
+          if (++tw == g.ntw) { tw = 0; ++th; }
+        }
+      }
+      // ... and B (bf16 weights): up to 8 chunks per thread per plane
+      const size_t kbase = (size_t)kc * BK;
+      uint4 bh[8], bl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = t + u * CPROD;
+        if (i < nB) {
+          const int row = i >> 3, ch = i & 7;
+          const size_t goff = (size_t)(n0 + row) * p.Kpad + kbase + ch * 8;
+          bh[u] = __ldg(reinterpret_cast<const uint4*>(p.Bhi + goff));
+          if (nplanes == 2) bl[u] = __ldg(reinterpret_cast<const uint4*>(p.Blo + goff));
+        }
+      }
+      // ---- convert + store A
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         const float f[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -146,18 +191,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
             lo[e] = *reinterpret_cast<uint32_t*>(&l2);
           }
         }
-        const uint32_t off = row_off + (uint32_t)((j ^ rx) << 4);
+        const uint32_t off = row_off + (uint32_t)(((half * 4 + j) ^ rx) << 4);
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (nplanes == 2) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      // ---- B: BN rows x 8 chunks per plane, already bf16
-      const size_t kbase = (size_t)kc * BK;
-      for (int i = t; i < p.BN * 8; i += NPROD) {
-        const int row = i >> 3, ch = i & 7;
-        const size_t goff = (size_t)(n0 + row) * p.Kpad + kbase + ch * 8;
-        const uint32_t soff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
-        *reinterpret_cast<uint4*>(b_hi + soff) = __ldg(reinterpret_cast<const uint4*>(p.Bhi + goff));
-        if (nplanes == 2) *reinterpret_cast<uint4*>(b_lo + soff) = __ldg(reinterpret_cast<const uint4*>(p.Blo + goff));
+      // ---- store B
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = t + u * CPROD;
+        if (i < nB) {
+          const int row = i >> 3, ch = i & 7;
+          const uint32_t soff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(b_hi + soff) = bh[u];
+          if (nplanes == 2) *reinterpret_cast<uint4*>(b_lo + soff) = bl[u];
+        }
       }
       fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&full[s]);
@@ -166,24 +213,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
     // ===================== epilogue: TMEM -> registers -> global ===========================
     mbar_wait(accum, 0);
     tcgen05_fence_after();
+    const int q4 = warp & 3;               // TMEM lane quarter of this warp
+    const int er = q4 * 32 + lane;         // tile row handled in the epilogue
+    const long long em = m0 + er;
+    const bool e_ok = em < g.M;
     float* dptr = nullptr;
-    if (row_ok) {
-      int rw = (int)(m % g.Wr);
-      long long q = m / g.Wr;
-      int rh = (int)(q % g.Hr);
-      size_t pix = ((size_t)rn * g.Hd + (rh * g.dsh + g.doh)) * g.Wd + (rw * g.dsw + g.dow);
-      dptr = g.dst + pix * g.Cd + n0;
+    if (e_ok) {
+      if (p.partial) {
+        dptr = p.partial + ((size_t)blockIdx.z * g.M + em) * g.Cd + n0;
+      } else {
+        int ew = (int)(em % g.Wr);
+        long long q = em / g.Wr;
+        int eh = (int)(q % g.Hr);
+        int en = (int)(q / g.Hr);
+        size_t pix = ((size_t)en * g.Hd + (eh * g.dsh + g.doh)) * g.Wd + (ew * g.dsw + g.dow);
+        dptr = g.dst + pix * g.Cd + n0;
+      }
     }
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int ncol16 = p.BN / 16;
+    const int cbeg = (warp >> 2) ? (ncol16 + 1) / 2 : 0;     // warps 4-7 take the upper column half
+    const int cend = (warp >> 2) ? ncol16 : (ncol16 + 1) / 2;
+    const bool raw = p.partial != nullptr;
+    for (int cb = cbeg; cb < cend; ++cb) {
+      const int c0 = cb * 16;
       uint32_t acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
-      if (row_ok) {
+      if (e_ok) {
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float b = (g.bias && n0 + c0 + j < g.Cd) ? __ldg(g.bias + n0 + c0 + j) : 0.f;
-          o[j] = epi_act(__uint_as_float(acc[j]) + b, g.act);
+          float v0 = __uint_as_float(acc[j]);
+          if (!raw) {
+            float b = (g.bias && n0 + c0 + j < g.Cd) ? __ldg(g.bias + n0 + c0 + j) : 0.f;
+            v0 = epi_act(v0 + b, g.act);
+          }
+          o[j] = v0;
         }
         if (((g.Cd & 3) == 0) && n0 + c0 + 15 < g.Cd) {
 #pragma unroll
@@ -197,11 +262,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
       }
     }
   } else {
-    // ===================== MMA issuer (warp 4) ==============================================
+    // ===================== MMA issuer (warp 8) ==============================================
     const uint32_t idesc = make_idesc_bf16(BM, p.BN);
-    for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc % p.stages;
-      const uint32_t ph = (uint32_t)((kc / p.stages) & 1);
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)((it / p.stages) & 1);
       mbar_wait(&full[s], ph);
       tcgen05_fence_after();
       if (lane == 0) {
@@ -215,11 +280,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t da = make_desc_sw128(ab + k16 * 32);
             const uint64_t db = make_desc_sw128(bb + k16 * 32);
-            umma_bf16(tmem_base, da, db, idesc, (kc | pass | k16) != 0);
+            umma_bf16(tmem_base, da, db, idesc, (it | pass | k16) != 0);
           }
         }
         umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
-        if (kc == nk - 1) umma_commit(accum);
+        if (it == nk - 1) umma_commit(accum);
       }
       __syncwarp();
     }
@@ -227,7 +292,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const TcParams p) 
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// split-K reduce: dst[pix(m), n] = act(sum_z partial[z][m][n] + bias[n])
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, const IGemmParams g, int splits) {
+  const size_t total = (size_t)g.M * g.Cd;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % g.Cd);
+  const long long m = (long long)(idx / g.Cd);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + idx];
+  if (g.bias) s += __ldg(g.bias + n);
+  s = epi_act(s, g.act);
+  int rw = (int)(m % g.Wr);
+  long long q = m / g.Wr;
+  int rh = (int)(q % g.Hr);
+  int rn = (int)(q / g.Hr);
+  size_t pix = ((size_t)rn * g.Hd + (rh * g.dsh + g.doh)) * g.Wd + (rw * g.dsw + g.dow);
+  g.dst[pix * g.Cd + n] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,7 +363,7 @@ int tc_bn_for(int Cd) {
 bool tc_gather_eligible(int Cs, int Cd) { return (Cs % 8) == 0 && Cd >= 1; }
 
 // layout of the packed buffer of one gather-GEMM problem (K = ntaps * Cs, N = Cd)
-TcWeightLayout tc_weight_layout(int ntaps, int Cs, int Cd, int passes) {
+static TcWeightLayout tc_weight_layout(int ntaps, int Cs, int Cd, int passes) {
   TcWeightLayout L;
   L.BN = tc_bn_for(Cd);
   L.ntiles = ceil_div(Cd, L.BN);
@@ -312,7 +396,30 @@ int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, i
   return check_launch("pack_tc_kernel");
 }
 
-int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, cudaStream_t st) {
+// split-K factor for one gather-GEMM problem
+static int tc_splits(long long M, int ntiles, int nk) {
+  const long long ctas = ceil_div_ll(M, BM) * ntiles;
+  if (ctas >= 96 || nk < 8) return 1;
+  long long want = ceil_div_ll(2 * kNumSMs, ctas);
+  long long maxs = nk / 4;
+  long long s = want < maxs ? want : maxs;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+
+size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int passes) {
+  TcWeightLayout L = tc_weight_layout(ntaps, Cs, Cd, passes);
+  const int nk = L.Kpad / BK;
+  int splits = tc_splits(M, L.ntiles, nk);
+  if (splits <= 1) return 0;
+  const int per = ceil_div(nk, splits);
+  splits = ceil_div(nk, per);
+  return splits > 1 ? (size_t)splits * M * Cd * sizeof(float) : 0;
+}
+
+int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* workspace, size_t ws_bytes,
+                    cudaStream_t st) {
   TcWeightLayout L = tc_weight_layout(g.nth * g.ntw, g.Cs, g.Cd, passes);
   TcParams p;
   p.g = g;
@@ -321,6 +428,18 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, cudaSt
   p.Kpad = L.Kpad;
   p.BN = L.BN;
   p.passes = passes;
+  const int nk = L.Kpad / BK;
+  int splits = tc_splits(g.M, L.ntiles, nk);
+  int per = ceil_div(nk, splits);
+  splits = ceil_div(nk, per);
+  p.splits = splits;
+  p.kc_per_split = per;
+  p.partial = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * g.M * g.Cd * sizeof(float);
+    if (!workspace || ws_bytes < need) return fail(MOG_ERR_WORKSPACE, "conv (tcgen05 split-K): workspace %zu < %zu", ws_bytes, need);
+    p.partial = static_cast<float*>(workspace);
+  }
   const int stage_bytes = L.planes * (BM * 128 + L.BN * 128);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -336,9 +455,13 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, cudaSt
     if (e != cudaSuccess) return fail(MOG_ERR_CUDA, "conv_tc_kernel smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div_ll(g.M, BM), (unsigned)L.ntiles);
-  conv_tc_kernel<<<grid, NTHREADS, smem, st>>>(p);
-  return check_launch("conv_tc_kernel");
+  dim3 grid((unsigned)ceil_div_ll(g.M, BM), (unsigned)L.ntiles, (unsigned)splits);
+  conv_tc_kernel<<<grid, CTHREADS, smem, st>>>(p);
+  int rc = check_launch("conv_tc_kernel");
+  if (rc || splits == 1) return rc;
+  const size_t total = (size_t)g.M * g.Cd;
+  splitk_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(p.partial, g, splits);
+  return check_launch("splitk_reduce_kernel");
 }
 
 }  // namespace mog
