@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--impl", default="mog", choices=["mog", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
-    ap.add_argument("--precision", default=os.environ.get("MOG_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("MOG_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mog":
