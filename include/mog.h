@@ -75,21 +75,31 @@ size_t mog_packed_weight_bytes(const MogConvDesc* d, int which);
 int mog_pack_weight(const MogConvDesc* d, int which, const float* w_oihw, void* w_packed, void* stream);
 
 /* ---- convolution ----------------------------------------------------------------------- */
+/* Operand formats.  MOG_PREC_FP32: fp32 NHWC tensors.  tcgen05 precisions: the gathered operands
+ * (x for forward/wgrad, dy for dgrad/wgrad) are preferably passed as pre-split bf16 *planes*
+ * made by mog_split_planes -- [rows][C8] bf16 "hi" plane followed (BF16X3 only) by the "lo" plane,
+ * C8 = C rounded up to 8, pad channels zero -- so a tensor is split once and reused by every
+ * kernel that reads it; when the planes pointer is NULL the fp32 tensor is split on the fly
+ * (channel count must then be a multiple of 8). */
+size_t mog_planes_bytes(long long rows, int C, int precision);
+int mog_split_planes(const float* x, long long rows, int C, int precision, void* planes, void* stream);
+
 /* replaces: nn.Conv2d forward incl. a preceding nn.Upsample(2,'nearest') (model.py:41-55,
  * 587-609,626,664-677; GlobalAttention.py:25-28) and nn.Linear (H=W=KH=KW=1; model.py:324,
  * 365,371).  y: [N,Ho,Wo,Cout]; bias may be NULL. */
 int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo);
 size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which /*0 fwd, 1 dgrad, 2 wgrad*/);
-int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* w_packed_fwd, const float* bias,
-                   float* y, void* workspace, size_t ws_bytes, void* stream);
+int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* x_planes, const void* w_packed_fwd,
+                   const float* bias, float* y, void* workspace, size_t ws_bytes, void* stream);
 /* replaces: autograd of the above w.r.t. the input.  dy: [N,Ho,Wo,Cout] (already multiplied by
  * the epilogue derivative, see mog_act_bwd), dx: [N,H,W,Cin]. */
-int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* w_packed_dgrad, float* dx,
-                     void* workspace, size_t ws_bytes, void* stream);
+int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* dy_planes, const void* w_packed_dgrad,
+                     float* dx, void* workspace, size_t ws_bytes, void* stream);
 /* replaces: autograd w.r.t. the weight; writes dw in OIHW (state_dict layout), deterministic
- * split reduction through the workspace.  dbias (may be NULL): [Cout]. */
-int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const float* dy, float* dw_oihw, float* dbias,
-                     void* workspace, size_t ws_bytes, void* stream);
+ * split reduction through the workspace.  dbias (may be NULL; needs the fp32 dy): [Cout]. */
+int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const void* x_planes, const float* dy,
+                     const void* dy_planes, float* dw_oihw, float* dbias, void* workspace, size_t ws_bytes,
+                     void* stream);
 
 /* ---- BatchNorm (train mode) + activation ------------------------------------------------ */
 /* x is [S*M][C] (S segments of M rows; the object pathway calls the same BN once per object

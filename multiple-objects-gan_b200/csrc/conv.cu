@@ -1,8 +1,10 @@
 // conv.cu -- C-ABI entry points of the convolution family.  Builds the gather-GEMM problems
 // (forward: one; data gradient: one per stride phase) and dispatches on MogConvDesc.precision:
-// MOG_PREC_FP32 -> CUDA-core kernels (conv_ffma.cu); MOG_PREC_BF16X3 / MOG_PREC_BF16 -> tcgen05
-// kernels (conv_tc.cu, conv_tc_wgrad.cu) whenever the shape is eligible (gathered channel count
-// a multiple of 8), else the exact CUDA-core kernel.
+//   MOG_PREC_FP32              -> CUDA-core kernels (conv_ffma.cu), fp32 operands
+//   MOG_PREC_BF16X3 / _BF16    -> tcgen05 kernels (conv_tc.cu, conv_tc_wgrad.cu), always.  The
+//       gathered operands are either pre-split bf16 planes (mog_split_planes; channel pitch rounded
+//       up to 8, so every channel count is accepted) or fp32 tensors split on the fly (only when
+//       the channel count is a multiple of 8).
 #include "conv_common.cuh"
 
 using namespace mog;
@@ -32,8 +34,8 @@ static void out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
 }
 
 static int passes_of(const MogConvDesc* d) { return d->precision == MOG_PREC_BF16X3 ? 3 : 1; }
-static bool tc_fwd(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_gather_eligible(d->Cin, d->Cout); }
-static bool tc_dgrad(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_gather_eligible(d->Cout, d->Cin); }
+static bool use_tc(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32; }
+static int p8(int c) { return ceil_div(c, 8) * 8; }
 
 // ---- problem builders -----------------------------------------------------------------------
 static IGemmParams fwd_problem(const MogConvDesc* d) {
@@ -82,9 +84,8 @@ static bool dgrad_problem(const MogConvDesc* d, int ph, int pw, IGemmParams* out
   return true;
 }
 
-static size_t tc_bytes(int ntaps, int Cs, int Cd, int passes) { return tc_packed_bytes(ntaps, Cs, Cd, passes); }
-
-static bool tc_wgrad(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32 && tc_wgrad_eligible(*d); }
+// tcgen05 path: k runs over (tap, channel) with the channel pitch rounded up to 8
+static size_t tc_bytes(int ntaps, int Cs, int Cd, int passes) { return tc_packed_bytes(ntaps, p8(Cs), Cd, passes); }
 
 // dgrad workspace = [hi-res gradient of the fused upsample][split-K partials of the largest phase]
 static size_t dgrad_up_bytes(const MogConvDesc* d) {
@@ -92,16 +93,35 @@ static size_t dgrad_up_bytes(const MogConvDesc* d) {
   return (b + 255) / 256 * 256;
 }
 static size_t dgrad_split_bytes(const MogConvDesc* d) {
-  if (!tc_dgrad(d)) return 0;
+  if (!use_tc(d)) return 0;
   size_t mx = 0;
   for (int ph = 0; ph < d->stride; ++ph)
     for (int pw = 0; pw < d->stride; ++pw) {
       IGemmParams p;
       if (!dgrad_problem(d, ph, pw, &p)) continue;
-      size_t b = tc_igemm_workspace_bytes(p.M, p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+      size_t b = tc_igemm_workspace_bytes(p.M, p.nth * p.ntw, p8(d->Cout), d->Cin, passes_of(d));
       if (b > mx) mx = b;
     }
   return mx;
+}
+
+// attach the gathered operand (planes or fp32) of a tcgen05 problem; Cs becomes the channel pitch
+static int attach_source(IGemmParams* p, const float* src_f32, const void* planes, long long pixels, const char* who) {
+  const int CsReal = p->Cs;
+  if (planes) {
+    p->Cs = p8(CsReal);
+    p->src = nullptr;
+    p->src_planes = planes;
+    p->src_plane_elems = (size_t)pixels * p->Cs;
+  } else {
+    if (CsReal % 8) return fail(MOG_ERR_UNSUPPORTED, "%s: %d channels need pre-split planes (mog_split_planes) in tcgen05 precision", who, CsReal);
+    if (!src_f32) return fail(MOG_ERR_BAD_ARG, "%s: neither an fp32 tensor nor planes given", who);
+    p->src = src_f32;
+    p->src_planes = nullptr;
+    p->src_plane_elems = 0;
+  }
+  p->K = p->nth * p->ntw * p->Cs;
+  return MOG_OK;
 }
 
 // ---- public API ---------------------------------------------------------------------------------
@@ -115,12 +135,23 @@ extern "C" int mog_conv_out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
   return MOG_OK;
 }
 
+extern "C" size_t mog_planes_bytes(long long rows, int C, int precision) {
+  if (rows <= 0 || C <= 0 || precision == MOG_PREC_FP32) return 0;
+  return (size_t)rows * p8(C) * 2 * (precision == MOG_PREC_BF16X3 ? 2 : 1);
+}
+
+extern "C" int mog_split_planes(const float* x, long long rows, int C, int precision, void* planes, void* stream) {
+  MOG_REQUIRE(x && planes && rows > 0 && C > 0, "mog_split_planes: bad argument");
+  MOG_REQUIRE(precision == MOG_PREC_BF16X3 || precision == MOG_PREC_BF16, "mog_split_planes: precision must be a tcgen05 mode");
+  return launch_split_planes(x, rows, C, p8(C), planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream));
+}
+
 extern "C" size_t mog_packed_weight_bytes(const MogConvDesc* d, int which) {
   if (validate(d, "mog_packed_weight_bytes")) return 0;
   const size_t dense = (size_t)d->KH * d->KW * d->Cin * d->Cout * sizeof(float);
-  if (which == 0) return tc_fwd(d) ? tc_bytes(d->KH * d->KW, d->Cin, d->Cout, passes_of(d)) : dense;
+  if (!use_tc(d)) return dense;
+  if (which == 0) return tc_bytes(d->KH * d->KW, d->Cin, d->Cout, passes_of(d));
   if (which == 1) {
-    if (!tc_dgrad(d)) return dense;
     size_t tot = 0;
     for (int ph = 0; ph < d->stride; ++ph)
       for (int pw = 0; pw < d->stride; ++pw) {
@@ -140,18 +171,17 @@ extern "C" int mog_pack_weight(const MogConvDesc* d, int which, const float* w, 
   cudaStream_t st = as_stream(stream);
   const size_t total = (size_t)d->Cout * d->Cin * d->KH * d->KW;
   const unsigned blocks = (unsigned)ceil_div_ll((long long)total, 256);
-  if (which == 0) {
-    if (!tc_fwd(d)) {
+  if (!use_tc(d)) {
+    if (which == 0)
       pack_fwd_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
-      return check_launch("pack_fwd_kernel");
-    }
+    else
+      pack_dgrad_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
+    return check_launch("pack_kernel");
+  }
+  if (which == 0) {
     int taps[64];
     for (int i = 0; i < d->KH * d->KW; ++i) taps[i] = i;
     return tc_pack(w, out, d->Cout, d->Cin, d->KH, d->KW, 0, d->KH * d->KW, taps, passes_of(d), st);
-  }
-  if (!tc_dgrad(d)) {
-    pack_dgrad_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
-    return check_launch("pack_dgrad_kernel");
   }
   unsigned char* o = static_cast<unsigned char*>(out);
   for (int ph = 0; ph < d->stride; ++ph)
@@ -170,31 +200,39 @@ extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
   if (which == 0) {
-    if (!tc_fwd(d)) return 0;
-    return tc_igemm_workspace_bytes((long long)d->N * Ho * Wo, d->KH * d->KW, d->Cin, d->Cout, passes_of(d));
+    if (!use_tc(d)) return 0;
+    return tc_igemm_workspace_bytes((long long)d->N * Ho * Wo, d->KH * d->KW, p8(d->Cin), d->Cout, passes_of(d));
   }
   if (which == 1) return dgrad_up_bytes(d) + dgrad_split_bytes(d);
-  if (which == 2) return tc_wgrad(d) ? tc_wgrad_workspace_bytes(*d, Ho, Wo) : wgrad_ffma_workspace_bytes(*d, Ho, Wo);
+  if (which == 2) return use_tc(d) ? tc_wgrad_workspace_bytes(*d, Ho, Wo) : wgrad_ffma_workspace_bytes(*d, Ho, Wo);
   return 0;
 }
 
-extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* w, const float* bias, float* y,
-                              void* workspace, size_t ws_bytes, void* stream) {
+extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* x_planes, const void* w,
+                              const float* bias, float* y, void* workspace, size_t ws_bytes, void* stream) {
   int rc = validate(d, "mog_conv2d_fwd");
   if (rc) return rc;
-  MOG_REQUIRE(x && w && y, "mog_conv2d_fwd: null tensor");
+  MOG_REQUIRE((x || x_planes) && w && y, "mog_conv2d_fwd: null tensor");
   IGemmParams p = fwd_problem(d);
-  p.src = x; p.bias = bias; p.dst = y;
-  if (tc_fwd(d)) return launch_igemm_tc(p, w, passes_of(d), workspace, ws_bytes, as_stream(stream));
+  p.bias = bias; p.dst = y;
+  if (use_tc(d)) {
+    rc = attach_source(&p, x, x_planes, (long long)d->N * d->H * d->W, "mog_conv2d_fwd");
+    if (rc) return rc;
+    return launch_igemm_tc(p, w, passes_of(d), workspace, ws_bytes, as_stream(stream));
+  }
+  MOG_REQUIRE(x, "mog_conv2d_fwd: fp32 precision needs the fp32 input");
+  p.src = x;
   p.wmat = static_cast<const float*>(w);
   return launch_igemm_ffma(p, as_stream(stream));
 }
 
-extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* wt, float* dx, void* workspace,
-                                size_t ws_bytes, void* stream) {
+extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* dy_planes, const void* wt,
+                                float* dx, void* workspace, size_t ws_bytes, void* stream) {
   int rc = validate(d, "mog_conv2d_dgrad");
   if (rc) return rc;
-  MOG_REQUIRE(dy && wt && dx, "mog_conv2d_dgrad: null tensor");
+  MOG_REQUIRE((dy || dy_planes) && wt && dx, "mog_conv2d_dgrad: null tensor");
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
   float* target = dx;
   const size_t need = mog_conv_workspace_bytes(d, 1);
   if (need && (!workspace || ws_bytes < need)) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_dgrad: workspace %zu < %zu", ws_bytes, need);
@@ -202,17 +240,20 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
   unsigned char* split_ws = workspace ? static_cast<unsigned char*>(workspace) + dgrad_up_bytes(d) : nullptr;
   const size_t split_bytes = need - dgrad_up_bytes(d);
   cudaStream_t st = as_stream(stream);
-  const bool use_tc = tc_dgrad(d);
   const unsigned char* wp = static_cast<const unsigned char*>(wt);
   for (int ph = 0; ph < d->stride; ++ph) {
     for (int pw = 0; pw < d->stride; ++pw) {
       IGemmParams p;
       if (!dgrad_problem(d, ph, pw, &p)) continue;
-      p.src = dy; p.bias = nullptr; p.dst = target;
-      if (use_tc) {
+      p.bias = nullptr; p.dst = target;
+      if (use_tc(d)) {
+        rc = attach_source(&p, dy, dy_planes, (long long)d->N * Ho * Wo, "mog_conv2d_dgrad");
+        if (rc) return rc;
         rc = launch_igemm_tc(p, wp, passes_of(d), split_ws, split_bytes, st);
         wp += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
       } else {
+        MOG_REQUIRE(dy, "mog_conv2d_dgrad: fp32 precision needs the fp32 gradient");
+        p.src = dy;
         p.wmat = static_cast<const float*>(wt);
         rc = launch_igemm_ffma(p, st);
       }
@@ -223,11 +264,13 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
   return MOG_OK;
 }
 
-extern "C" int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const float* dy, float* dw, float* dbias,
-                                void* workspace, size_t ws_bytes, void* stream) {
+extern "C" int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const void* x_planes, const float* dy,
+                                const void* dy_planes, float* dw, float* dbias, void* workspace, size_t ws_bytes,
+                                void* stream) {
   int rc = validate(d, "mog_conv2d_wgrad");
   if (rc) return rc;
-  MOG_REQUIRE(x && dy && dw, "mog_conv2d_wgrad: null tensor");
+  MOG_REQUIRE((x || x_planes) && (dy || dy_planes) && dw, "mog_conv2d_wgrad: null tensor");
+  MOG_REQUIRE(!dbias || dy, "mog_conv2d_wgrad: the bias gradient needs the fp32 dy");
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
   size_t need = mog_conv_workspace_bytes(d, 2);
@@ -235,12 +278,23 @@ extern "C" int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const floa
   cudaStream_t st = as_stream(stream);
   int splits = 1;
   float* ws = static_cast<float*>(workspace);
-  if (tc_wgrad(d))
-    rc = launch_wgrad_tc(*d, Ho, Wo, x, dy, ws, passes_of(d), &splits, st);
-  else
+  int CinP = d->Cin;
+  if (use_tc(d)) {
+    const bool planes = x_planes && dy_planes;
+    if (!planes) {
+      MOG_REQUIRE(x && dy, "mog_conv2d_wgrad: give both operands as planes or both as fp32 tensors");
+      if ((d->Cin % 8) || (d->Cout % 8))
+        return fail(MOG_ERR_UNSUPPORTED, "mog_conv2d_wgrad: %d/%d channels need pre-split planes in tcgen05 precision", d->Cin, d->Cout);
+    }
+    CinP = planes ? p8(d->Cin) : d->Cin;
+    rc = launch_wgrad_tc(*d, Ho, Wo, x, dy, planes ? x_planes : nullptr, (size_t)d->N * d->H * d->W * p8(d->Cin),
+                         planes ? dy_planes : nullptr, (size_t)d->N * Ho * Wo * p8(d->Cout), ws, passes_of(d), &splits, st);
+  } else {
+    MOG_REQUIRE(x && dy, "mog_conv2d_wgrad: fp32 precision needs fp32 tensors");
     rc = launch_wgrad_ffma_partial(*d, Ho, Wo, x, dy, ws, &splits, st);
+  }
   if (rc) return rc;
-  rc = launch_wgrad_reduce(ws, dw, splits, d->KH * d->KW * d->Cin, d->Cout, d->Cin, d->KH * d->KW, st);
+  rc = launch_wgrad_reduce(ws, dw, splits, d->KH * d->KW * CinP, d->Cout, d->Cin, CinP, d->KH * d->KW, st);
   if (rc) return rc;
   if (dbias) return launch_colsum(dy, dbias, (long long)d->N * Ho * Wo, d->Cout, st);
   return MOG_OK;

@@ -9,7 +9,9 @@ namespace mog {
 // in the logical (optionally 2x nearest-upsampled) source; destination pixel = (rh*dsh + doh, rw*dsw + dow).
 // The forward conv is one such problem; the data gradient is one per stride phase.
 struct IGemmParams {
-  const float* src;
+  const float* src;            // fp32 NHWC source (CUDA-core path, or tcgen05 path without planes)
+  const void* src_planes;      // tcgen05 path: bf16 hi plane [pixels][Cs] followed by the lo plane, or nullptr
+  size_t src_plane_elems;      // elements per plane
   const float* wmat;
   const float* bias;
   float* dst;
@@ -30,13 +32,13 @@ int launch_igemm_ffma(const IGemmParams& p, cudaStream_t st);
 int launch_wgrad_ffma_partial(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws,
                               int* splits_out, cudaStream_t st);
 size_t wgrad_ffma_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
-int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int KHW, cudaStream_t st);
+int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int CinP, int KHW,
+                        cudaStream_t st);
 int launch_colsum(const float* x, float* out, long long M, int C, cudaStream_t st);
 int launch_sumpool(const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st);
 
 // tcgen05 path (conv_tc.cu, conv_tc_wgrad.cu)
 namespace tc { struct TcWeightLayout; }
-bool tc_gather_eligible(int Cs, int Cd);
 int tc_bn_for(int Cd);
 int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
             const int* taps, int passes, cudaStream_t st);
@@ -44,9 +46,11 @@ size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes);
 int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* workspace, size_t ws_bytes,
                     cudaStream_t st);
 size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int passes);
-bool tc_wgrad_eligible(const MogConvDesc& d);
+bool tc_wgrad_eligible(const MogConvDesc& d, bool planes);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
-int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws, int passes,
+int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, const void* x_planes,
+                    size_t x_plane_elems, const void* dy_planes, size_t dy_plane_elems, float* ws, int passes,
                     int* splits_out, cudaStream_t st);
+int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st);
 
 }  // namespace mog

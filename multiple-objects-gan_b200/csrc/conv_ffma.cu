@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(NT, 2) wgrad_kernel(const WgradParams p) {
 
 // dw_oihw[co][ci][kh][kw] = sum_z ws[z][(kh*KW+kw)*Cin+ci][co]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int K,
-                                    int Cout, int Cin, int KHW) {
+                                    int Cout, int Cin, int CinP, int KHW) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)K * Cout;
   if (idx >= total) return;
@@ -356,8 +356,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   int kf = (int)(idx / Cout);
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + idx];
-  int tap = kf / Cin, ci = kf - tap * Cin;
-  dw[((size_t)co * Cin + ci) * KHW + tap] = s;
+  int tap = kf / CinP, ci = kf - tap * CinP;   // CinP: channel pitch of kf (Cin rounded up to 8 with planes)
+  if (ci < Cin) dw[((size_t)co * Cin + ci) * KHW + tap] = s;
 }
 
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int C) {
@@ -454,9 +454,10 @@ size_t wgrad_ffma_workspace_bytes(const MogConvDesc& d, int Ho, int Wo) {
   return (size_t)wgrad_splits(d, Ho, Wo) * d.KH * d.KW * d.Cin * d.Cout * sizeof(float);
 }
 
-int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int KHW, cudaStream_t st) {
+int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int CinP, int KHW,
+                        cudaStream_t st) {
   size_t total = (size_t)K * Cout;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(ws, dw, splits, K, Cout, Cin, KHW);
+  wgrad_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(ws, dw, splits, K, Cout, Cin, CinP, KHW);
   return check_launch("wgrad_reduce_kernel");
 }
 

@@ -37,6 +37,8 @@ constexpr int CTHREADS = CPROD + 32;   // + MMA warp (warp 8)
 
 struct TcParams {
   IGemmParams g;
+  const __nv_bfloat16* Xhi;  // gathered operand as pre-split bf16 planes [pixels][Cs] (PLANES kernel) or nullptr
+  const __nv_bfloat16* Xlo;
   const __nv_bfloat16* Bhi;  // [Npad][Kpad]
   const __nv_bfloat16* Blo;  // [Npad][Kpad] (3-pass mode) or nullptr
   float* partial;            // split-K workspace [splits][M][Cd] or nullptr
@@ -57,6 +59,7 @@ __device__ __forceinline__ float epi_act(float v, int act) {
   return v;
 }
 
+template <bool PLANES>
 __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned base (SWIZZLE_128B atoms)
@@ -123,6 +126,74 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
       tw = tap - th * g.ntw;
     }
     const int nB = p.BN * 8;   // 16-byte chunks of one B plane per stage
+    if (PLANES) {
+      // ---- pre-split bf16 planes: pure 16-byte async copies (cp.async, zero-fill for padding), no ALU work.
+      // Completion is signalled LAG stages late so several stages of copies stay in flight per thread.
+      const int LAG = p.stages >= 3 ? 2 : 1;
+      for (int it = 0; it < nk; ++it) {
+        const int kc = kc_begin + it;
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(&empty[s], ph ^ 1u);
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + a_plane;
+        const uint32_t b_hi = st + nplanes * a_plane, b_lo = b_hi + b_plane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool inb = false;
+          size_t off = 0;
+          if (row_ok && th < g.nth) {
+            const int sh = h0 + g.off_h[th], sw = w0 + g.off_w[tw];
+            if (sh >= 0 && sh < HL && sw >= 0 && sw < WL) {
+              inb = true;
+              off = (((size_t)rn * g.Hs + (sh >> g.up2x)) * g.Ws + (sw >> g.up2x)) * g.Cs + c;
+            }
+          }
+          const uint32_t soff = row_off + (uint32_t)(((half * 4 + j) ^ rx) << 4);
+          cp_async16(a_hi + soff, p.Xhi + off, inb ? 16u : 0u);
+          if (nplanes == 2) cp_async16(a_lo + soff, p.Xlo + off, inb ? 16u : 0u);
+          c += 8;
+          if (c >= g.Cs) {
+            c = 0;
+            if (++tw == g.ntw) { tw = 0; ++th; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // skip the other half's 4 chunks
+          c += 8;
+          if (c >= g.Cs) {
+            c = 0;
+            if (++tw == g.ntw) { tw = 0; ++th; }
+          }
+        }
+        const size_t kbase = (size_t)kc * BK;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = t + u * CPROD;
+          if (i < nB) {
+            const int row = i >> 3, ch = i & 7;
+            const size_t goff = (size_t)(n0 + row) * p.Kpad + kbase + ch * 8;
+            const uint32_t soff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
+            cp_async16(b_hi + soff, p.Bhi + goff, 16u);
+            if (nplanes == 2) cp_async16(b_lo + soff, p.Blo + goff, 16u);
+          }
+        }
+        cp_async_commit();
+        if (it >= LAG) {
+          if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(&full[(it - LAG) % p.stages]);
+        }
+      }
+      if (LAG == 2 && nk >= 2) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&full[(nk - 2) % p.stages]);
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&full[(nk - 1) % p.stages]);
+    } else {
     for (int it = 0; it < nk; ++it) {
       const int kc = kc_begin + it;
       const int s = it % p.stages;
@@ -208,6 +279,8 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
       }
       fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&full[s]);
+    }
+
     }
 
     // ===================== epilogue: TMEM -> registers -> global ===========================
@@ -325,7 +398,7 @@ struct PackArgs {
   int transpose;  // 0: n = co, c = ci (forward)    1: n = ci, c = co (data gradient)
   int ntaps;
   int taps[64];
-  int Nreal, Npad, Cs, K, Kpad;
+  int Nreal, Npad, Cs, CsReal, K, Kpad;   // Cs: channel pitch of k (multiple of 8), CsReal: channels that exist
 };
 
 __global__ void pack_tc_kernel(const PackArgs a) {
@@ -337,13 +410,47 @@ __global__ void pack_tc_kernel(const PackArgs a) {
   float v = 0.f;
   if (n < a.Nreal && k < a.K) {
     int tl = k / a.Cs, c = k - tl * a.Cs;
-    int tap = a.taps[tl];
-    int co = a.transpose ? c : n, ci = a.transpose ? n : c;
-    v = a.w[((size_t)co * a.Cin + ci) * a.KHW + tap];
+    if (c < a.CsReal) {
+      int tap = a.taps[tl];
+      int co = a.transpose ? c : n, ci = a.transpose ? n : c;
+      v = a.w[((size_t)co * a.Cin + ci) * a.KHW + tap];
+    }
   }
   __nv_bfloat16 h = __float2bfloat16_rn(v);
   a.hi[idx] = h;
   if (a.lo) a.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// fp32 [rows][C] -> bf16 planes [rows][CP] (hi, and lo = bf16(x - hi) when nplanes == 2); CP = C rounded up
+// to 8, pad channels zero.  One thread per 8-channel chunk.
+__global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int C, int CP, __nv_bfloat16* hi,
+                                    __nv_bfloat16* lo) {
+  const int cpr = CP >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cpr) return;
+  const long long r = idx / cpr;
+  const int c0 = (int)(idx - r * cpr) * 8;
+  float f[8];
+  const float* xp = x + (size_t)r * C + c0;
+  if (c0 + 7 < C && (C & 3) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xp)), b = __ldg(reinterpret_cast<const float4*>(xp) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? __ldg(xp + j) : 0.f;
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    h[e] = *reinterpret_cast<uint32_t*>(&h2);
+    float2 hf = __bfloat1622float2(h2);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+    l[e] = *reinterpret_cast<uint32_t*>(&l2);
+  }
+  const size_t o = (size_t)r * CP + c0;
+  *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace tc
@@ -353,6 +460,14 @@ __global__ void pack_tc_kernel(const PackArgs a) {
 // ---------------------------------------------------------------------------------------------
 using namespace tc;
 
+int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st) {
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(planes);
+  __nv_bfloat16* lo = nplanes == 2 ? hi + (size_t)rows * CP : nullptr;
+  const long long n = rows * (CP / 8);
+  tc::split_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, rows, C, CP, hi, lo);
+  return check_launch("split_planes_kernel");
+}
+
 int tc_bn_for(int Cd) {
   int cpad = ceil_div(Cd, 16) * 16;
   int tiles = ceil_div(cpad, 256);
@@ -360,7 +475,6 @@ int tc_bn_for(int Cd) {
   return bn;
 }
 
-bool tc_gather_eligible(int Cs, int Cd) { return (Cs % 8) == 0 && Cd >= 1; }
 
 // layout of the packed buffer of one gather-GEMM problem (K = ntaps * Cs, N = Cd)
 static TcWeightLayout tc_weight_layout(int ntaps, int Cs, int Cd, int passes) {
@@ -383,7 +497,8 @@ size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes) {
 
 int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
             const int* taps, int passes, cudaStream_t st) {
-  const int Cs = transpose ? Cout : Cin, Cd = transpose ? Cin : Cout;
+  const int CsReal = transpose ? Cout : Cin, Cd = transpose ? Cin : Cout;
+  const int Cs = ceil_div(CsReal, 8) * 8;
   TcWeightLayout L = tc_weight_layout(ntaps, Cs, Cd, passes);
   PackArgs a;
   a.w = w_oihw;
@@ -391,7 +506,7 @@ int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, i
   a.lo = L.planes == 2 ? a.hi + L.plane_elems : nullptr;
   a.Cout = Cout; a.Cin = Cin; a.KHW = KH * KW; a.transpose = transpose; a.ntaps = ntaps;
   for (int i = 0; i < ntaps; ++i) a.taps[i] = taps[i];
-  a.Nreal = Cd; a.Npad = L.Npad; a.Cs = Cs; a.K = L.K; a.Kpad = L.Kpad;
+  a.Nreal = Cd; a.Npad = L.Npad; a.Cs = Cs; a.CsReal = CsReal; a.K = L.K; a.Kpad = L.Kpad;
   pack_tc_kernel<<<(unsigned)ceil_div_ll((long long)L.plane_elems, 256), 256, 0, st>>>(a);
   return check_launch("pack_tc_kernel");
 }
@@ -451,12 +566,20 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* 
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(MOG_ERR_CUDA, "conv_tc_kernel smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div_ll(g.M, BM), (unsigned)L.ntiles, (unsigned)splits);
-  conv_tc_kernel<<<grid, CTHREADS, smem, st>>>(p);
+  if (g.src_planes) {
+    p.Xhi = static_cast<const __nv_bfloat16*>(g.src_planes);
+    p.Xlo = p.Xhi + g.src_plane_elems;
+    conv_tc_kernel<true><<<grid, CTHREADS, smem, st>>>(p);
+  } else {
+    p.Xhi = p.Xlo = nullptr;
+    conv_tc_kernel<false><<<grid, CTHREADS, smem, st>>>(p);
+  }
   int rc = check_launch("conv_tc_kernel");
   if (rc || splits == 1) return rc;
   const size_t total = (size_t)g.M * g.Cd;

@@ -27,6 +27,11 @@ constexpr int A_PLANE = 2 * BLK_BYTES;  // 128 kf
 struct WgParams {
   const float* x;
   const float* dy;
+  const __nv_bfloat16* xhi;   // PLANES kernel: pre-split bf16 planes [pixels][Cin] / [P][CoutP]
+  const __nv_bfloat16* xlo;
+  const __nv_bfloat16* dyhi;
+  const __nv_bfloat16* dylo;
+  int CoutP;                  // channel pitch of the dy planes (Cout rounded up to 8); == Cout for fp32 input
   float* ws;  // [splits][K][Cout]
   int N, H, W, Cin, up2x, Ho, Wo, Cout, KH, KW, stride, pad;
   long long P, chunk;
@@ -49,6 +54,7 @@ __device__ __forceinline__ void split_store(const float4& v0, const float4& v1, 
   if (two) *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+template <bool PLANES>
 __global__ void __launch_bounds__(WTHREADS, 1) wgrad_tc_kernel(const WgParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -105,6 +111,66 @@ __global__ void __launch_bounds__(WTHREADS, 1) wgrad_tc_kernel(const WgParams p)
       a_ow[j] = kw - p.pad;
     }
     const int nchB = p.BN / 8;  // 16-byte chunks per pixel of the B tile
+    if (PLANES) {
+      const int LAG = p.stages >= 3 ? 2 : 1;
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(&empty[s], ph ^ 1u);
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + A_PLANE;
+        const uint32_t b_hi = st + nplanes * A_PLANE, b_lo = b_hi + b_plane;
+        const long long pp = p_begin + (long long)it * PIX + pk;
+        const bool pix_ok = pp < p_end;
+        int n = 0, ho = 0, wo = 0;
+        if (pix_ok) {
+          wo = (int)(pp % p.Wo);
+          long long qq = pp / p.Wo;
+          ho = (int)(qq % p.Ho);
+          n = (int)(qq / p.Ho);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool inb = false;
+          size_t off = 0;
+          if (pix_ok && a_ok[j]) {
+            const int sh = ho * p.stride + a_oh[j], sw = wo * p.stride + a_ow[j];
+            if (sh >= 0 && sh < HL && sw >= 0 && sw < WL) {
+              inb = true;
+              off = (((size_t)n * p.H + (sh >> p.up2x)) * p.W + (sw >> p.up2x)) * p.Cin + a_c[j];
+            }
+          }
+          const int cm = q * 4 + j;
+          const uint32_t soff = (uint32_t)((cm >> 3) * BLK_BYTES + kgrp * 1024 + kin * 128 + (((cm & 7) ^ kin) << 4));
+          cp_async16(a_hi + soff, p.xhi + off, inb ? 16u : 0u);
+          if (two) cp_async16(a_lo + soff, p.xlo + off, inb ? 16u : 0u);
+        }
+        for (int cb = q; cb < nchB; cb += 4) {
+          const int co = n0 + cb * 8;
+          const bool ok = pix_ok && co < p.CoutP;
+          const size_t off = ok ? (size_t)pp * p.CoutP + co : 0;
+          const uint32_t soff = (uint32_t)((cb >> 3) * BLK_BYTES + kgrp * 1024 + kin * 128 + (((cb & 7) ^ kin) << 4));
+          cp_async16(b_hi + soff, p.dyhi + off, ok ? 16u : 0u);
+          if (two) cp_async16(b_lo + soff, p.dylo + off, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (it >= LAG) {
+          if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(&full[(it - LAG) % p.stages]);
+        }
+      }
+      if (nst > 0) {
+        if (LAG == 2 && nst >= 2) {
+          cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(&full[(nst - 2) % p.stages]);
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(&full[(nst - 1) % p.stages]);
+      }
+    } else {
     for (int it = 0; it < nst; ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)((it / p.stages) & 1);
@@ -159,6 +225,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) wgrad_tc_kernel(const WgParams p)
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
+    }
     }
     // ===================== epilogue (warps 0-3) ===============================================
     if (warp < 4) {
@@ -228,13 +295,14 @@ __global__ void __launch_bounds__(WTHREADS, 1) wgrad_tc_kernel(const WgParams p)
 
 using namespace tc;
 
-bool tc_wgrad_eligible(const MogConvDesc& d) { return (d.Cin % 8) == 0 && (d.Cout % 8) == 0; }
+// fp32 operands need whole 8-channel chunks; pre-split planes are padded to multiples of 8 by the splitter
+bool tc_wgrad_eligible(const MogConvDesc& d, bool planes) { return planes || ((d.Cin % 8) == 0 && (d.Cout % 8) == 0); }
 
 static void wg_tiling(const MogConvDesc& d, int Ho, int Wo, int* BN, int* ntn, int* splits, long long* chunk) {
   *BN = tc_bn_for(d.Cout);
   *ntn = ceil_div(d.Cout, *BN);
   const long long P = (long long)d.N * Ho * Wo;
-  const int K = d.KH * d.KW * d.Cin;
+  const int K = d.KH * d.KW * (ceil_div(d.Cin, 8) * 8);
   long long tiles = (long long)ceil_div(K, BM) * (*ntn);
   long long want = ceil_div_ll(2 * kNumSMs, tiles);
   long long maxs = ceil_div_ll(P, 4 * PIX);
@@ -251,17 +319,26 @@ size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo) {
   int BN, ntn, splits;
   long long chunk;
   wg_tiling(d, Ho, Wo, &BN, &ntn, &splits, &chunk);
-  return (size_t)splits * d.KH * d.KW * d.Cin * d.Cout * sizeof(float);
+  return (size_t)splits * d.KH * d.KW * (ceil_div(d.Cin, 8) * 8) * d.Cout * sizeof(float);
 }
 
-int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, float* ws, int passes,
+int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, const void* x_planes,
+                    size_t x_plane_elems, const void* dy_planes, size_t dy_plane_elems, float* ws, int passes,
                     int* splits_out, cudaStream_t st) {
+  // with planes the channel counts seen by the kernel are the padded ones (multiples of 8)
+  const bool planes = x_planes != nullptr;
+  const int CinP = planes ? ceil_div(d.Cin, 8) * 8 : d.Cin;
   WgParams p;
   p.x = x; p.dy = dy; p.ws = ws;
-  p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.up2x = d.up2x; p.Ho = Ho; p.Wo = Wo; p.Cout = d.Cout;
+  p.xhi = static_cast<const __nv_bfloat16*>(x_planes);
+  p.xlo = p.xhi ? p.xhi + x_plane_elems : nullptr;
+  p.dyhi = static_cast<const __nv_bfloat16*>(dy_planes);
+  p.dylo = p.dyhi ? p.dyhi + dy_plane_elems : nullptr;
+  p.CoutP = planes ? ceil_div(d.Cout, 8) * 8 : d.Cout;
+  p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = CinP; p.up2x = d.up2x; p.Ho = Ho; p.Wo = Wo; p.Cout = d.Cout;
   p.KH = d.KH; p.KW = d.KW; p.stride = d.stride; p.pad = d.pad;
   p.P = (long long)d.N * Ho * Wo;
-  p.K = d.KH * d.KW * d.Cin;
+  p.K = d.KH * d.KW * CinP;
   int ntn, splits;
   wg_tiling(d, Ho, Wo, &p.BN, &ntn, &splits, &p.chunk);
   p.nblkB = ceil_div(p.BN, 64);
@@ -278,12 +355,16 @@ int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const 
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(MOG_ERR_CUDA, "wgrad_tc_kernel smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid(ceil_div(p.K, BM), ntn, splits);
-  wgrad_tc_kernel<<<grid, WTHREADS, smem, st>>>(p);
+  if (planes)
+    wgrad_tc_kernel<true><<<grid, WTHREADS, smem, st>>>(p);
+  else
+    wgrad_tc_kernel<false><<<grid, WTHREADS, smem, st>>>(p);
   *splits_out = splits;
   return check_launch("wgrad_tc_kernel");
 }

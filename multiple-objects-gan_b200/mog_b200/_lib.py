@@ -39,9 +39,11 @@ SIGNATURES = {
     "mog_pack_weight": (_i, [_dp, _i, _p, _p, _p]),
     "mog_conv_out_hw": (_i, [_dp, C.POINTER(_i), C.POINTER(_i)]),
     "mog_conv_workspace_bytes": (_sz, [_dp, _i]),
-    "mog_conv2d_fwd": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
-    "mog_conv2d_dgrad": (_i, [_dp, _p, _p, _p, _p, _sz, _p]),
-    "mog_conv2d_wgrad": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
+    "mog_planes_bytes": (_sz, [C.c_longlong, _i, _i]),
+    "mog_split_planes": (_i, [_p, C.c_longlong, _i, _i, _p, _p]),
+    "mog_conv2d_fwd": (_i, [_dp, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mog_conv2d_dgrad": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
+    "mog_conv2d_wgrad": (_i, [_dp, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mog_bn_stats": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "mog_bn_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "mog_affine_act_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

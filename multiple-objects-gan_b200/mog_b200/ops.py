@@ -136,8 +136,21 @@ def _workspace(d, which, device):
     return ws, n
 
 
+def split_planes(x: torch.Tensor, precision: int):
+    """fp32 [..., C] -> bf16 planes buffer (hi [rows][C8], then lo for bf16x3) for the tcgen05 kernels."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    n = _lib.lib().mog_planes_bytes(rows, Cc, precision)
+    planes = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
+    call("mog_split_planes", x.data_ptr(), rows, Cc, precision, planes.data_ptr(), _stream())
+    return planes
+
+
 class Conv2dFn(torch.autograd.Function):
-    """y = act(conv(up2x?(x), w) + b), NHWC.  replaces nn.Conv2d (+ nn.Upsample) of model.py."""
+    """y = act(conv(up2x?(x), w) + b), NHWC.  replaces nn.Conv2d (+ nn.Upsample) of model.py.
+    In the tcgen05 precisions the input is split once into bf16 planes (kept for the weight
+    gradient instead of the fp32 tensor); the output gradient is split once in backward and
+    shared by the data and weight gradients."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad, up2x, act, precision):
@@ -147,37 +160,42 @@ class Conv2dFn(torch.autograd.Function):
         y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
         ws, nws = _workspace(d, 0, x.device)
         b = None if bias is None else bias.detach().contiguous()
-        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _packed(weight, "fwd", d).data_ptr(), _ptr(b),
+        xp = split_planes(x, precision) if precision != PREC_FP32 else None
+        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _ptr(xp), _packed(weight, "fwd", d).data_ptr(), _ptr(b),
              y.data_ptr(), _ptr(ws), nws, _stream())
-        ctx.cfg = (stride, pad, up2x, act, precision)
+        ctx.cfg = (stride, pad, up2x, act, precision, tuple(x.shape))
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.save_for_backward(x if xp is None else None, xp, weight, y if act != ACT_NONE else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
-        stride, pad, up2x, act, precision = ctx.cfg
+        x, xp, weight, y = ctx.saved_tensors
+        stride, pad, up2x, act, precision, xshape = ctx.cfg
         dy = dy.contiguous()
         w4 = weight if weight.dim() == 4 else weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
-        d, Ho, Wo = _desc(x.shape, w4.shape, stride, pad, up2x, ACT_NONE, precision)
+        d, Ho, Wo = _desc(xshape, w4.shape, stride, pad, up2x, ACT_NONE, precision)
         st = _stream()
+        dev = dy.device
         if act != ACT_NONE:
             dz = torch.empty_like(dy)
             call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, st)
             dy = dz
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        dyp = split_planes(dy, precision) if precision != PREC_FP32 and (need_dx or need_dw) else None
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            ws, nws = _workspace(d, 1, x.device)
-            call("mog_conv2d_dgrad", C.byref(d), dy.data_ptr(), _packed(weight, "dgrad", d).data_ptr(),
+        if need_dx:
+            dx = torch.empty(xshape, device=dev, dtype=torch.float32)
+            ws, nws = _workspace(d, 1, dev)
+            call("mog_conv2d_dgrad", C.byref(d), dy.data_ptr(), _ptr(dyp), _packed(weight, "dgrad", d).data_ptr(),
                  dx.data_ptr(), _ptr(ws), nws, st)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty(w4.shape, device=x.device, dtype=torch.float32)
+        if need_dw:
+            dw = torch.empty(w4.shape, device=dev, dtype=torch.float32)
             if ctx.has_bias:
-                db = torch.empty(d.Cout, device=x.device, dtype=torch.float32)
-            ws, nws = _workspace(d, 2, x.device)
-            call("mog_conv2d_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _ptr(db),
+                db = torch.empty(d.Cout, device=dev, dtype=torch.float32)
+            ws, nws = _workspace(d, 2, dev)
+            call("mog_conv2d_wgrad", C.byref(d), _ptr(x), _ptr(xp), dy.data_ptr(), _ptr(dyp), dw.data_ptr(), _ptr(db),
                  _ptr(ws), nws, st)
             dw = dw.reshape(weight.shape)
         return dx, dw, db, None, None, None, None, None

@@ -41,6 +41,13 @@ TC_CASES = [
     (1, 4, 4, 768, 1536, 4, 2, 1, False, False, 0),   # D_NET256 deep layer: K=12288, 6 N tiles of 256, M=4
     (2, 4, 4, 1024, 768, 3, 1, 1, False, False, 0),   # COND_DNET.jointConv
     (1, 40, 40, 8, 8, 3, 1, 1, True, False, 0),       # up2x, Cin=8: every chunk is its own tap
+    # channel counts that are not multiples of 8: planes are padded to 8 by mog_split_planes
+    (2, 16, 16, 3, 96, 4, 2, 1, False, False, 2),     # D first conv: Cin=3
+    (3, 16, 16, 84, 40, 4, 1, 1, False, False, 0),    # D_NET64.local: Cin=84
+    (2, 16, 16, 100, 50, 3, 2, 1, False, False, 2),   # bbox_net: 100 -> 50
+    (2, 9, 9, 25, 12, 3, 2, 1, False, False, 0),      # bbox_net: 25 -> 12, odd spatial size
+    (5, 1, 1, 181, 100, 1, 1, 0, False, False, 0),    # label Linear 181 -> 100
+    (4, 4, 4, 64, 1, 4, 4, 0, False, True, 0),        # outlogits: Cout=1 (dgrad gathers 1 -> 8 channels)
 ]
 
 
