@@ -72,6 +72,9 @@ int mog_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, v
  * stride phase for the tcgen05 path.  The buffer is opaque; size it with mog_packed_weight_bytes.
  * Re-pack after every optimiser step (weights changed). */
 size_t mog_packed_weight_bytes(const MogConvDesc* d, int which);
+/* Tag of the packed layout chosen for (d, which): it depends on the problem shape (the TMA-staged
+ * kernel uses a 64-channel tap pitch), so cache packed weights per (parameter version, tag). */
+int mog_packed_weight_layout(const MogConvDesc* d, int which);
 int mog_pack_weight(const MogConvDesc* d, int which, const float* w_oihw, void* w_packed, void* stream);
 
 /* ---- convolution ----------------------------------------------------------------------- */

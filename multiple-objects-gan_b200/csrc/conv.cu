@@ -84,8 +84,12 @@ static bool dgrad_problem(const MogConvDesc* d, int ph, int pw, IGemmParams* out
   return true;
 }
 
-// tcgen05 path: k runs over (tap, channel) with the channel pitch rounded up to 8
-static size_t tc_bytes(int ntaps, int Cs, int Cd, int passes) { return tc_packed_bytes(ntaps, p8(Cs), Cd, passes); }
+// tcgen05 path: k runs over (tap, channel); the channel pitch per tap is Cs rounded up to 8 for the
+// generic gather kernel and to 64 for the TMA kernel (whole 128-byte swizzle rows per box).
+static int tap_pitch(const IGemmParams& shape, int CsReal) { return tma_shape_eligible(shape) ? tma_tap_pitch(CsReal) : p8(CsReal); }
+static size_t tc_bytes(const IGemmParams& shape, int CsReal, int passes) {
+  return tc_packed_bytes(shape.nth * shape.ntw, tap_pitch(shape, CsReal), shape.Cd, passes);
+}
 
 // dgrad workspace = [hi-res gradient of the fused upsample][split-K partials of the largest phase]
 static size_t dgrad_up_bytes(const MogConvDesc* d) {
@@ -99,6 +103,7 @@ static size_t dgrad_split_bytes(const MogConvDesc* d) {
     for (int pw = 0; pw < d->stride; ++pw) {
       IGemmParams p;
       if (!dgrad_problem(d, ph, pw, &p)) continue;
+      if (tma_shape_eligible(p)) continue;
       size_t b = tc_igemm_workspace_bytes(p.M, p.nth * p.ntw, p8(d->Cout), d->Cin, passes_of(d));
       if (b > mx) mx = b;
     }
@@ -150,18 +155,34 @@ extern "C" size_t mog_packed_weight_bytes(const MogConvDesc* d, int which) {
   if (validate(d, "mog_packed_weight_bytes")) return 0;
   const size_t dense = (size_t)d->KH * d->KW * d->Cin * d->Cout * sizeof(float);
   if (!use_tc(d)) return dense;
-  if (which == 0) return tc_bytes(d->KH * d->KW, d->Cin, d->Cout, passes_of(d));
+  if (which == 0) return tc_bytes(fwd_problem(d), d->Cin, passes_of(d));
   if (which == 1) {
     size_t tot = 0;
     for (int ph = 0; ph < d->stride; ++ph)
       for (int pw = 0; pw < d->stride; ++pw) {
         IGemmParams p;
         if (!dgrad_problem(d, ph, pw, &p)) continue;
-        tot += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+        tot += tc_bytes(p, d->Cout, passes_of(d));
       }
     return tot;
   }
   return 0;
+}
+
+// Identifies the packed layout chosen for (d, which) so callers can cache packed weights per layout:
+// bit i set = stride phase i (forward: bit 0) uses the TMA kernel's 64-channel tap pitch.
+extern "C" int mog_packed_weight_layout(const MogConvDesc* d, int which) {
+  if (validate(d, "mog_packed_weight_layout")) return -1;
+  if (!use_tc(d)) return 0;
+  if (which == 0) return tma_shape_eligible(fwd_problem(d)) ? 1 : 0;
+  int tag = 0, i = 0;
+  for (int ph = 0; ph < d->stride; ++ph)
+    for (int pw = 0; pw < d->stride; ++pw, ++i) {
+      IGemmParams p;
+      if (!dgrad_problem(d, ph, pw, &p)) continue;
+      if (tma_shape_eligible(p)) tag |= 1 << (i & 30);
+    }
+  return tag;
 }
 
 extern "C" int mog_pack_weight(const MogConvDesc* d, int which, const float* w, void* out, void* stream) {
@@ -181,16 +202,17 @@ extern "C" int mog_pack_weight(const MogConvDesc* d, int which, const float* w, 
   if (which == 0) {
     int taps[64];
     for (int i = 0; i < d->KH * d->KW; ++i) taps[i] = i;
-    return tc_pack(w, out, d->Cout, d->Cin, d->KH, d->KW, 0, d->KH * d->KW, taps, passes_of(d), st);
+    return tc_pack_pitch(w, out, d->Cout, d->Cin, d->KH, d->KW, 0, d->KH * d->KW, taps, tap_pitch(fwd_problem(d), d->Cin),
+                         passes_of(d), st);
   }
   unsigned char* o = static_cast<unsigned char*>(out);
   for (int ph = 0; ph < d->stride; ++ph)
     for (int pw = 0; pw < d->stride; ++pw) {
       IGemmParams p;
       if (!dgrad_problem(d, ph, pw, &p)) continue;
-      rc = tc_pack(w, o, d->Cout, d->Cin, d->KH, d->KW, 1, p.nth * p.ntw, p.tapw, passes_of(d), st);
+      rc = tc_pack_pitch(w, o, d->Cout, d->Cin, d->KH, d->KW, 1, p.nth * p.ntw, p.tapw, tap_pitch(p, d->Cout), passes_of(d), st);
       if (rc) return rc;
-      o += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+      o += tc_bytes(p, d->Cout, passes_of(d));
     }
   return MOG_OK;
 }
@@ -200,7 +222,7 @@ extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
   if (which == 0) {
-    if (!use_tc(d)) return 0;
+    if (!use_tc(d) || tma_shape_eligible(fwd_problem(d))) return 0;
     return tc_igemm_workspace_bytes((long long)d->N * Ho * Wo, d->KH * d->KW, p8(d->Cin), d->Cout, passes_of(d));
   }
   if (which == 1) return dgrad_up_bytes(d) + dgrad_split_bytes(d);
@@ -216,8 +238,11 @@ extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* 
   IGemmParams p = fwd_problem(d);
   p.bias = bias; p.dst = y;
   if (use_tc(d)) {
+    const bool tma = tma_shape_eligible(p);
+    if (tma && !x_planes) return fail(MOG_ERR_BAD_ARG, "mog_conv2d_fwd: this shape runs on the TMA kernel and needs x_planes");
     rc = attach_source(&p, x, x_planes, (long long)d->N * d->H * d->W, "mog_conv2d_fwd");
     if (rc) return rc;
+    if (tma) return launch_igemm_tma(p, w, passes_of(d), 0, as_stream(stream));
     return launch_igemm_tc(p, w, passes_of(d), workspace, ws_bytes, as_stream(stream));
   }
   MOG_REQUIRE(x, "mog_conv2d_fwd: fp32 precision needs the fp32 input");
@@ -247,10 +272,13 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
       if (!dgrad_problem(d, ph, pw, &p)) continue;
       p.bias = nullptr; p.dst = target;
       if (use_tc(d)) {
+        const bool tma = tma_shape_eligible(p);
+        const size_t wbytes = tc_bytes(p, d->Cout, passes_of(d));
+        if (tma && !dy_planes) return fail(MOG_ERR_BAD_ARG, "mog_conv2d_dgrad: this shape runs on the TMA kernel and needs dy_planes");
         rc = attach_source(&p, dy, dy_planes, (long long)d->N * Ho * Wo, "mog_conv2d_dgrad");
         if (rc) return rc;
-        rc = launch_igemm_tc(p, wp, passes_of(d), split_ws, split_bytes, st);
-        wp += tc_bytes(p.nth * p.ntw, d->Cout, d->Cin, passes_of(d));
+        rc = tma ? launch_igemm_tma(p, wp, passes_of(d), 0, st) : launch_igemm_tc(p, wp, passes_of(d), split_ws, split_bytes, st);
+        wp += wbytes;
       } else {
         MOG_REQUIRE(dy, "mog_conv2d_dgrad: fp32 precision needs the fp32 gradient");
         p.src = dy;

@@ -47,6 +47,12 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* 
                     cudaStream_t st);
 size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int passes);
 bool tc_wgrad_eligible(const MogConvDesc& d, bool planes);
+// TMA-staged persistent kernel (conv_tma.cu)
+bool tma_shape_eligible(const IGemmParams& g);
+int tma_tap_pitch(int Cs);
+int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, int accum_dst, cudaStream_t st);
+int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
+                  const int* taps, int pitch, int passes, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
 int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, const void* x_planes,
                     size_t x_plane_elems, const void* dy_planes, size_t dy_plane_elems, float* ws, int passes,

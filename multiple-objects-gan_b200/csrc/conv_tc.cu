@@ -497,8 +497,15 @@ size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes) {
 
 int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
             const int* taps, int passes, cudaStream_t st) {
+  const int CsReal = transpose ? Cout : Cin;
+  return tc_pack_pitch(w_oihw, out, Cout, Cin, KH, KW, transpose, ntaps, taps, ceil_div(CsReal, 8) * 8, passes, st);
+}
+
+// k = local_tap * pitch + c  (pitch >= channel count, multiple of 8; channels beyond the real count are zero)
+int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
+                  const int* taps, int pitch, int passes, cudaStream_t st) {
   const int CsReal = transpose ? Cout : Cin, Cd = transpose ? Cin : Cout;
-  const int Cs = ceil_div(CsReal, 8) * 8;
+  const int Cs = pitch;
   TcWeightLayout L = tc_weight_layout(ntaps, Cs, Cd, passes);
   PackArgs a;
   a.w = w_oihw;

@@ -36,6 +36,7 @@ SIGNATURES = {
     "mog_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mog_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mog_packed_weight_bytes": (_sz, [_dp, _i]),
+    "mog_packed_weight_layout": (_i, [_dp, _i]),
     "mog_pack_weight": (_i, [_dp, _i, _p, _p, _p]),
     "mog_conv_out_hw": (_i, [_dp, C.POINTER(_i), C.POINTER(_i)]),
     "mog_conv_workspace_bytes": (_sz, [_dp, _i]),

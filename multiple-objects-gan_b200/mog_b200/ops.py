@@ -102,14 +102,15 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc) -> torch.Tensor:
         except Exception:
             pass
     # the dgrad packing depends on stride/pad (phase tap subsets) and, with odd sizes, on H/W parity
-    key = (which, d.precision, d.stride, d.pad, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
+    wi = 0 if which == "fwd" else 1
+    tag = _lib.lib().mog_packed_weight_layout(C.byref(d), wi)
+    key = (which, tag, d.precision, d.stride, d.pad, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
     if key not in cache:
         w = weight.detach()
         if w.dim() == 2:
             w = w.reshape(w.shape[0], w.shape[1], 1, 1)
         w = w.contiguous()
         _chk(w, "weight")
-        wi = 0 if which == "fwd" else 1
         n = _lib.lib().mog_packed_weight_bytes(C.byref(d), wi)
         out = torch.empty((n + 3) // 4, device=w.device, dtype=torch.float32)
         call("mog_pack_weight", C.byref(d), wi, w.data_ptr(), out.data_ptr(), _stream())

@@ -9,7 +9,7 @@ from mog_b200._lib import PREC_NAMES
 
 precs = sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16x3"]
 for prec in precs:
-    for case in T.TC_CASES:
+    for case in (T.TMA_CASES if 'tma' in sys.argv else T.TC_CASES):
         N, H, W, Ci, Co, k, s, p, up, has_b, act = case
         x = T.rnd(N, Ci, H, W, seed=1).requires_grad_(True)
         w = T.rnd(Co, Ci, k, k, seed=2, scale=1.0 / np.sqrt(Ci * k * k)).requires_grad_(True)
