@@ -1,10 +1,20 @@
-// conv.cu -- C-ABI entry points of the convolution family.  Builds the gather-GEMM problems
-// (forward: one; data gradient: one per stride phase) and dispatches on MogConvDesc.precision:
-//   MOG_PREC_FP32              -> CUDA-core kernels (conv_ffma.cu), fp32 operands
-//   MOG_PREC_BF16X3 / _BF16    -> tcgen05 kernels (conv_tc.cu, conv_tc_wgrad.cu), always.  The
-//       gathered operands are either pre-split bf16 planes (mog_split_planes; channel pitch rounded
-//       up to 8, so every channel count is accepted) or fp32 tensors split on the fly (only when
-//       the channel count is a multiple of 8).
+// conv.cu -- C-ABI entry points of the convolution family.
+//
+// A convolution (forward or data gradient) is decomposed into one or more *gather-GEMM problems*
+// (IGemmParams): rows = a grid of output pixels, K = (local tap, channel), unit or strided gather
+// from an NHWC source (possibly a parity *view* of it), destination pixels on a strided sub-grid.
+//   MOG_PREC_FP32            -> one problem per conv / stride phase on the CUDA cores (conv_ffma.cu)
+//   MOG_PREC_BF16X3 / _BF16  -> tcgen05 kernels, always:
+//       * upsample(2x nearest)+conv  = 4 sub-pixel phases: each a stride-1 conv with 2x2 taps whose
+//         weights are pre-summed filter taps (2.25x fewer MACs than the dense 3x3 on the 4x grid);
+//         its data gradient = the 4 transposed phase convs over the parity views of dy, accumulated.
+//       * stride-s conv = s*s unit-stride convs over the parity views of x, accumulated (when the
+//         grid is big enough for the TMA kernel), its data gradient = one unit-stride problem per
+//         stride phase of dx.
+//       * each problem runs on the persistent TMA-staged kernel (conv_tma.cu) when its shape allows,
+//         else on the generic gather kernel with split-K (conv_tc.cu).
+//     Operands are pre-split bf16 planes (mog_split_planes) or, for the generic kernel only, fp32
+//     tensors split on the fly (channel count multiple of 8).
 #include "conv_common.cuh"
 
 using namespace mog;
@@ -19,7 +29,7 @@ static int validate(const MogConvDesc* d, const char* who) {
   MOG_REQUIRE(d, "%s: null descriptor", who);
   MOG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "%s: non-positive dims", who);
   MOG_REQUIRE(d->KH > 0 && d->KW > 0 && d->KH <= 8 && d->KW <= 8 && d->KH * d->KW <= 64, "%s: filter %dx%d unsupported", who, d->KH, d->KW);
-  MOG_REQUIRE(d->stride >= 1 && d->stride <= 8 && d->pad >= 0, "%s: bad stride/pad", who);
+  MOG_REQUIRE(d->stride >= 1 && d->stride <= 4 && d->pad >= 0, "%s: bad stride/pad", who);
   MOG_REQUIRE(d->up2x == 0 || d->up2x == 1, "%s: up2x must be 0/1", who);
   MOG_REQUIRE(d->precision >= MOG_PREC_FP32 && d->precision <= MOG_PREC_BF16, "%s: unknown precision %d", who, d->precision);
   int HL = d->H << d->up2x, WL = d->W << d->up2x;
@@ -36,9 +46,25 @@ static void out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
 static int passes_of(const MogConvDesc* d) { return d->precision == MOG_PREC_BF16X3 ? 3 : 1; }
 static bool use_tc(const MogConvDesc* d) { return d->precision != MOG_PREC_FP32; }
 static int p8(int c) { return ceil_div(c, 8) * 8; }
+static int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }   // floor division, b > 0
+static int pmod(int a, int b) { return ((a % b) + b) % b; }
 
-// ---- problem builders -----------------------------------------------------------------------
-static IGemmParams fwd_problem(const MogConvDesc* d) {
+// ---- problems ---------------------------------------------------------------------------------
+struct Problem {
+  IGemmParams g;      // shape; src/dst/bias pointers are attached at call time
+  int taps[64][4];    // filter taps (kh*KW + kw) summed into each local tap, -1 = unused
+  int transpose;      // weight operand orientation: 0 n=co,c=ci (forward)   1 n=ci,c=co (data gradient)
+  int CsReal;         // channels of the gathered tensor
+  int src_pixels_h, src_pixels_w;   // physical source dims
+};
+
+static void clear_taps(Problem* q) {
+  for (int i = 0; i < 64; ++i)
+    for (int u = 0; u < 4; ++u) q->taps[i][u] = -1;
+}
+
+// the single dense problem of a forward conv (also the CUDA-core formulation)
+static void fwd_single(const MogConvDesc* d, Problem* q) {
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
   IGemmParams p{};
@@ -52,13 +78,15 @@ static IGemmParams fwd_problem(const MogConvDesc* d) {
   p.act = d->act;
   p.M = (long long)d->N * Ho * Wo;
   p.K = d->KH * d->KW * d->Cin;
-  return p;
+  q->g = p;
+  clear_taps(q);
+  for (int i = 0; i < d->KH * d->KW; ++i) q->taps[i][0] = i;
+  q->transpose = 0; q->CsReal = d->Cin; q->src_pixels_h = d->H; q->src_pixels_w = d->W;
 }
 
-// One gather-GEMM per stride phase: input pixels (hi, wi) with hi%s==ph, wi%s==pw only see the taps
-// kh with (ph + pad - kh) % s == 0, at dy row hi/s + (ph + pad - kh)/s.  Returns false for an
-// empty phase (no rows).
-static bool dgrad_problem(const MogConvDesc* d, int ph, int pw, IGemmParams* out) {
+// One gather-GEMM per stride phase of dx: input pixels (hi, wi) with hi%s==ph, wi%s==pw only see the taps
+// kh with (ph + pad - kh) % s == 0, at dy row hi/s + (ph + pad - kh)/s.  Returns false for an empty phase.
+static bool dgrad_phase(const MogConvDesc* d, int ph, int pw, Problem* q) {
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
   const int HL = d->H << d->up2x, WL = d->W << d->up2x;
@@ -69,64 +97,197 @@ static bool dgrad_problem(const MogConvDesc* d, int ph, int pw, IGemmParams* out
   if (p.Hr <= 0 || p.Wr <= 0) return false;
   int nth = 0, ntw = 0, khs[8], kws[8];
   for (int kh = 0; kh < d->KH; ++kh)
-    if (((ph + d->pad - kh) % s + s) % s == 0) { khs[nth] = kh; p.off_h[nth] = (ph + d->pad - kh) / s; ++nth; }
+    if (pmod(ph + d->pad - kh, s) == 0) { khs[nth] = kh; p.off_h[nth] = (ph + d->pad - kh) / s; ++nth; }
   for (int kw = 0; kw < d->KW; ++kw)
-    if (((pw + d->pad - kw) % s + s) % s == 0) { kws[ntw] = kw; p.off_w[ntw] = (pw + d->pad - kw) / s; ++ntw; }
+    if (pmod(pw + d->pad - kw, s) == 0) { kws[ntw] = kw; p.off_w[ntw] = (pw + d->pad - kw) / s; ++ntw; }
   if (nth == 0 || ntw == 0) { nth = 0; ntw = 1; }  // no tap reaches this phase: K = 0, zeros are written
   p.nth = nth; p.ntw = ntw;
+  clear_taps(q);
   for (int a = 0; a < nth; ++a)
-    for (int b = 0; b < ntw; ++b) p.tapw[a * ntw + b] = khs[a] * d->KW + kws[b];
+    for (int b = 0; b < ntw; ++b) {
+      p.tapw[a * ntw + b] = khs[a] * d->KW + kws[b];
+      q->taps[a * ntw + b][0] = khs[a] * d->KW + kws[b];
+    }
   p.Cd = d->Cin; p.Hd = HL; p.Wd = WL; p.dsh = s; p.doh = ph; p.dsw = s; p.dow = pw;
   p.act = MOG_ACT_NONE;
   p.M = (long long)d->N * p.Hr * p.Wr;
   p.K = nth * ntw * d->Cout;
-  *out = p;
+  q->g = p;
+  q->transpose = 1; q->CsReal = d->Cout; q->src_pixels_h = Ho; q->src_pixels_w = Wo;
   return true;
+}
+
+// upsample+conv as 4 sub-pixel phases: output row 2i+a reads low-res rows i + floor((a + kh - pad)/2)
+static bool up2x_phases_ok(const MogConvDesc* d) {
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  return d->up2x && d->stride == 1 && Ho == 2 * d->H && Wo == 2 * d->W && d->KH <= 3 && d->KW <= 3;
+}
+// distinct low-res offsets of phase a along one axis and the filter taps that map to each
+static int phase_axis(int a, int K, int pad, int* offs, int (*members)[2]) {
+  int n = 0;
+  for (int k = 0; k < K; ++k) {
+    const int dd = fdiv(a + k - pad, 2);
+    int j = 0;
+    for (; j < n; ++j)
+      if (offs[j] == dd) break;
+    if (j == n) { offs[n] = dd; members[n][0] = members[n][1] = -1; ++n; }
+    if (members[j][0] < 0) members[j][0] = k; else members[j][1] = k;
+  }
+  return n;
+}
+static void up2x_phase(const MogConvDesc* d, int a, int b, bool dgrad, Problem* q) {
+  int oh[4], ow[4], mh[4][2], mw[4][2];
+  const int nth = phase_axis(a, d->KH, d->pad, oh, mh), ntw = phase_axis(b, d->KW, d->pad, ow, mw);
+  IGemmParams p{};
+  p.N = d->N; p.up2x = 0; p.rs = 1; p.nth = nth; p.ntw = ntw;
+  p.Hr = d->H; p.Wr = d->W;
+  p.M = (long long)d->N * d->H * d->W;
+  clear_taps(q);
+  for (int i = 0; i < nth; ++i)
+    for (int j = 0; j < ntw; ++j) {
+      int u = 0;
+      for (int x = 0; x < 2; ++x)
+        for (int y = 0; y < 2; ++y)
+          if (mh[i][x] >= 0 && mw[j][y] >= 0) q->taps[i * ntw + j][u++] = mh[i][x] * d->KW + mw[j][y];
+    }
+  if (!dgrad) {
+    // y[2i+a, 2j+b] = sum_taps x[i + oh, j + ow] * W'
+    p.Hs = d->H; p.Ws = d->W; p.Cs = d->Cin;
+    for (int i = 0; i < nth; ++i) p.off_h[i] = oh[i];
+    for (int j = 0; j < ntw; ++j) p.off_w[j] = ow[j];
+    p.Cd = d->Cout; p.Hd = 2 * d->H; p.Wd = 2 * d->W; p.dsh = 2; p.doh = a; p.dsw = 2; p.dow = b;
+    p.act = d->act;
+    q->transpose = 0; q->CsReal = d->Cin; q->src_pixels_h = d->H; q->src_pixels_w = d->W;
+  } else {
+    // dx[i, j] += sum_taps dy[2(i - oh) + a, 2(j - ow) + b] * W'^T : parity view (a, b) of dy, offsets -oh
+    p.Hs = d->H; p.Ws = d->W; p.Cs = d->Cout;
+    p.vstep = 2; p.voh = a; p.vow = b; p.Hp = 2 * d->H; p.Wp = 2 * d->W;
+    for (int i = 0; i < nth; ++i) p.off_h[i] = -oh[i];
+    for (int j = 0; j < ntw; ++j) p.off_w[j] = -ow[j];
+    p.Cd = d->Cin; p.Hd = d->H; p.Wd = d->W; p.dsh = 1; p.doh = 0; p.dsw = 1; p.dow = 0;
+    p.act = MOG_ACT_NONE;
+    p.accum_dst = (a | b) != 0;
+    q->transpose = 1; q->CsReal = d->Cout; q->src_pixels_h = 2 * d->H; q->src_pixels_w = 2 * d->W;
+  }
+  p.K = nth * ntw * p.Cs;
+  q->g = p;
+}
+
+// stride-s forward conv over the parity view (a, b) of x: taps with (k - pad) % s == a at view offset (k - pad - a)/s
+static bool strided_view(const MogConvDesc* d, int a, int b, Problem* q) {
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  const int s = d->stride;
+  IGemmParams p{};
+  p.N = d->N; p.up2x = 0; p.rs = 1;
+  p.vstep = s; p.voh = a; p.vow = b; p.Hp = d->H; p.Wp = d->W;
+  p.Hs = d->H / s; p.Ws = d->W / s; p.Cs = d->Cin;
+  p.Hr = Ho; p.Wr = Wo;
+  int nth = 0, ntw = 0, khs[8], kws[8];
+  for (int kh = 0; kh < d->KH; ++kh)
+    if (pmod(kh - d->pad, s) == a) { khs[nth] = kh; p.off_h[nth] = fdiv(kh - d->pad - a, s); ++nth; }
+  for (int kw = 0; kw < d->KW; ++kw)
+    if (pmod(kw - d->pad, s) == b) { kws[ntw] = kw; p.off_w[ntw] = fdiv(kw - d->pad - b, s); ++ntw; }
+  if (nth == 0 || ntw == 0) return false;
+  p.nth = nth; p.ntw = ntw;
+  clear_taps(q);
+  for (int i = 0; i < nth; ++i)
+    for (int j = 0; j < ntw; ++j) q->taps[i * ntw + j][0] = khs[i] * d->KW + kws[j];
+  p.Cd = d->Cout; p.Hd = Ho; p.Wd = Wo; p.dsh = 1; p.doh = 0; p.dsw = 1; p.dow = 0;
+  p.act = MOG_ACT_NONE;
+  p.M = (long long)d->N * Ho * Wo;
+  p.K = nth * ntw * p.Cs;
+  q->g = p;
+  q->transpose = 0; q->CsReal = d->Cin; q->src_pixels_h = d->H; q->src_pixels_w = d->W;
+  return true;
+}
+
+// problems of the forward conv in tcgen05 precision; returns the count (<= 16)
+static int build_fwd(const MogConvDesc* d, Problem* out) {
+  if (up2x_phases_ok(d)) {
+    int n = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) up2x_phase(d, a, b, false, &out[n++]);
+    return n;
+  }
+  if (d->stride > 1 && !d->up2x && (d->H % d->stride) == 0 && (d->W % d->stride) == 0) {
+    Problem probe;
+    if (strided_view(d, pmod(-d->pad, d->stride), pmod(-d->pad, d->stride), &probe) && tma_shape_eligible(probe.g)) {
+      int n = 0;
+      for (int a = 0; a < d->stride; ++a)
+        for (int b = 0; b < d->stride; ++b)
+          if (strided_view(d, a, b, &out[n])) ++n;
+      for (int i = 0; i < n; ++i) out[i].g.accum_dst = i > 0;
+      out[n - 1].g.act = d->act;   // bias (attached at call time to the last problem) and activation once, at the end
+      return n;
+    }
+  }
+  fwd_single(d, &out[0]);
+  return 1;
+}
+
+// problems of the data gradient; *hires = 1 when they produce the gradient of the upsampled input
+// (fallback path: caller sum-pools it)
+static int build_dgrad(const MogConvDesc* d, Problem* out, int* hires) {
+  *hires = 0;
+  if (use_tc(d) && up2x_phases_ok(d)) {
+    int n = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) up2x_phase(d, a, b, true, &out[n++]);
+    return n;
+  }
+  int n = 0;
+  for (int ph = 0; ph < d->stride; ++ph)
+    for (int pw = 0; pw < d->stride; ++pw)
+      if (dgrad_phase(d, ph, pw, &out[n])) ++n;
+  *hires = d->up2x;
+  return n;
 }
 
 // tcgen05 path: k runs over (tap, channel); the channel pitch per tap is Cs rounded up to 8 for the
 // generic gather kernel and to 64 for the TMA kernel (whole 128-byte swizzle rows per box).
-static int tap_pitch(const IGemmParams& shape, int CsReal) { return tma_shape_eligible(shape) ? tma_tap_pitch(CsReal) : p8(CsReal); }
-static size_t tc_bytes(const IGemmParams& shape, int CsReal, int passes) {
-  return tc_packed_bytes(shape.nth * shape.ntw, tap_pitch(shape, CsReal), shape.Cd, passes);
+static int tap_pitch(const Problem& q) { return tma_shape_eligible(q.g) ? tma_tap_pitch(q.CsReal) : p8(q.CsReal); }
+static size_t tc_bytes(const Problem& q, int passes) {
+  return tc_packed_bytes(q.g.nth * q.g.ntw, tap_pitch(q), q.g.Cd, passes);
+}
+static size_t split_bytes(const Problem& q, int passes) {
+  if (tma_shape_eligible(q.g)) return 0;
+  return tc_igemm_workspace_bytes(q.g.M, q.g.nth * q.g.ntw, p8(q.CsReal), q.g.Cd, passes);
 }
 
-// dgrad workspace = [hi-res gradient of the fused upsample][split-K partials of the largest phase]
-static size_t dgrad_up_bytes(const MogConvDesc* d) {
-  size_t b = d->up2x ? (size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cin * sizeof(float) : 0;
+static size_t dgrad_up_bytes(const MogConvDesc* d, int hires) {
+  size_t b = hires ? (size_t)d->N * (2 * d->H) * (2 * d->W) * d->Cin * sizeof(float) : 0;
   return (b + 255) / 256 * 256;
-}
-static size_t dgrad_split_bytes(const MogConvDesc* d) {
-  if (!use_tc(d)) return 0;
-  size_t mx = 0;
-  for (int ph = 0; ph < d->stride; ++ph)
-    for (int pw = 0; pw < d->stride; ++pw) {
-      IGemmParams p;
-      if (!dgrad_problem(d, ph, pw, &p)) continue;
-      if (tma_shape_eligible(p)) continue;
-      size_t b = tc_igemm_workspace_bytes(p.M, p.nth * p.ntw, p8(d->Cout), d->Cin, passes_of(d));
-      if (b > mx) mx = b;
-    }
-  return mx;
 }
 
 // attach the gathered operand (planes or fp32) of a tcgen05 problem; Cs becomes the channel pitch
-static int attach_source(IGemmParams* p, const float* src_f32, const void* planes, long long pixels, const char* who) {
-  const int CsReal = p->Cs;
+static int attach_source(Problem* q, const float* src_f32, const void* planes, int N, const char* who) {
+  IGemmParams* p = &q->g;
   if (planes) {
-    p->Cs = p8(CsReal);
+    p->Cs = p8(q->CsReal);
     p->src = nullptr;
     p->src_planes = planes;
-    p->src_plane_elems = (size_t)pixels * p->Cs;
+    p->src_plane_elems = (size_t)N * q->src_pixels_h * q->src_pixels_w * p->Cs;
   } else {
-    if (CsReal % 8) return fail(MOG_ERR_UNSUPPORTED, "%s: %d channels need pre-split planes (mog_split_planes) in tcgen05 precision", who, CsReal);
+    if (q->CsReal % 8) return fail(MOG_ERR_UNSUPPORTED, "%s: %d channels need pre-split planes (mog_split_planes) in tcgen05 precision", who, q->CsReal);
     if (!src_f32) return fail(MOG_ERR_BAD_ARG, "%s: neither an fp32 tensor nor planes given", who);
+    p->Cs = q->CsReal;
     p->src = src_f32;
     p->src_planes = nullptr;
     p->src_plane_elems = 0;
   }
   p->K = p->nth * p->ntw * p->Cs;
   return MOG_OK;
+}
+
+static int run_tc_problem(Problem* q, const float* src_f32, const void* planes, int N, const void* wpacked, int passes,
+                          void* ws, size_t ws_bytes, cudaStream_t st, const char* who) {
+  const bool tma = tma_shape_eligible(q->g);
+  if (tma && !planes) return fail(MOG_ERR_BAD_ARG, "%s: this shape runs on the TMA kernel and needs pre-split planes", who);
+  int rc = attach_source(q, src_f32, planes, N, who);
+  if (rc) return rc;
+  return tma ? launch_igemm_tma(q->g, wpacked, passes, st) : launch_igemm_tc(q->g, wpacked, passes, ws, ws_bytes, st);
 }
 
 // ---- public API ---------------------------------------------------------------------------------
@@ -151,37 +312,33 @@ extern "C" int mog_split_planes(const float* x, long long rows, int C, int preci
   return launch_split_planes(x, rows, C, p8(C), planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream));
 }
 
+static int build(const MogConvDesc* d, int which, Problem* probs, int* hires) {
+  *hires = 0;
+  return which == 0 ? build_fwd(d, probs) : build_dgrad(d, probs, hires);
+}
+
 extern "C" size_t mog_packed_weight_bytes(const MogConvDesc* d, int which) {
-  if (validate(d, "mog_packed_weight_bytes")) return 0;
-  const size_t dense = (size_t)d->KH * d->KW * d->Cin * d->Cout * sizeof(float);
-  if (!use_tc(d)) return dense;
-  if (which == 0) return tc_bytes(fwd_problem(d), d->Cin, passes_of(d));
-  if (which == 1) {
-    size_t tot = 0;
-    for (int ph = 0; ph < d->stride; ++ph)
-      for (int pw = 0; pw < d->stride; ++pw) {
-        IGemmParams p;
-        if (!dgrad_problem(d, ph, pw, &p)) continue;
-        tot += tc_bytes(p, d->Cout, passes_of(d));
-      }
-    return tot;
-  }
-  return 0;
+  if (validate(d, "mog_packed_weight_bytes") || (which != 0 && which != 1)) return 0;
+  if (!use_tc(d)) return (size_t)d->KH * d->KW * d->Cin * d->Cout * sizeof(float);
+  Problem probs[16];
+  int hires;
+  const int n = build(d, which, probs, &hires);
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) tot += tc_bytes(probs[i], passes_of(d));
+  return tot;
 }
 
 // Identifies the packed layout chosen for (d, which) so callers can cache packed weights per layout:
-// bit i set = stride phase i (forward: bit 0) uses the TMA kernel's 64-channel tap pitch.
+// low bits: which problems use the TMA kernel's 64-channel tap pitch; high bits: the decomposition.
 extern "C" int mog_packed_weight_layout(const MogConvDesc* d, int which) {
-  if (validate(d, "mog_packed_weight_layout")) return -1;
+  if (validate(d, "mog_packed_weight_layout") || (which != 0 && which != 1)) return -1;
   if (!use_tc(d)) return 0;
-  if (which == 0) return tma_shape_eligible(fwd_problem(d)) ? 1 : 0;
-  int tag = 0, i = 0;
-  for (int ph = 0; ph < d->stride; ++ph)
-    for (int pw = 0; pw < d->stride; ++pw, ++i) {
-      IGemmParams p;
-      if (!dgrad_problem(d, ph, pw, &p)) continue;
-      if (tma_shape_eligible(p)) tag |= 1 << (i & 30);
-    }
+  Problem probs[16];
+  int hires;
+  const int n = build(d, which, probs, &hires);
+  int tag = n << 20;
+  for (int i = 0; i < n; ++i)
+    if (tma_shape_eligible(probs[i].g)) tag |= 1 << i;
   return tag;
 }
 
@@ -190,30 +347,25 @@ extern "C" int mog_pack_weight(const MogConvDesc* d, int which, const float* w, 
   if (rc) return rc;
   MOG_REQUIRE(w && out && (which == 0 || which == 1), "mog_pack_weight: bad argument");
   cudaStream_t st = as_stream(stream);
-  const size_t total = (size_t)d->Cout * d->Cin * d->KH * d->KW;
-  const unsigned blocks = (unsigned)ceil_div_ll((long long)total, 256);
   if (!use_tc(d)) {
+    const size_t total = (size_t)d->Cout * d->Cin * d->KH * d->KW;
+    const unsigned blocks = (unsigned)ceil_div_ll((long long)total, 256);
     if (which == 0)
       pack_fwd_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
     else
       pack_dgrad_kernel<<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), d->Cout, d->Cin, d->KH * d->KW);
     return check_launch("pack_kernel");
   }
-  if (which == 0) {
-    int taps[64];
-    for (int i = 0; i < d->KH * d->KW; ++i) taps[i] = i;
-    return tc_pack_pitch(w, out, d->Cout, d->Cin, d->KH, d->KW, 0, d->KH * d->KW, taps, tap_pitch(fwd_problem(d), d->Cin),
-                         passes_of(d), st);
-  }
+  Problem probs[16];
+  int hires;
+  const int n = build(d, which, probs, &hires);
   unsigned char* o = static_cast<unsigned char*>(out);
-  for (int ph = 0; ph < d->stride; ++ph)
-    for (int pw = 0; pw < d->stride; ++pw) {
-      IGemmParams p;
-      if (!dgrad_problem(d, ph, pw, &p)) continue;
-      rc = tc_pack_pitch(w, o, d->Cout, d->Cin, d->KH, d->KW, 1, p.nth * p.ntw, p.tapw, tap_pitch(p, d->Cout), passes_of(d), st);
-      if (rc) return rc;
-      o += tc_bytes(p, d->Cout, passes_of(d));
-    }
+  for (int i = 0; i < n; ++i) {
+    const Problem& q = probs[i];
+    rc = tc_pack_pitch(w, o, d->Cout, d->Cin, d->KH, d->KW, q.transpose, q.g.nth * q.g.ntw, q.taps, tap_pitch(q), passes_of(d), st);
+    if (rc) return rc;
+    o += tc_bytes(q, passes_of(d));
+  }
   return MOG_OK;
 }
 
@@ -221,13 +373,18 @@ extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   if (validate(d, "mog_conv_workspace_bytes")) return 0;
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
-  if (which == 0) {
-    if (!use_tc(d) || tma_shape_eligible(fwd_problem(d))) return 0;
-    return tc_igemm_workspace_bytes((long long)d->N * Ho * Wo, d->KH * d->KW, p8(d->Cin), d->Cout, passes_of(d));
-  }
-  if (which == 1) return dgrad_up_bytes(d) + dgrad_split_bytes(d);
   if (which == 2) return use_tc(d) ? tc_wgrad_workspace_bytes(*d, Ho, Wo) : wgrad_ffma_workspace_bytes(*d, Ho, Wo);
-  return 0;
+  if (which != 0 && which != 1) return 0;
+  if (!use_tc(d)) return which == 1 ? dgrad_up_bytes(d, d->up2x) : 0;
+  Problem probs[16];
+  int hires;
+  const int n = build(d, which, probs, &hires);
+  size_t mx = 0;
+  for (int i = 0; i < n; ++i) {
+    size_t b = split_bytes(probs[i], passes_of(d));
+    if (b > mx) mx = b;
+  }
+  return dgrad_up_bytes(d, hires) + mx;
 }
 
 extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* x_planes, const void* w,
@@ -235,20 +392,31 @@ extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* 
   int rc = validate(d, "mog_conv2d_fwd");
   if (rc) return rc;
   MOG_REQUIRE((x || x_planes) && w && y, "mog_conv2d_fwd: null tensor");
-  IGemmParams p = fwd_problem(d);
-  p.bias = bias; p.dst = y;
-  if (use_tc(d)) {
-    const bool tma = tma_shape_eligible(p);
-    if (tma && !x_planes) return fail(MOG_ERR_BAD_ARG, "mog_conv2d_fwd: this shape runs on the TMA kernel and needs x_planes");
-    rc = attach_source(&p, x, x_planes, (long long)d->N * d->H * d->W, "mog_conv2d_fwd");
-    if (rc) return rc;
-    if (tma) return launch_igemm_tma(p, w, passes_of(d), 0, as_stream(stream));
-    return launch_igemm_tc(p, w, passes_of(d), workspace, ws_bytes, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (!use_tc(d)) {
+    MOG_REQUIRE(x, "mog_conv2d_fwd: fp32 precision needs the fp32 input");
+    Problem q;
+    fwd_single(d, &q);
+    q.g.src = x; q.g.bias = bias; q.g.dst = y;
+    q.g.wmat = static_cast<const float*>(w);
+    return launch_igemm_ffma(q.g, st);
   }
-  MOG_REQUIRE(x, "mog_conv2d_fwd: fp32 precision needs the fp32 input");
-  p.src = x;
-  p.wmat = static_cast<const float*>(w);
-  return launch_igemm_ffma(p, as_stream(stream));
+  Problem probs[16];
+  const int n = build_fwd(d, probs);
+  const size_t need = mog_conv_workspace_bytes(d, 0);
+  if (need && (!workspace || ws_bytes < need)) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_fwd: workspace %zu < %zu", ws_bytes, need);
+  const unsigned char* wp = static_cast<const unsigned char*>(w);
+  for (int i = 0; i < n; ++i) {
+    Problem& q = probs[i];
+    const size_t wbytes = tc_bytes(q, passes_of(d));
+    q.g.dst = y;
+    // bias: every sub-pixel phase writes its own pixels (bias each); accumulated parity views add it once, at the end
+    q.g.bias = (q.g.accum_dst || (n > 1 && q.g.vstep > 1)) ? (i == n - 1 ? bias : nullptr) : bias;
+    rc = run_tc_problem(&q, x, x_planes, d->N, wp, passes_of(d), workspace, ws_bytes, st, "mog_conv2d_fwd");
+    if (rc) return rc;
+    wp += wbytes;
+  }
+  return MOG_OK;
 }
 
 extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* dy_planes, const void* wt,
@@ -256,39 +424,32 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
   int rc = validate(d, "mog_conv2d_dgrad");
   if (rc) return rc;
   MOG_REQUIRE((dy || dy_planes) && wt && dx, "mog_conv2d_dgrad: null tensor");
-  int Ho, Wo;
-  out_hw(d, &Ho, &Wo);
-  float* target = dx;
+  cudaStream_t st = as_stream(stream);
+  Problem probs[16];
+  int hires;
+  const int n = build_dgrad(d, probs, &hires);
   const size_t need = mog_conv_workspace_bytes(d, 1);
   if (need && (!workspace || ws_bytes < need)) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_dgrad: workspace %zu < %zu", ws_bytes, need);
-  if (d->up2x) target = static_cast<float*>(workspace);
-  unsigned char* split_ws = workspace ? static_cast<unsigned char*>(workspace) + dgrad_up_bytes(d) : nullptr;
-  const size_t split_bytes = need - dgrad_up_bytes(d);
-  cudaStream_t st = as_stream(stream);
+  float* target = hires ? static_cast<float*>(workspace) : dx;
+  unsigned char* sws = workspace ? static_cast<unsigned char*>(workspace) + dgrad_up_bytes(d, hires) : nullptr;
+  const size_t sbytes = need - dgrad_up_bytes(d, hires);
   const unsigned char* wp = static_cast<const unsigned char*>(wt);
-  for (int ph = 0; ph < d->stride; ++ph) {
-    for (int pw = 0; pw < d->stride; ++pw) {
-      IGemmParams p;
-      if (!dgrad_problem(d, ph, pw, &p)) continue;
-      p.bias = nullptr; p.dst = target;
-      if (use_tc(d)) {
-        const bool tma = tma_shape_eligible(p);
-        const size_t wbytes = tc_bytes(p, d->Cout, passes_of(d));
-        if (tma && !dy_planes) return fail(MOG_ERR_BAD_ARG, "mog_conv2d_dgrad: this shape runs on the TMA kernel and needs dy_planes");
-        rc = attach_source(&p, dy, dy_planes, (long long)d->N * Ho * Wo, "mog_conv2d_dgrad");
-        if (rc) return rc;
-        rc = tma ? launch_igemm_tma(p, wp, passes_of(d), 0, st) : launch_igemm_tc(p, wp, passes_of(d), split_ws, split_bytes, st);
-        wp += wbytes;
-      } else {
-        MOG_REQUIRE(dy, "mog_conv2d_dgrad: fp32 precision needs the fp32 gradient");
-        p.src = dy;
-        p.wmat = static_cast<const float*>(wt);
-        rc = launch_igemm_ffma(p, st);
-      }
-      if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    Problem& q = probs[i];
+    q.g.bias = nullptr; q.g.dst = target;
+    if (use_tc(d)) {
+      const size_t wbytes = tc_bytes(q, passes_of(d));
+      rc = run_tc_problem(&q, dy, dy_planes, d->N, wp, passes_of(d), sws, sbytes, st, "mog_conv2d_dgrad");
+      wp += wbytes;
+    } else {
+      MOG_REQUIRE(dy, "mog_conv2d_dgrad: fp32 precision needs the fp32 gradient");
+      q.g.src = dy;
+      q.g.wmat = static_cast<const float*>(wt);
+      rc = launch_igemm_ffma(q.g, st);
     }
+    if (rc) return rc;
   }
-  if (d->up2x) return launch_sumpool(target, dx, d->N, d->H, d->W, d->Cin, st);
+  if (hires) return launch_sumpool(target, dx, d->N, d->H, d->W, d->Cin, st);
   return MOG_OK;
 }
 

@@ -15,7 +15,10 @@ struct IGemmParams {
   const float* wmat;
   const float* bias;
   float* dst;
-  int N, Hs, Ws, Cs;
+  int N, Hs, Ws, Cs;           // logical source grid (a strided *view* of the physical tensor when vstep > 1)
+  int vstep, voh, vow, Hp, Wp; // view: logical pixel (h, w) = physical (h*vstep + voh, w*vstep + vow) of an Hp x Wp tensor;
+                               // vstep == 0 means "no view" (physical == logical)
+  int accum_dst;               // epilogue adds to dst instead of overwriting (sums over parity views)
   int up2x;
   int Hr, Wr, rs;
   int nth, ntw;
@@ -40,8 +43,6 @@ int launch_sumpool(const float* src, float* dst, int N, int H, int W, int C, cud
 // tcgen05 path (conv_tc.cu, conv_tc_wgrad.cu)
 namespace tc { struct TcWeightLayout; }
 int tc_bn_for(int Cd);
-int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
-            const int* taps, int passes, cudaStream_t st);
 size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes);
 int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* workspace, size_t ws_bytes,
                     cudaStream_t st);
@@ -50,9 +51,9 @@ bool tc_wgrad_eligible(const MogConvDesc& d, bool planes);
 // TMA-staged persistent kernel (conv_tma.cu)
 bool tma_shape_eligible(const IGemmParams& g);
 int tma_tap_pitch(int Cs);
-int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, int accum_dst, cudaStream_t st);
+int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, cudaStream_t st);
 int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
-                  const int* taps, int pitch, int passes, cudaStream_t st);
+                  const int (*taps)[4], int pitch, int passes, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
 int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, const void* x_planes,
                     size_t x_plane_elems, const void* dy_planes, size_t dy_plane_elems, float* ws, int passes,

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
       w0 = rw * g.rs;
     }
     const int HL = g.Hs << g.up2x, WL = g.Ws << g.up2x;
+    const int vs = g.vstep > 0 ? g.vstep : 1, Hp = g.vstep > 0 ? g.Hp : g.Hs, Wp = g.vstep > 0 ? g.Wp : g.Ws;
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const int rx = r & 7;
     // running decode of k -> (tap, channel); chunks of 8 channels never straddle a tap (Cs % 8 == 0)
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
             const int sh = h0 + g.off_h[th], sw = w0 + g.off_w[tw];
             if (sh >= 0 && sh < HL && sw >= 0 && sw < WL) {
               inb = true;
-              off = (((size_t)rn * g.Hs + (sh >> g.up2x)) * g.Ws + (sw >> g.up2x)) * g.Cs + c;
+              off = (((size_t)rn * Hp + ((sh >> g.up2x) * vs + g.voh)) * Wp + ((sw >> g.up2x) * vs + g.vow)) * g.Cs + c;
             }
           }
           const uint32_t soff = row_off + (uint32_t)(((half * 4 + j) ^ rx) << 4);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
         if (row_ok && th < g.nth) {
           const int sh = h0 + g.off_h[th], sw = w0 + g.off_w[tw];
           if (sh >= 0 && sh < HL && sw >= 0 && sw < WL) {
-            const size_t off = (((size_t)rn * g.Hs + (sh >> g.up2x)) * g.Ws + (sw >> g.up2x)) * g.Cs + c;
+            const size_t off = (((size_t)rn * Hp + ((sh >> g.up2x) * vs + g.voh)) * Wp + ((sw >> g.up2x) * vs + g.vow)) * g.Cs + c;
             const float4* sp = reinterpret_cast<const float4*>(g.src + off);
             v[j][0] = __ldg(sp);
             v[j][1] = __ldg(sp + 1);
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
           float v0 = __uint_as_float(acc[j]);
           if (!raw) {
             float b = (g.bias && n0 + c0 + j < g.Cd) ? __ldg(g.bias + n0 + c0 + j) : 0.f;
+            if (g.accum_dst && n0 + c0 + j < g.Cd) b += dptr[c0 + j];
             v0 = epi_act(v0 + b, g.act);
           }
           o[j] = v0;
@@ -378,13 +380,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, const IG
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + idx];
   if (g.bias) s += __ldg(g.bias + n);
-  s = epi_act(s, g.act);
   int rw = (int)(m % g.Wr);
   long long q = m / g.Wr;
   int rh = (int)(q % g.Hr);
   int rn = (int)(q / g.Hr);
   size_t pix = ((size_t)rn * g.Hd + (rh * g.dsh + g.doh)) * g.Wd + (rw * g.dsw + g.dow);
-  g.dst[pix * g.Cd + n] = s;
+  if (g.accum_dst) s += g.dst[pix * g.Cd + n];
+  g.dst[pix * g.Cd + n] = epi_act(s, g.act);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -397,7 +399,7 @@ struct PackArgs {
   int Cout, Cin, KHW;
   int transpose;  // 0: n = co, c = ci (forward)    1: n = ci, c = co (data gradient)
   int ntaps;
-  int taps[64];
+  int taps[64][4];   // up to 4 filter taps summed into one local tap (sub-pixel phases of upsample+conv); -1 = unused
   int Nreal, Npad, Cs, CsReal, K, Kpad;   // Cs: channel pitch of k (multiple of 8), CsReal: channels that exist
 };
 
@@ -411,9 +413,11 @@ __global__ void pack_tc_kernel(const PackArgs a) {
   if (n < a.Nreal && k < a.K) {
     int tl = k / a.Cs, c = k - tl * a.Cs;
     if (c < a.CsReal) {
-      int tap = a.taps[tl];
       int co = a.transpose ? c : n, ci = a.transpose ? n : c;
-      v = a.w[((size_t)co * a.Cin + ci) * a.KHW + tap];
+      const float* wp = a.w + ((size_t)co * a.Cin + ci) * a.KHW;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (a.taps[tl][u] >= 0) v += wp[a.taps[tl][u]];
     }
   }
   __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -495,15 +499,10 @@ size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes) {
   return (b + 255) / 256 * 256;  // keep every phase 256-byte aligned
 }
 
-int tc_pack(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
-            const int* taps, int passes, cudaStream_t st) {
-  const int CsReal = transpose ? Cout : Cin;
-  return tc_pack_pitch(w_oihw, out, Cout, Cin, KH, KW, transpose, ntaps, taps, ceil_div(CsReal, 8) * 8, passes, st);
-}
 
 // k = local_tap * pitch + c  (pitch >= channel count, multiple of 8; channels beyond the real count are zero)
 int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
-                  const int* taps, int pitch, int passes, cudaStream_t st) {
+                  const int (*taps)[4], int pitch, int passes, cudaStream_t st) {
   const int CsReal = transpose ? Cout : Cin, Cd = transpose ? Cin : Cout;
   const int Cs = pitch;
   TcWeightLayout L = tc_weight_layout(ntaps, Cs, Cd, passes);
@@ -512,7 +511,8 @@ int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int
   a.hi = static_cast<__nv_bfloat16*>(out);
   a.lo = L.planes == 2 ? a.hi + L.plane_elems : nullptr;
   a.Cout = Cout; a.Cin = Cin; a.KHW = KH * KW; a.transpose = transpose; a.ntaps = ntaps;
-  for (int i = 0; i < ntaps; ++i) a.taps[i] = taps[i];
+  for (int i = 0; i < ntaps; ++i)
+    for (int u = 0; u < 4; ++u) a.taps[i][u] = taps[i][u];
   a.Nreal = Cd; a.Npad = L.Npad; a.Cs = Cs; a.CsReal = CsReal; a.K = L.K; a.Kpad = L.Kpad;
   pack_tc_kernel<<<(unsigned)ceil_div_ll((long long)L.plane_elems, 256), 256, 0, st>>>(a);
   return check_launch("pack_tc_kernel");

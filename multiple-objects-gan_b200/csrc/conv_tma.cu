@@ -279,6 +279,7 @@ int tma_tap_pitch(int Cs) { return ceil_div(Cs, 64) * 64; }
 // shape-only test (the weight packing depends on it); Cs is the channel count of the gathered tensor
 bool tma_shape_eligible(const IGemmParams& g) {
   if (g.rs != 1 || g.up2x) return false;
+  if (g.vstep > 1 && ((g.Hp % g.vstep) || (g.Wp % g.vstep))) return false;
   if (!is_pow2(g.Hr) || !is_pow2(g.Wr)) return false;
   if (g.Wr > 128 && (g.Wr % 128)) return false;
   if (g.nth < 1 || g.ntw < 1) return false;
@@ -287,7 +288,8 @@ bool tma_shape_eligible(const IGemmParams& g) {
   return encode_fn() != nullptr;
 }
 
-int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, int accum_dst, cudaStream_t st) {
+int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, cudaStream_t st) {
+  const int accum_dst = g.accum_dst;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   if (!g.src_planes || (g.Cs % 8)) return fail(MOG_ERR_BAD_ARG, "conv (TMA): needs pre-split planes with a channel pitch multiple of 8");
@@ -326,11 +328,13 @@ int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, int a
   for (int pl = 0; pl < 2; ++pl) {
     const int src = pl < nplanes ? pl : 0;   // unused maps alias plane 0 (never dereferenced)
     {
+      // (strided) view of the physical [N][Hp][Wp][Cs] plane: logical (h, w) = physical (h*vs + voh, w*vs + vow)
+      const int vs = g.vstep > 0 ? g.vstep : 1, Hp = g.vstep > 0 ? g.Hp : g.Hs, Wp = g.vstep > 0 ? g.Wp : g.Ws;
       cuuint64_t dims[4] = {(cuuint64_t)g.Cs, (cuuint64_t)g.Ws, (cuuint64_t)g.Hs, (cuuint64_t)g.N};
-      cuuint64_t strides[3] = {(cuuint64_t)g.Cs * 2, (cuuint64_t)g.Ws * g.Cs * 2, (cuuint64_t)g.Hs * g.Ws * g.Cs * 2};
+      cuuint64_t strides[3] = {(cuuint64_t)vs * g.Cs * 2, (cuuint64_t)vs * Wp * g.Cs * 2, (cuuint64_t)Hp * Wp * g.Cs * 2};
       cuuint32_t box[4] = {64u, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
       cuuint32_t es[4] = {1, 1, 1, 1};
-      void* base = const_cast<__nv_bfloat16*>(xa + (size_t)src * g.src_plane_elems);
+      void* base = const_cast<__nv_bfloat16*>(xa + (size_t)src * g.src_plane_elems + ((size_t)g.voh * Wp + g.vow) * g.Cs);
       CUresult r = enc(&tmA[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);

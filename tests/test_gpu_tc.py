@@ -171,6 +171,10 @@ TMA_CASES = [
     (16, 32, 32, 96, 192, 4, 2, 1, False, False, 0),   # stride 2: dgrad phases (16x16 grids, M=4096... generic) + fwd generic
     (4, 64, 64, 96, 192, 4, 2, 1, False, False, 0),    # stride 2 with 32x32 phase grids (M=4096 per phase: generic) sanity
     (32, 32, 32, 40, 56, 4, 2, 1, False, False, 0),    # dgrad phases on 32x32 grids with M=32768 -> TMA, taps 2x2 per phase
+    (8, 32, 32, 96, 96, 3, 1, 1, True, False, 0),      # upBlock: 4 sub-pixel phases (2x2 summed taps) on TMA; dgrad over parity views of dy
+    (8, 32, 32, 24, 40, 3, 1, 1, True, True, 2),       # same with bias + LeakyReLU epilogue per phase
+    (8, 64, 64, 3, 96, 4, 2, 1, False, False, 2),      # D first conv: stride 2 = 4 parity views of x accumulated, activation at the end
+    (32, 32, 32, 24, 16, 3, 2, 1, False, True, 0),     # 3x3/s2: parity classes with 1 and 2 taps, bias once
 ]
 
 
