@@ -163,15 +163,29 @@ int mog_word_attention_fwd(const float* h, const float* src, const uint8_t* mask
 int mog_word_attention_bwd(const float* h, const float* src, const uint8_t* mask, const float* dout,
                            float* dh, float* dsrc, int B, int Q, int D, int T, int mask_quirk, void* stream);
 
+/* ---- DAMSM word-region matching (AttnGAN) ---------------------------------------------------- */
+/* replaces: the per-caption loop of words_loss, each a func_attention call + cosine similarity +
+ * log-sum-exp (miscc/losses.py:72-112, GlobalAttention.py:31-69).  ctx [B][R][D] region features
+ * (NHWC), words [NI][D][Tw] (reference layout), lens [NI] int32.  sims[b][i] = log sum_t exp(gamma2 *
+ * cos(word_t, attended context)); paired=1 evaluates only pairs (b, b) (func_attention's contract) and
+ * then sims is [B]; wei_out [pairs][D][Tw] and attn_out [pairs][Tw][R] are optional outputs. */
+int mog_damsm_words_fwd(const float* ctx, const float* words, const int* lens, float* sims, float* wei_out,
+                        float* attn_out, int B, int NI, int R, int D, int Tw, int paired, float gamma1, float gamma2,
+                        void* stream);
+/* gradient w.r.t. the region features (the word embeddings come from the frozen text encoder). */
+int mog_damsm_words_bwd(const float* ctx, const float* words, const int* lens, const float* dsims, float* dctx,
+                        int B, int NI, int R, int D, int Tw, float gamma1, float gamma2, void* stream);
+
 /* ---- loss heads --------------------------------------------------------------------------- */
 /* loss[0] (+)= weight * mean_i BCE(sigmoid(z_i), target_i) with torch's log clamp at -100;
  * prob (may be NULL) receives sigmoid(z).  replaces: nn.Sigmoid + nn.BCELoss
- * (model.py:627, miscc/losses.py:156-171,195-200). */
+ * (model.py:627, miscc/losses.py:156-171,195-200).  with_logits=1: nn.BCEWithLogitsLoss of the
+ * StackGAN / CLEVR / Multi-MNIST programs (stackgan/miscc/utils.py:77, no clamp, stable form). */
 int mog_sigmoid_bce_fwd(const float* z, const float* target /*[n]*/, float weight, int n, float* prob, float* loss,
-                        int accumulate, void* stream);
+                        int accumulate, int with_logits, void* stream);
 /* dz_i = gscale[0] * weight * dBCE/dz_i / n */
 int mog_sigmoid_bce_bwd(const float* z, const float* target /*[n]*/, float weight, int n, const float* gscale,
-                        float* dz, void* stream);
+                        float* dz, int with_logits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -346,18 +346,36 @@ __global__ void __launch_bounds__(NT, 2) wgrad_kernel(const WgradParams p) {
   }
 }
 
-// dw_oihw[co][ci][kh][kw] = sum_z ws[z][(kh*KW+kw)*Cin+ci][co]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int K,
-                                    int Cout, int Cin, int CinP, int KHW) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)K * Cout;
-  if (idx >= total) return;
-  int co = (int)(idx % Cout);
-  int kf = (int)(idx / Cout);
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + idx];
-  int tap = kf / CinP, ci = kf - tap * CinP;   // CinP: channel pitch of kf (Cin rounded up to 8 with planes)
-  if (ci < Cin) dw[((size_t)co * Cin + ci) * KHW + tap] = s;
+// dw_oihw[co][ci][tap] = sum_z ws[z][tap*CinP + ci][co]      (deterministic split reduction + layout change)
+// Block = 32 output channels x 16 input channels x all taps: reads are coalesced along co (128 B per kf row),
+// the tile is transposed through shared memory and written as contiguous (ci, tap) runs per co.
+constexpr int RCO = 32, RCI = 16;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits,
+                                                           int K, int Cout, int Cin, int CinP, int KHW) {
+  extern __shared__ float tile[];   // [RCO][RCI*KHW + 1]
+  const int ld = RCI * KHW + 1;
+  const int ci0 = blockIdx.x * RCI, co0 = blockIdx.y * RCO;
+  const size_t total = (size_t)K * Cout;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;   // lane -> co, 8 warps -> (tap, ci) rows
+  for (int r = wrp; r < RCI * KHW; r += 8) {
+    const int tap = r / RCI, cil = r - tap * RCI;
+    const int ci = ci0 + cil, co = co0 + lane;
+    float s = 0.f;
+    if (ci < Cin && co < Cout) {
+      const size_t idx = (size_t)(tap * CinP + ci) * Cout + co;
+      for (int z = 0; z < splits; ++z) s += ws[(size_t)z * total + idx];
+    }
+    tile[lane * ld + cil * KHW + tap] = s;
+  }
+  __syncthreads();
+  const int nci = min(RCI, Cin - ci0);
+  const int run = nci * KHW;   // contiguous floats per co in the OIHW tensor
+  for (int c = wrp; c < RCO; c += 8) {
+    const int co = co0 + c;
+    if (co >= Cout) break;
+    float* out = dw + ((size_t)co * Cin + ci0) * KHW;
+    for (int i = lane; i < run; i += 32) out[i] = tile[c * ld + i];
+  }
 }
 
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int C) {
@@ -456,8 +474,9 @@ size_t wgrad_ffma_workspace_bytes(const MogConvDesc& d, int Ho, int Wo) {
 
 int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout, int Cin, int CinP, int KHW,
                         cudaStream_t st) {
-  size_t total = (size_t)K * Cout;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(ws, dw, splits, K, Cout, Cin, CinP, KHW);
+  dim3 grid(ceil_div(Cin, RCI), ceil_div(Cout, RCO));
+  const size_t smem = sizeof(float) * RCO * (RCI * KHW + 1);
+  wgrad_reduce_kernel<<<grid, 256, smem, st>>>(ws, dw, splits, K, Cout, Cin, CinP, KHW);
   return check_launch("wgrad_reduce_kernel");
 }
 

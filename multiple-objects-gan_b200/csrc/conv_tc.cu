@@ -522,7 +522,7 @@ int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int
 static int tc_splits(long long M, int ntiles, int nk) {
   const long long ctas = ceil_div_ll(M, BM) * ntiles;
   if (ctas >= 96 || nk < 8) return 1;
-  long long want = ceil_div_ll(2 * kNumSMs, ctas);
+  long long want = (2 * kNumSMs) / ctas;   // floor: whole waves
   long long maxs = nk / 4;
   long long s = want < maxs ? want : maxs;
   if (s < 1) s = 1;

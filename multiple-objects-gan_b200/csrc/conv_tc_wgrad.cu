@@ -304,7 +304,7 @@ static void wg_tiling(const MogConvDesc& d, int Ho, int Wo, int* BN, int* ntn, i
   const long long P = (long long)d.N * Ho * Wo;
   const int K = d.KH * d.KW * (ceil_div(d.Cin, 8) * 8);
   long long tiles = (long long)ceil_div(K, BM) * (*ntn);
-  long long want = ceil_div_ll(2 * kNumSMs, tiles);
+  long long want = (2 * kNumSMs) / tiles;   // floor: two full waves of CTAs, no ragged third wave
   long long maxs = ceil_div_ll(P, 4 * PIX);
   long long s = want < maxs ? want : maxs;
   if (s < 1) s = 1;

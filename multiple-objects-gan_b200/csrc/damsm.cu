@@ -1,0 +1,359 @@
+// damsm.cu -- fused DAMSM word-region attention similarity (AttnGAN matching loss).
+//
+// replaces: the Python loop of words_loss over captions, each iteration a func_attention call
+// (bmm -> softmax over words -> *gamma1 -> softmax over regions -> bmm) followed by a cosine
+// similarity and a log-sum-exp (miscc/losses.py:72-112, GlobalAttention.py:31-69):
+//
+//   for image b, caption i (n_i words):
+//     S[r,t]   = <ctx[b,r,:], w_i[:,t]>                       r: regions (17*17), t < n_i
+//     a1[r,:]  = softmax_t S[r,:]
+//     a2[t,:]  = softmax_r (gamma1 * a1[:,t])
+//     v[:,t]   = sum_r a2[t,r] ctx[b,r,:]
+//     sim[b,i] = log sum_t exp(gamma2 * cos(w_i[:,t], v[:,t]))
+//
+// One CTA per (image, caption) pair in the forward; the whole pair stays on chip (scores in shared
+// memory, per-thread channel accumulators), ctx[b] is streamed from L2 twice.  The backward runs one
+// CTA per image and loops over the captions, accumulating d ctx[b] in place (deterministic, no atomics).
+// FLOPs are small (5.4 GFLOP at B=32); this kernel exists to remove ~15 launches x B iterations of latency.
+#include "common.cuh"
+
+namespace mog {
+
+constexpr int DT = 256;     // threads
+constexpr int TMAXW = 32;   // max words per caption
+constexpr int MAXCPT = 2;   // channels per thread (template parameter CPT) -> D <= 512
+
+struct DamsmArgs {
+  const float* ctx;    // [B][R][D]   region features, NHWC
+  const float* words;  // [NI][D][Tw] word embeddings (reference layout: batch x nef x seq_len)
+  const int* lens;     // [NI]
+  float* sims;         // [B][NI]
+  float* wei_out;      // optional [B*NI][D][Tw]
+  float* attn_out;     // optional [B*NI][Tw][R]
+  const float* dsims;  // backward: [B][NI]
+  float* dctx;         // backward: [B][R][D]
+  int B, NI, R, D, Tw, paired;
+  float g1, g2, eps;
+};
+
+// shared state of one (b, i) pair
+struct PairSmem {
+  float* w;    // [D][TMAXW+1]
+  float* S;    // [R][TMAXW+1]  scores -> a1
+  float* A2;   // [TMAXW][R+1]
+  float* red;  // [3][TMAXW][DT/32 + 1]
+  float* cosv; // [TMAXW] cos, [TMAXW] |w|, [TMAXW] |v|, [TMAXW] wv
+};
+
+__device__ __forceinline__ PairSmem carve(float* sm, int R, int D) {
+  PairSmem p;
+  p.w = sm;
+  p.S = p.w + (size_t)D * (TMAXW + 1);
+  p.A2 = p.S + (size_t)R * (TMAXW + 1);
+  p.red = p.A2 + (size_t)TMAXW * (R + 1);
+  p.cosv = p.red + 3 * TMAXW * (DT / 32 + 1);
+  return p;
+}
+static size_t pair_smem_bytes(int R, int D) {
+  return sizeof(float) * ((size_t)D * (TMAXW + 1) + (size_t)R * (TMAXW + 1) + (size_t)TMAXW * (R + 1) +
+                          3 * TMAXW * (DT / 32 + 1) + 4 * TMAXW + (size_t)TMAXW * (R + 1));
+}
+
+// forward of one pair up to v (kept in registers: v[k][t] for channel c = tid + k*DT) and cos/|w|/|v|/wv in smem
+template <int CPT>
+__device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float* ctx, const float* wi, int n,
+                             float (&v)[CPT][TMAXW]) {
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int ldw = TMAXW + 1;
+  for (int i = tid; i < a.D * n; i += DT) {
+    int c = i / n, t = i - c * n;
+    s.w[c * ldw + t] = __ldg(wi + (size_t)c * a.Tw + t);
+  }
+  __syncthreads();
+  // scores: one warp per region, lanes over channels
+  for (int r = wrp; r < a.R; r += DT / 32) {
+    float acc[TMAXW];
+#pragma unroll
+    for (int t = 0; t < TMAXW; ++t) acc[t] = 0.f;
+    for (int c = lane; c < a.D; c += 32) {
+      const float x = __ldg(ctx + (size_t)r * a.D + c);
+#pragma unroll
+      for (int t = 0; t < TMAXW; ++t)
+        if (t < n) acc[t] = fmaf(x, s.w[c * ldw + t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < TMAXW; ++t) {
+      if (t < n) {
+        float z = warp_sum(acc[t]);
+        if (lane == 0) s.S[r * ldw + t] = z;
+      }
+    }
+  }
+  __syncthreads();
+  // a1 = softmax over words (per region)
+  for (int r = tid; r < a.R; r += DT) {
+    float mx = -INFINITY;
+    for (int t = 0; t < n; ++t) mx = fmaxf(mx, s.S[r * ldw + t]);
+    float sum = 0.f;
+    for (int t = 0; t < n; ++t) {
+      float e = expf(s.S[r * ldw + t] - mx);
+      s.S[r * ldw + t] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    for (int t = 0; t < n; ++t) s.S[r * ldw + t] *= inv;
+  }
+  __syncthreads();
+  // a2 = softmax over regions of gamma1 * a1 (per word): one warp per word
+  for (int t = wrp; t < n; t += DT / 32) {
+    float mx = -INFINITY;
+    for (int r = lane; r < a.R; r += 32) mx = fmaxf(mx, a.g1 * s.S[r * ldw + t]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int r = lane; r < a.R; r += 32) {
+      float e = expf(a.g1 * s.S[r * ldw + t] - mx);
+      s.A2[t * (a.R + 1) + r] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int r = lane; r < a.R; r += 32) s.A2[t * (a.R + 1) + r] *= inv;
+  }
+  __syncthreads();
+  // v[c][t] = sum_r a2[t][r] ctx[r][c]: thread per channel (coalesced over c)
+#pragma unroll
+  for (int k = 0; k < CPT; ++k)
+#pragma unroll
+    for (int t = 0; t < TMAXW; ++t) v[k][t] = 0.f;
+  for (int r = 0; r < a.R; ++r) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * DT;
+      if (c < a.D) {
+        const float x = __ldg(ctx + (size_t)r * a.D + c);
+#pragma unroll
+        for (int t = 0; t < TMAXW; ++t)
+          if (t < n) v[k][t] = fmaf(x, s.A2[t * (a.R + 1) + r], v[k][t]);
+      }
+    }
+  }
+  // cos(w_t, v_t): block reductions of <w,v>, |w|^2, |v|^2 over channels
+  const int ldr = DT / 32 + 1;
+#pragma unroll
+  for (int t = 0; t < TMAXW; ++t) {
+    if (t < n) {
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int c = tid + k * DT;
+        if (c < a.D) {
+          const float wv = s.w[c * ldw + t];
+          p0 = fmaf(wv, v[k][t], p0);
+          p1 = fmaf(wv, wv, p1);
+          p2 = fmaf(v[k][t], v[k][t], p2);
+        }
+      }
+      p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+      if (lane == 0) {
+        s.red[(0 * TMAXW + t) * ldr + wrp] = p0;
+        s.red[(1 * TMAXW + t) * ldr + wrp] = p1;
+        s.red[(2 * TMAXW + t) * ldr + wrp] = p2;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < n) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    for (int j = 0; j < DT / 32; ++j) {
+      p0 += s.red[(0 * TMAXW + tid) * ldr + j];
+      p1 += s.red[(1 * TMAXW + tid) * ldr + j];
+      p2 += s.red[(2 * TMAXW + tid) * ldr + j];
+    }
+    const float nw = sqrtf(p1), nv = sqrtf(p2);
+    s.cosv[tid] = p0 / fmaxf(nw * nv, a.eps);   // miscc/losses.py:11-17
+    s.cosv[TMAXW + tid] = nw;
+    s.cosv[2 * TMAXW + tid] = nv;
+    s.cosv[3 * TMAXW + tid] = p0;
+  }
+  __syncthreads();
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(DT) damsm_fwd_kernel(DamsmArgs a) {
+  extern __shared__ float sm[];
+  const PairSmem s = carve(sm, a.R, a.D);
+  const int b = blockIdx.x, i = a.paired ? blockIdx.x : blockIdx.y;
+  const int n = min(a.lens[i], a.Tw);
+  const float* ctx = a.ctx + (size_t)b * a.R * a.D;
+  const float* wi = a.words + (size_t)i * a.D * a.Tw;
+  float v[CPT][TMAXW];
+  pair_forward<CPT>(a, s, ctx, wi, n, v);
+  const int tid = threadIdx.x;
+  const size_t pair = a.paired ? (size_t)b : (size_t)b * a.NI + i;
+  if (tid == 0 && a.sims) {
+    float sum = 0.f;
+    for (int t = 0; t < n; ++t) sum += expf(a.g2 * s.cosv[t]);
+    a.sims[pair] = logf(sum);
+  }
+  if (a.wei_out) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * DT;
+      if (c < a.D)
+        for (int t = 0; t < n; ++t) a.wei_out[(pair * a.D + c) * a.Tw + t] = v[k][t];
+    }
+  }
+  if (a.attn_out) {
+    for (int j = tid; j < n * a.R; j += DT) {
+      int t = j / a.R, r = j - t * a.R;
+      a.attn_out[(pair * a.Tw + t) * a.R + r] = s.A2[t * (a.R + 1) + r];
+    }
+  }
+}
+
+// backward w.r.t. ctx: one CTA per image, loop over captions, d ctx accumulated in place (zeroed by the host)
+template <int CPT>
+__global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
+  extern __shared__ float sm[];
+  const PairSmem s = carve(sm, a.R, a.D);
+  float* dA = s.cosv + 4 * TMAXW;   // [TMAXW][R+1]: d a2 -> d(gamma1*a1) -> reused
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const float* ctx = a.ctx + (size_t)b * a.R * a.D;
+  float* dctx = a.dctx + (size_t)b * a.R * a.D;
+  const int ldw = TMAXW + 1;
+  for (int i = 0; i < a.NI; ++i) {
+    const float gsim = a.dsims[(size_t)b * a.NI + i];
+    const int n = min(a.lens[i], a.Tw);
+    const float* wi = a.words + (size_t)i * a.D * a.Tw;
+    float v[CPT][TMAXW];
+    __syncthreads();
+    pair_forward<CPT>(a, s, ctx, wi, n, v);
+    // d cos_t = gsim * gamma2 * softmax_t(gamma2 cos);  dv_t[c] = dcos_t (w_t/(|w||v|) - cos_t v_t/|v|^2)
+    float esum = 0.f;
+    for (int t = 0; t < n; ++t) esum += expf(a.g2 * s.cosv[t]);
+    float dv[CPT][TMAXW];
+#pragma unroll
+    for (int t = 0; t < TMAXW; ++t) {
+      float dcos = 0.f, inv_wv = 0.f, c_over_v2 = 0.f;
+      if (t < n) {
+        dcos = gsim * a.g2 * expf(a.g2 * s.cosv[t]) / esum;
+        const float nw = s.cosv[TMAXW + t], nv = s.cosv[2 * TMAXW + t];
+        if (nw * nv > a.eps) {   // clamp inactive (always, in practice)
+          inv_wv = 1.f / (nw * nv);
+          c_over_v2 = s.cosv[t] / (nv * nv);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int c = tid + k * DT;
+        dv[k][t] = (t < n && c < a.D) ? dcos * (s.w[c * ldw + t] * inv_wv - c_over_v2 * v[k][t]) : 0.f;
+      }
+    }
+    // stash dv in the (now free) w-shaped scratch?  w is still needed -> reuse S? S (a1) still needed.
+    // => keep dv in registers and compute d a2[t][r] = sum_c dv_t[c] ctx[r][c] with a block reduction per region chunk:
+    // write dv to global scratch-free path: use dA as [t][r] accumulators via warp-per-region dot products needs dv by
+    // channel across lanes, so stage dv through shared memory in slices of 32 words x D channels: reuse s.red? too small.
+    // Use the w buffer layout for dv (D x ldw) in a dedicated region appended after dA.
+    float* dvs = dA + (size_t)TMAXW * (a.R + 1);   // [D][TMAXW+1]
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * DT;
+      if (c < a.D)
+        for (int t = 0; t < n; ++t) dvs[c * ldw + t] = dv[k][t];
+    }
+    __syncthreads();
+    for (int r = wrp; r < a.R; r += DT / 32) {
+      float acc[TMAXW];
+#pragma unroll
+      for (int t = 0; t < TMAXW; ++t) acc[t] = 0.f;
+      for (int c = lane; c < a.D; c += 32) {
+        const float x = __ldg(ctx + (size_t)r * a.D + c);
+#pragma unroll
+        for (int t = 0; t < TMAXW; ++t)
+          if (t < n) acc[t] = fmaf(x, dvs[c * ldw + t], acc[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < TMAXW; ++t) {
+        if (t < n) {
+          float z = warp_sum(acc[t]);
+          if (lane == 0) dA[t * (a.R + 1) + r] = z;   // d a2[t][r]
+        }
+      }
+    }
+    __syncthreads();
+    // softmax-over-regions backward: d(gamma1 a1[r][t]) = a2 (da2 - <a2, da2>)  -> da1 = gamma1 * that
+    for (int t = wrp; t < n; t += DT / 32) {
+      float dot = 0.f;
+      for (int r = lane; r < a.R; r += 32) dot = fmaf(s.A2[t * (a.R + 1) + r], dA[t * (a.R + 1) + r], dot);
+      dot = warp_sum(dot);
+      for (int r = lane; r < a.R; r += 32)
+        dA[t * (a.R + 1) + r] = a.g1 * s.A2[t * (a.R + 1) + r] * (dA[t * (a.R + 1) + r] - dot);   // = d a1[r][t]
+    }
+    __syncthreads();
+    // softmax-over-words backward (per region): dS[r][t] = a1 (da1 - <a1, da1>), stored back into dA[t][r]
+    for (int r = tid; r < a.R; r += DT) {
+      float dot = 0.f;
+      for (int t = 0; t < n; ++t) dot = fmaf(s.S[r * ldw + t], dA[t * (a.R + 1) + r], dot);
+      for (int t = 0; t < n; ++t) dA[t * (a.R + 1) + r] = s.S[r * ldw + t] * (dA[t * (a.R + 1) + r] - dot);
+    }
+    __syncthreads();
+    // d ctx[r][c] += sum_t dv_t[c] a2[t][r] + dS[r][t] w[c][t]
+    for (int r = 0; r < a.R; ++r) {
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const int c = tid + k * DT;
+        if (c < a.D) {
+          float g = 0.f;
+#pragma unroll
+          for (int t = 0; t < TMAXW; ++t)
+            if (t < n) g = fmaf(dv[k][t], s.A2[t * (a.R + 1) + r], fmaf(dA[t * (a.R + 1) + r], s.w[c * ldw + t], g));
+          dctx[(size_t)r * a.D + c] += g;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mog
+
+using namespace mog;
+
+static int check_damsm(int B, int NI, int R, int D, int Tw, const char* who) {
+  MOG_REQUIRE(B > 0 && NI > 0 && R > 0 && D > 0 && Tw > 0, "%s: non-positive dims", who);
+  MOG_REQUIRE(Tw <= TMAXW && D <= DT * MAXCPT && R <= 2048, "%s: Tw=%d (<=32), D=%d (<=512), R=%d (<=2048) out of range", who, Tw, D, R);
+  MOG_REQUIRE(B <= 65535 && NI <= 65535, "%s: batch too large", who);
+  return MOG_OK;
+}
+
+extern "C" int mog_damsm_words_fwd(const float* ctx, const float* words, const int* lens, float* sims, float* wei_out,
+                                   float* attn_out, int B, int NI, int R, int D, int Tw, int paired, float gamma1,
+                                   float gamma2, void* stream) {
+  int rc = check_damsm(B, NI, R, D, Tw, "mog_damsm_words_fwd");
+  if (rc) return rc;
+  MOG_REQUIRE(ctx && words && lens && (sims || wei_out || attn_out), "mog_damsm_words_fwd: null tensor");
+  MOG_REQUIRE(!paired || B == NI, "mog_damsm_words_fwd: paired mode needs B == NI");
+  DamsmArgs a{ctx, words, lens, sims, wei_out, attn_out, nullptr, nullptr, B, NI, R, D, Tw, paired, gamma1, gamma2, 1e-8f};
+  const size_t smem = pair_smem_bytes(R, D);
+  auto kern = D <= DT ? damsm_fwd_kernel<1> : damsm_fwd_kernel<2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MOG_ERR_UNSUPPORTED, "mog_damsm_words_fwd: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+  dim3 grid(B, paired ? 1 : NI);
+  kern<<<grid, DT, smem, as_stream(stream)>>>(a);
+  return check_launch("damsm_fwd_kernel");
+}
+
+extern "C" int mog_damsm_words_bwd(const float* ctx, const float* words, const int* lens, const float* dsims, float* dctx,
+                                   int B, int NI, int R, int D, int Tw, float gamma1, float gamma2, void* stream) {
+  int rc = check_damsm(B, NI, R, D, Tw, "mog_damsm_words_bwd");
+  if (rc) return rc;
+  MOG_REQUIRE(ctx && words && lens && dsims && dctx, "mog_damsm_words_bwd: null tensor");
+  DamsmArgs a{ctx, words, lens, nullptr, nullptr, nullptr, dsims, dctx, B, NI, R, D, Tw, 0, gamma1, gamma2, 1e-8f};
+  const size_t smem = pair_smem_bytes(R, D) + sizeof(float) * (size_t)D * (TMAXW + 1);
+  auto kern = D <= DT ? damsm_bwd_kernel<1> : damsm_bwd_kernel<2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MOG_ERR_UNSUPPORTED, "mog_damsm_words_bwd: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(dctx, 0, sizeof(float) * (size_t)B * R * D, st);
+  kern<<<B, DT, smem, st>>>(a);
+  return check_launch("damsm_bwd_kernel");
+}

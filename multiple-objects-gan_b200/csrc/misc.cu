@@ -29,16 +29,22 @@ static int launch_transpose(const float* src, float* dst, int N, int rows, int c
 }
 
 // BCE(sigmoid(z), t) = -(t*max(log p, -100) + (1-t)*max(log(1-p), -100))   (torch.nn.BCELoss)
+// with_logits: BCEWithLogitsLoss, max(z,0) - z*t + log1p(exp(-|z|)) (stackgan/miscc/utils.py:77)
 __global__ void sigmoid_bce_fwd_kernel(const float* __restrict__ z, const float* __restrict__ tgt, float weight, int n,
-                                       float* prob, float* loss, int accumulate) {
+                                       float* prob, float* loss, int accumulate, int with_logits) {
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float p = sigmoidf_(z[i]);
     if (prob) prob[i] = p;
-    float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
     const float target = tgt[i];
-    s -= target * lp + (1.f - target) * lq;
+    if (with_logits) {
+      const float zz = z[i];
+      s += fmaxf(zz, 0.f) - zz * target + log1pf(expf(-fabsf(zz)));
+    } else {
+      float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+      s -= target * lp + (1.f - target) * lq;
+    }
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -54,13 +60,13 @@ __global__ void sigmoid_bce_fwd_kernel(const float* __restrict__ z, const float*
 }
 
 __global__ void sigmoid_bce_bwd_kernel(const float* __restrict__ z, const float* __restrict__ tgt, float weight, int n,
-                                       const float* __restrict__ gscale, float* __restrict__ dz) {
+                                       const float* __restrict__ gscale, float* __restrict__ dz, int with_logits) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float p = sigmoidf_(z[i]);
   // torch: grad_p = (p - t) / max((1-p)*p, 1e-12); sigmoid': p*(1-p)
   float pq = (1.f - p) * p;
-  float g = (p - tgt[i]) / fmaxf(pq, 1e-12f) * pq;
+  float g = with_logits ? (p - tgt[i]) : (p - tgt[i]) / fmaxf(pq, 1e-12f) * pq;
   dz[i] = g * weight * (gscale ? gscale[0] : 1.f) / (float)n;
 }
 
@@ -78,14 +84,14 @@ extern "C" int mog_nhwc_to_nchw(const float* src, float* dst, int N, int C, int 
 }
 
 extern "C" int mog_sigmoid_bce_fwd(const float* z, const float* target, float weight, int n, float* prob, float* loss,
-                                   int accumulate, void* stream) {
+                                   int accumulate, int with_logits, void* stream) {
   MOG_REQUIRE(z && target && loss && n > 0, "mog_sigmoid_bce_fwd: bad argument");
-  sigmoid_bce_fwd_kernel<<<1, 256, 0, as_stream(stream)>>>(z, target, weight, n, prob, loss, accumulate);
+  sigmoid_bce_fwd_kernel<<<1, 256, 0, as_stream(stream)>>>(z, target, weight, n, prob, loss, accumulate, with_logits);
   return check_launch("sigmoid_bce_fwd_kernel");
 }
 extern "C" int mog_sigmoid_bce_bwd(const float* z, const float* target, float weight, int n, const float* gscale,
-                                   float* dz, void* stream) {
+                                   float* dz, int with_logits, void* stream) {
   MOG_REQUIRE(z && target && dz && n > 0, "mog_sigmoid_bce_bwd: bad argument");
-  sigmoid_bce_bwd_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(z, target, weight, n, gscale, dz);
+  sigmoid_bce_bwd_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(z, target, weight, n, gscale, dz, with_logits);
   return check_launch("sigmoid_bce_bwd_kernel");
 }

@@ -56,8 +56,10 @@ SIGNATURES = {
     "mog_stn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_word_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mog_word_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "mog_sigmoid_bce_fwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _p]),
-    "mog_sigmoid_bce_bwd": (_i, [_p, _p, _f, _i, _p, _p, _p]),
+    "mog_damsm_words_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "mog_damsm_words_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "mog_sigmoid_bce_fwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _i, _p]),
+    "mog_sigmoid_bce_bwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _p]),
 }
 
 _lib = None

@@ -21,6 +21,16 @@ def conv1x1(in_planes, out_planes):
     return Conv2d(in_planes, out_planes, 1, 1, 0, bias=False)
 
 
+def func_attention(query, context, gamma1):
+    """GlobalAttention.py:31-69 -- query: batch x ndf x queryL, context: batch x ndf x ih x iw ->
+    (weightedContext batch x ndf x queryL, attn batch x queryL x ih x iw).  Forward only here; the
+    training path uses the fused ``miscc.losses.words_loss``."""
+    ctx = ops.nhwc(context)
+    B, ih, iw, D = ctx.shape
+    wei, attn = ops.func_attention_paired(query, ctx.reshape(B, ih * iw, D), gamma1)
+    return wei, attn.reshape(B, -1, ih, iw)
+
+
 class GlobalAttentionGeneral(nn.Module):
     def __init__(self, idf, cdf):
         super().__init__()

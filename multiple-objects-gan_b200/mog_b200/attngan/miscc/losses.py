@@ -88,9 +88,42 @@ def KL_loss(mu, logvar):
     return torch.mean(KLD_element).mul(-0.5)
 
 
+def _class_masks(class_ids, batch_size, device):
+    """losses.py:24-34 -- mis-match samples of the same class are masked out of the negatives."""
+    import numpy as np
+    ids = np.asarray(class_ids)
+    m = (ids[:, None] == ids[None, :])
+    m[np.arange(batch_size), np.arange(batch_size)] = False
+    return torch.from_numpy(m).to(device)
+
+
 def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size):
-    raise NotImplementedError("DAMSM words_loss: fused all-pairs kernel is the next scope row (SURVEY 8 a18)")
+    """losses.py:62-132 -- the caption loop + func_attention + cosine + log-sum-exp is ONE fused kernel
+    (``mog_damsm_words_fwd/bwd``); only the final B x B cross-entropies are left to torch.  The attention
+    maps (third return value, used for visualisation only) are not produced: ``None``."""
+    feat = ops.nhwc(img_features)
+    B, ih, iw, D = feat.shape
+    sims = ops.damsm_similarities(feat.reshape(B, ih * iw, D), words_emb, torch.as_tensor(cap_lens),
+                                  cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2)
+    similarities = sims * cfg.TRAIN.SMOOTH.GAMMA3
+    if class_ids is not None:
+        similarities = similarities.masked_fill(_class_masks(class_ids, batch_size, similarities.device), -float('inf'))
+    if labels is None:
+        return None, None, None
+    ce = torch.nn.functional.cross_entropy
+    return ce(similarities, labels), ce(similarities.transpose(0, 1), labels), None
 
 
 def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8):
-    raise NotImplementedError("DAMSM sent_loss: next scope row (SURVEY 8 a19)")
+    """losses.py:20-59 -- B x B cosine matrix (GEMM through libmog) * gamma3, two cross-entropies."""
+    cnn_code = cnn_code.contiguous()
+    rnn_code = rnn_code.detach().contiguous()
+    cnn_norm = torch.norm(cnn_code, 2, dim=1, keepdim=True)
+    rnn_norm = torch.norm(rnn_code, 2, dim=1, keepdim=True)
+    scores0 = ops.linear(cnn_code, rnn_code) / (cnn_norm * rnn_norm.transpose(0, 1)).clamp(min=eps) * cfg.TRAIN.SMOOTH.GAMMA3
+    if class_ids is not None:
+        scores0 = scores0.masked_fill(_class_masks(class_ids, batch_size, scores0.device), -float('inf'))
+    if labels is None:
+        return None, None
+    ce = torch.nn.functional.cross_entropy
+    return ce(scores0, labels), ce(scores0.transpose(0, 1), labels)

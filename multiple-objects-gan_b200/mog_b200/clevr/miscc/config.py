@@ -1,0 +1,26 @@
+"""Global ``cfg`` of the clevr program: keys and defaults of ``code/clevr/miscc/config.py``."""
+from ..._cfg_util import edict, make_cfg
+
+
+def _defaults():
+    c = edict()
+    c.DATASET_NAME = 'clevr'
+    c.CONFIG_NAME = ''
+    c.GPU_ID = '0'
+    c.CUDA = True
+    c.WORKERS = 6
+    c.NET_G = ''
+    c.NET_D = ''
+    c.DATA_DIR = ''
+    c.VIS_COUNT = 64
+    c.Z_DIM = 100
+    c.IMSIZE = 64
+    c.USE_LOCAL_PATHWAY = True
+    c.USE_BBOX_LAYOUT = True
+    c.TRAIN = edict(FLAG=True, BATCH_SIZE=64, MAX_EPOCH=600, SNAPSHOT_INTERVAL=50, PRETRAINED_MODEL='',
+                    PRETRAINED_EPOCH=600, LR_DECAY_EPOCH=600, DISCRIMINATOR_LR=2e-4, GENERATOR_LR=2e-4)
+    c.GAN = edict(CONDITION_DIM=128, DF_DIM=64, GF_DIM=128, R_NUM=4)
+    return c
+
+
+cfg, cfg_from_file, reset_cfg = make_cfg(_defaults)

@@ -378,7 +378,7 @@ def word_attention(h, src, mask=None, mask_quirk=True, want_attn=True):
 # ---------------------------------------------------------------------------------------------
 class SigmoidBceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, target, weight):
+    def forward(ctx, z, target, weight, with_logits):
         z = z.contiguous()
         _chk(z, "bce logits")
         target = target.detach().to(torch.float32).contiguous()
@@ -387,8 +387,9 @@ class SigmoidBceFn(torch.autograd.Function):
             raise RuntimeError("bce: %d logits vs %d targets" % (z.numel(), target.numel()))
         loss = torch.empty(1, device=z.device, dtype=torch.float32)
         call("mog_sigmoid_bce_fwd", z.data_ptr(), target.data_ptr(), float(weight), z.numel(), None,
-             loss.data_ptr(), 0, _stream())
+             loss.data_ptr(), 0, int(with_logits), _stream())
         ctx.weight = float(weight)
+        ctx.with_logits = int(with_logits)
         ctx.save_for_backward(z, target)
         return loss.reshape(())
 
@@ -398,13 +399,14 @@ class SigmoidBceFn(torch.autograd.Function):
         g = g.contiguous().reshape(1)
         dz = torch.empty_like(z)
         call("mog_sigmoid_bce_bwd", z.data_ptr(), target.data_ptr(), ctx.weight, z.numel(), g.data_ptr(),
-             dz.data_ptr(), _stream())
-        return dz, None, None
+             dz.data_ptr(), ctx.with_logits, _stream())
+        return dz, None, None, None
 
 
-def sigmoid_bce(z, target, weight: float = 1.0):
-    """weight * mean BCE(sigmoid(z), target)   (nn.Sigmoid + nn.BCELoss of the reference heads)."""
-    return SigmoidBceFn.apply(z, target, weight)
+def sigmoid_bce(z, target, weight: float = 1.0, with_logits: bool = False):
+    """weight * mean BCE(sigmoid(z), target): nn.Sigmoid + nn.BCELoss of the AttnGAN heads, or
+    (with_logits) nn.BCEWithLogitsLoss of the StackGAN / CLEVR / Multi-MNIST programs."""
+    return SigmoidBceFn.apply(z, target, weight, with_logits)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -437,3 +439,54 @@ class ActFn(torch.autograd.Function):
 
 def activation(x, act):
     return ActFn.apply(x, act)
+
+
+# ---------------------------------------------------------------------------------------------
+# DAMSM word-region matching
+# ---------------------------------------------------------------------------------------------
+class DamsmSimsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, words, lens, g1, g2):
+        _chk(feat, "damsm region features")
+        words = words.detach().contiguous()
+        _chk(words, "damsm words")
+        B, R, D = feat.shape
+        NI, D2, Tw = words.shape
+        if D != D2:
+            raise RuntimeError("damsm: feature dim %d vs word dim %d" % (D, D2))
+        lens = lens.to(device=feat.device, dtype=torch.int32).contiguous()
+        sims = torch.empty((B, NI), device=feat.device, dtype=torch.float32)
+        call("mog_damsm_words_fwd", feat.data_ptr(), words.data_ptr(), lens.data_ptr(), sims.data_ptr(), None, None,
+             B, NI, R, D, Tw, 0, float(g1), float(g2), _stream())
+        ctx.cfg = (B, NI, R, D, Tw, float(g1), float(g2))
+        ctx.save_for_backward(feat, words, lens)
+        return sims
+
+    @staticmethod
+    def backward(ctx, dsims):
+        feat, words, lens = ctx.saved_tensors
+        B, NI, R, D, Tw, g1, g2 = ctx.cfg
+        dsims = dsims.contiguous()
+        dfeat = torch.empty_like(feat)
+        call("mog_damsm_words_bwd", feat.data_ptr(), words.data_ptr(), lens.data_ptr(), dsims.data_ptr(),
+             dfeat.data_ptr(), B, NI, R, D, Tw, g1, g2, _stream())
+        return dfeat, None, None, None, None
+
+
+def damsm_similarities(feat, words, lens, gamma1, gamma2):
+    """feat [B,R,D] (NHWC regions), words [NI,D,Tw], lens [NI] -> sims [B,NI] (before gamma3)."""
+    return DamsmSimsFn.apply(feat, words, lens, gamma1, gamma2)
+
+
+def func_attention_paired(query, context_nhwc, gamma1):
+    """GlobalAttention.func_attention for pairs (b, b): query [B,D,Tq], context [B,R,D] ->
+    (weightedContext [B,D,Tq], attn [B,Tq,R]).  Forward only."""
+    B, R, D = context_nhwc.shape
+    Tq = query.shape[2]
+    q = query.detach().contiguous()
+    lens = torch.full((B,), Tq, device=q.device, dtype=torch.int32)
+    wei = torch.zeros((B, D, Tq), device=q.device, dtype=torch.float32)
+    attn = torch.zeros((B, Tq, R), device=q.device, dtype=torch.float32)
+    call("mog_damsm_words_fwd", context_nhwc.detach().contiguous().data_ptr(), q.data_ptr(), lens.data_ptr(), None,
+         wei.data_ptr(), attn.data_ptr(), B, B, R, D, Tq, 1, float(gamma1), 1.0, _stream())
+    return wei, attn

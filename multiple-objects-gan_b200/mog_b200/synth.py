@@ -146,3 +146,42 @@ class StandInEncoder:
         feat = F.conv2d(F.adaptive_avg_pool2d(img, 17), self.w_feat)
         code = F.linear(F.adaptive_avg_pool2d(img, 4).reshape(img.shape[0], -1), self.w_code)
         return feat, code
+
+
+def stage1_batch(program: str, B: int, nz: int = 100, seed: int = 1234) -> dict:
+    """Synthetic batch for the single-stage programs (SURVEY.md section 8(d) "other configs").
+    multi-mnist: images U(-1,1) Bx1x64x64, 3 objects always valid, w in [10,20)/64, h in [16,20)/64
+    (multi-mnist/trainer.py:236-237), labels one-hot over 10.
+    clevr: Bx3x64x64, 4 slots with 2-4 valid objects, label = one-hot4(shape) + one-hot9(colour); an empty
+    slot has bbox -1 and an all -1 label row (clevr/miscc/datasets.py:54-80, cf. the clamp at
+    clevr/miscc/utils.py:99)."""
+    rng = np.random.RandomState(seed)
+    mn = program in ("mnist", "multi-mnist", "multi_mnist")
+    S, L, C = (3, 10, 1) if mn else (4, 13, 3)
+    out = {"noise": rng.standard_normal((B, nz)).astype(np.float32),
+           "imgs": rng.uniform(-1, 1, size=(B, C, 64, 64)).astype(np.float32)}
+    bbox = -np.ones((B, S, 4), np.float32)
+    label = np.zeros((B, S, L), np.float32)
+    for b in range(B):
+        k = S if mn else int(rng.randint(2, S + 1))
+        for s in range(S):
+            if s < k:
+                if mn:
+                    w, h = rng.randint(10, 20) / 64.0, rng.randint(16, 20) / 64.0
+                else:
+                    w, h = rng.uniform(0.15, 0.5, size=2)
+                x, y = rng.uniform(0.0, 0.999 - w), rng.uniform(0.0, 0.999 - h)
+                bbox[b, s] = (x, y, w, h)
+                if mn:
+                    label[b, s, rng.randint(0, 10)] = 1.0
+                else:
+                    label[b, s, rng.randint(0, 4)] = 1.0
+                    label[b, s, 4 + rng.randint(0, 9)] = 1.0
+            else:
+                label[b, s, :] = -1.0
+    flat = bbox.reshape(-1, 4)
+    out["bbox"] = bbox
+    out["label_one_hot"] = label
+    out["transf_matrices"] = transformation_matrix(flat).reshape(B, S, 2, 3)
+    out["transf_matrices_inv"] = transformation_matrix_inverse(flat).reshape(B, S, 2, 3)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}

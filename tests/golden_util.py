@@ -63,3 +63,18 @@ def full(summ, key):
     """A fully stored golden tensor as torch tensor."""
     s = summ[key]
     return torch.from_numpy(np.asarray(s["full"], np.float32).reshape(s["shape"]).copy())
+
+
+def save(name, entries, meta):
+    """Write tests/golden/<name>.npz (+ .json index) from a dict of summarize() results."""
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    arrays, index = {}, {}
+    for k, s in entries.items():
+        index[k] = {"shape": s["shape"], "l2": s["l2"], "sum": s["sum"], "kind": "full" if "full" in s else "sample"}
+        arrays[k] = s["full"] if "full" in s else s["sample"]
+    np.savez_compressed(os.path.join(here, name + ".npz"), **arrays)
+    with open(os.path.join(here, name + ".json"), "w") as f:
+        json.dump({"meta": meta, "index": index}, f, indent=1, sort_keys=True)
+    print("wrote", name, "entries", len(entries), "bytes", os.path.getsize(os.path.join(here, name + ".npz")))

@@ -269,3 +269,35 @@ def test_abi_errors_are_loud():
     assert L.mog_conv_out_hw(C.byref(d), None, None) == -1
     with pytest.raises(RuntimeError):
         ops.conv2d(torch.zeros(1, 4, 4, 8), torch.zeros(8, 8, 3, 3))
+
+
+def test_damsm_losses_golden():
+    """Fused words_loss (+ sent_loss) against the reference's miscc/losses.py on synthetic features."""
+    from mog_b200.attngan.miscc import losses as L
+    from mog_b200.attngan.miscc.config import cfg, reset_cfg
+    reset_cfg()
+    cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2, cfg.TRAIN.SMOOTH.GAMMA3 = 4.0, 5.0, 10.0
+    G, _ = gu.load("attention_cases")
+    feat = gu.full(G, "damsm/feat").cuda().requires_grad_(True)
+    code = gu.full(G, "damsm/code").cuda().requires_grad_(True)
+    words, sent = gu.full(G, "damsm/words").cuda(), gu.full(G, "damsm/sent").cuda()
+    lens = gu.full(G, "damsm/lens").long()
+    B = feat.shape[0]
+    labels = torch.arange(B, device="cuda")
+    w0, w1, _ = L.words_loss(feat, words, labels, lens, np.arange(B), B)
+    s0, s1 = L.sent_loss(code, sent, labels, np.arange(B), B)
+    for k, v in {"w0": w0, "w1": w1, "s0": s0, "s1": s1}.items():
+        gu.check(v, G["damsm/" + k], 2e-5, k)
+    (w0 + w1 + s0 + s1).backward()
+    gu.check(feat.grad, G["damsm/dfeat"], 1e-4, "dfeat")
+    gu.check(code.grad, G["damsm/dcode"], 1e-4, "dcode")
+    reset_cfg()
+
+
+def test_func_attention_matches_oracle():
+    from mog_b200.attngan.GlobalAttention import func_attention
+    q = rnd(3, 32, 7, seed=1)
+    c = rnd(3, 32, 17, 17, seed=2)
+    wref, aref = O.func_attention(q, c, 4.0)
+    w, a = func_attention(q.cuda(), c.cuda(), 4.0)
+    assert rel(w, wref) < 1e-5 and rel(a, aref) < 1e-5
