@@ -51,14 +51,6 @@ struct TcParams {
   int kc_per_split;
 };
 
-__device__ __forceinline__ float epi_act(float v, int act) {
-  if (act == MOG_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
-  if (act == MOG_ACT_TANH) return tanhf(v);
-  if (act == MOG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == MOG_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-  return v;
-}
-
 template <bool PLANES>
 __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -309,32 +301,14 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
     const int cbeg = (warp >> 2) ? (ncol16 + 1) / 2 : 0;     // warps 4-7 take the upper column half
     const int cend = (warp >> 2) ? ncol16 : (ncol16 + 1) / 2;
     const bool raw = p.partial != nullptr;
+    const bool vec = (g.Cd & 3) == 0;
     for (int cb = cbeg; cb < cend; ++cb) {
       const int c0 = cb * 16;
       uint32_t acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
-      if (e_ok) {
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v0 = __uint_as_float(acc[j]);
-          if (!raw) {
-            float b = (g.bias && n0 + c0 + j < g.Cd) ? __ldg(g.bias + n0 + c0 + j) : 0.f;
-            if (g.accum_dst && n0 + c0 + j < g.Cd) b += dptr[c0 + j];
-            v0 = epi_act(v0 + b, g.act);
-          }
-          o[j] = v0;
-        }
-        if (((g.Cd & 3) == 0) && n0 + c0 + 15 < g.Cd) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(dptr + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < g.Cd) dptr[c0 + j] = o[j];
-        }
-      }
+      if (e_ok && n0 + c0 < g.Cd)
+        epi_store16(acc, dptr + c0, (!raw && g.bias) ? g.bias + n0 + c0 : nullptr, g.Cd - n0 - c0, vec, !raw && g.accum_dst != 0,
+                    raw ? (int)MOG_ACT_NONE : g.act);
     }
   } else {
     // ===================== MMA issuer (warp 8) ==============================================
@@ -368,6 +342,14 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  if (act == MOG_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  if (act == MOG_ACT_TANH) return tanhf(v);
+  if (act == MOG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MOG_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
 }
 
 // split-K reduce: dst[pix(m), n] = act(sum_z partial[z][m][n] + bias[n])

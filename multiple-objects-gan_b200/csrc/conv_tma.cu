@@ -58,14 +58,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
-__device__ __forceinline__ float tma_epi_act(float v, int act) {
-  if (act == MOG_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
-  if (act == MOG_ACT_TANH) return tanhf(v);
-  if (act == MOG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == MOG_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-  return v;
-}
-
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TmaConvParams p) {
@@ -198,44 +190,26 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       mbar_wait(&tfull[as], aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t acc[16];
-        tmem_ld16(taddr + (uint32_t)c0, acc);
-        if (ok) {
-          float o[16];
-          const bool vec = ((p.Cd & 3) == 0) && n0c + c0 + 15 < p.Cd;
-          if (p.accum_dst) {
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 prev = *reinterpret_cast<const float4*>(dptr + c0 + j);
-                o[j] = prev.x; o[j + 1] = prev.y; o[j + 2] = prev.z; o[j + 3] = prev.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = (n0c + c0 + j < p.Cd) ? dptr[c0 + j] : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float b = (p.bias && n0c + c0 + j < p.Cd) ? __ldg(p.bias + n0c + c0 + j) : 0.f;
-            o[j] = tma_epi_act(o[j] + __uint_as_float(acc[j]) + b, p.act);
-          }
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(dptr + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0c + c0 + j < p.Cd) dptr[c0 + j] = o[j];
-          }
+      // software-pipelined TMEM reads: the load of group g+1 is in flight while group g is stored
+      const int ngrp = p.BN / 16;
+      const bool vec = (p.Cd & 3) == 0;
+      uint32_t acc[2][16];
+      tmem_ld16_async(taddr, acc[0]);
+#pragma unroll 1
+      for (int gq = 0; gq < ngrp; gq += 2) {
+        tmem_ld_wait(acc[0]);
+        if (gq + 1 < ngrp) tmem_ld16_async(taddr + (uint32_t)((gq + 1) * 16), acc[1]);
+        if (ok && n0c + gq * 16 < p.Cd)
+          epi_store16(acc[0], dptr + gq * 16, p.bias ? p.bias + n0c + gq * 16 : nullptr, p.Cd - n0c - gq * 16, vec, p.accum_dst != 0, p.act);
+        if (gq + 1 < ngrp) {
+          tmem_ld_wait(acc[1]);
+          if (gq + 2 < ngrp) tmem_ld16_async(taddr + (uint32_t)((gq + 2) * 16), acc[0]);
+          if (ok && n0c + (gq + 1) * 16 < p.Cd)
+            epi_store16(acc[1], dptr + (gq + 1) * 16, p.bias ? p.bias + n0c + (gq + 1) * 16 : nullptr, p.Cd - n0c - (gq + 1) * 16, vec,
+                        p.accum_dst != 0, p.act);
         }
       }
-      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): release the accumulator
+      // all TMEM reads of this warp are complete (every load was waited for): release the accumulator
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "common.cuh"
+
 namespace mog {
 namespace tc {
 
@@ -91,6 +93,94 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Asynchronous variant: the registers are valid only after tmem_ld_wait(r) (which names them as in/out operands
+// so the compiler cannot schedule a use above the wait).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// Epilogue math on a group of 16 consecutive output channels of one row: v = act(acc + prev + bias).
+// The activation switch is uniform and sits OUTSIDE the element loop (a per-element switch costs ~20
+// instructions and an indirect branch per value and made the epilogue the bottleneck of the conv kernels).
+__device__ __forceinline__ void epi_act16(float (&o)[16], int act) {
+  switch (act) {
+    case MOG_ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : 0.2f * o[j];
+      break;
+    case MOG_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+      break;
+    case MOG_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = tanhf(o[j]);
+      break;
+    case MOG_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = 1.0f / (1.0f + expf(-o[j]));
+      break;
+    default:
+      break;
+  }
+}
+// Stores one 16-channel group of an output row: dptr points at channel c of the row, `nvalid` channels exist from
+// there on (>= 16 for interior groups).  vec: the row pitch and c allow 16-byte accesses.
+__device__ __forceinline__ void epi_store16(const uint32_t (&acc)[16], float* dptr, const float* bias_c, int nvalid, bool vec,
+                                            bool accum_dst, int act) {
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]);
+  const bool full = vec && nvalid >= 16;
+  if (accum_dst) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(dptr + j);
+        o[j] += pv.x; o[j + 1] += pv.y; o[j + 2] += pv.z; o[j + 3] += pv.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) o[j] += dptr[j];
+    }
+  }
+  if (bias_c) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_c + j));
+        o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) o[j] += __ldg(bias_c + j);
+    }
+  }
+  if (act != MOG_ACT_NONE) epi_act16(o, act);
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dptr + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) dptr[j] = o[j];
+  }
 }
 
 // ---- UMMA descriptors ----------------------------------------------------------------------
