@@ -373,7 +373,11 @@ extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   if (validate(d, "mog_conv_workspace_bytes")) return 0;
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
-  if (which == 2) return use_tc(d) ? tc_wgrad_workspace_bytes(*d, Ho, Wo) : wgrad_ffma_workspace_bytes(*d, Ho, Wo);
+  if (which == 2) {
+    if (!use_tc(d)) return wgrad_ffma_workspace_bytes(*d, Ho, Wo);
+    const size_t a = tc_wgrad_workspace_bytes(*d, Ho, Wo), b = wgrad_halo_workspace_bytes(*d, Ho, Wo, passes_of(d));
+    return a > b ? a : b;
+  }
   if (which != 0 && which != 1) return 0;
   if (!use_tc(d)) return which == 1 ? dgrad_up_bytes(d, d->up2x) : 0;
   Problem probs[16];
@@ -425,6 +429,7 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
   if (rc) return rc;
   MOG_REQUIRE((dy || dy_planes) && wt && dx, "mog_conv2d_dgrad: null tensor");
   cudaStream_t st = as_stream(stream);
+  if (use_tc(d) && dy && patch_dgrad_eligible(*d)) return launch_patch_dgrad(*d, dy, wt, dx, passes_of(d), st);
   Problem probs[16];
   int hires;
   const int n = build_dgrad(d, probs, &hires);
@@ -474,6 +479,13 @@ extern "C" int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const void
       MOG_REQUIRE(x && dy, "mog_conv2d_wgrad: give both operands as planes or both as fp32 tensors");
       if ((d->Cin % 8) || (d->Cout % 8))
         return fail(MOG_ERR_UNSUPPORTED, "mog_conv2d_wgrad: %d/%d channels need pre-split planes in tcgen05 precision", d->Cin, d->Cout);
+    }
+    if (planes && wgrad_halo_eligible(*d, Ho, Wo, passes_of(d))) {
+      // halo-tile kernel: x staged once per filter column, reduce + OIHW scatter included
+      rc = launch_wgrad_halo(*d, Ho, Wo, x_planes, dy_planes, dw, ws, passes_of(d), st);
+      if (rc) return rc;
+      if (dbias) return launch_colsum(dy, dbias, (long long)d->N * Ho * Wo, d->Cout, st);
+      return MOG_OK;
     }
     CinP = planes ? p8(d->Cin) : d->Cin;
     rc = launch_wgrad_tc(*d, Ho, Wo, x, dy, planes ? x_planes : nullptr, (size_t)d->N * d->H * d->W * p8(d->Cin),

@@ -48,6 +48,8 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* 
                     cudaStream_t st);
 size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int passes);
 bool tc_wgrad_eligible(const MogConvDesc& d, bool planes);
+bool patch_dgrad_eligible(const MogConvDesc& d);
+int launch_patch_dgrad(const MogConvDesc& d, const float* dy, const void* packed, float* dx, int passes, cudaStream_t st);
 // TMA-staged persistent kernel (conv_tma.cu)
 bool tma_shape_eligible(const IGemmParams& g);
 int tma_tap_pitch(int Cs);
@@ -58,6 +60,11 @@ size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
 int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, const void* x_planes,
                     size_t x_plane_elems, const void* dy_planes, size_t dy_plane_elems, float* ws, int passes,
                     int* splits_out, cudaStream_t st);
+// halo-tile weight gradient (wgrad_halo.cu)
+bool wgrad_halo_eligible(const MogConvDesc& d, int Ho, int Wo, int passes);
+size_t wgrad_halo_workspace_bytes(const MogConvDesc& d, int Ho, int Wo, int passes);
+int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes, const void* dy_planes, float* dw, float* ws,
+                      int passes, cudaStream_t st);
 int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st);
 
 }  // namespace mog

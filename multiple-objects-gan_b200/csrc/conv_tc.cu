@@ -407,6 +407,42 @@ __global__ void pack_tc_kernel(const PackArgs a) {
   if (a.lo) a.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// Data gradient of a non-overlapping strided conv (stride == KH == KW, pad == 0, e.g. the 4x4/s4 logit heads,
+// model.py:627,640) with a handful of output channels: every dx pixel sees exactly one tap,
+//   dx[n, ho*s + kh, wo*s + kw, ci] = sum_co dy[n, ho, wo, co] * w[co, ci, kh, kw]
+// One CUDA-core pass instead of s*s tensor-core launches with M = N*Ho*Wo rows each.  The weights are read
+// from the per-phase packed buffer (hi + lo planes [Npad][Kpad], phase = kh*s + kw, k = co).
+struct PatchDgradArgs {
+  const float* dy;
+  const __nv_bfloat16* packed;
+  float* dx;
+  int N, Ho, Wo, Cout, Cin, s;
+  int Kpad;
+  size_t plane_elems, phase_elems;   // elements per plane / per phase block (all planes, incl. alignment)
+  int planes;
+};
+__global__ void patch_dgrad_kernel(const PatchDgradArgs a) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int H = a.Ho * a.s, W = a.Wo * a.s;
+  const size_t total = (size_t)a.N * H * W * a.Cin;
+  if (idx >= total) return;
+  const int ci = (int)(idx % a.Cin);
+  size_t r = idx / a.Cin;
+  const int w = (int)(r % W); r /= W;
+  const int h = (int)(r % H);
+  const int n = (int)(r / H);
+  const int ho = h / a.s, kh = h - ho * a.s, wo = w / a.s, kw = w - wo * a.s;
+  const __nv_bfloat16* wp = a.packed + (size_t)(kh * a.s + kw) * a.phase_elems + (size_t)ci * a.Kpad;
+  const float* dyp = a.dy + (((size_t)n * a.Ho + ho) * a.Wo + wo) * a.Cout;
+  float acc = 0.f;
+  for (int co = 0; co < a.Cout; ++co) {
+    float wv = __bfloat162float(wp[co]);
+    if (a.planes == 2) wv += __bfloat162float(wp[a.plane_elems + co]);
+    acc += __ldg(dyp + co) * wv;
+  }
+  a.dx[idx] = acc;
+}
+
 // fp32 [rows][C] -> bf16 planes [rows][CP] (hi, and lo = bf16(x - hi) when nplanes == 2); CP = C rounded up
 // to 8, pad channels zero.  One thread per 8-channel chunk.
 __global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int C, int CP, __nv_bfloat16* hi,
@@ -481,6 +517,25 @@ size_t tc_packed_bytes(int ntaps, int Cs, int Cd, int passes) {
   return (b + 255) / 256 * 256;  // keep every phase 256-byte aligned
 }
 
+
+bool patch_dgrad_eligible(const MogConvDesc& d) {
+  return !d.up2x && d.stride > 1 && d.stride == d.KH && d.stride == d.KW && d.pad == 0 && d.Cout <= 8 && (d.H % d.stride) == 0 &&
+         (d.W % d.stride) == 0 && (long long)d.N * (d.H / d.stride) * (d.W / d.stride) < 8192;   // (small M: packed with pitch p8)
+}
+
+// packed: the dgrad weight buffer of mog_pack_weight (one block per stride phase, each one tap, pitch p8(Cout))
+int launch_patch_dgrad(const MogConvDesc& d, const float* dy, const void* packed, float* dx, int passes, cudaStream_t st) {
+  const int pitch = ceil_div(d.Cout, 8) * 8;
+  TcWeightLayout L = tc_weight_layout(1, pitch, d.Cin, passes);
+  PatchDgradArgs a;
+  a.dy = dy; a.packed = static_cast<const __nv_bfloat16*>(packed); a.dx = dx;
+  a.N = d.N; a.Ho = d.H / d.stride; a.Wo = d.W / d.stride; a.Cout = d.Cout; a.Cin = d.Cin; a.s = d.stride;
+  a.Kpad = L.Kpad; a.plane_elems = L.plane_elems; a.planes = L.planes;
+  a.phase_elems = tc_packed_bytes(1, pitch, d.Cin, passes) / 2;
+  const size_t total = (size_t)d.N * d.H * d.W * d.Cin;
+  patch_dgrad_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(a);
+  return check_launch("patch_dgrad_kernel");
+}
 
 // k = local_tap * pitch + c  (pitch >= channel count, multiple of 8; channels beyond the real count are zero)
 int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,

@@ -145,20 +145,21 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(&full[s], ph);
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t a_hi = st, a_lo = st + a_plane;
-          const uint32_t b_hi = st + nplanes * a_plane, b_lo = b_hi + b_plane;
-          for (int pass = 0; pass < p.passes; ++pass) {
-            const uint32_t ab = pass == 1 ? a_lo : a_hi;   // 0: hi*hi   1: lo*hi   2: hi*lo
-            const uint32_t bb = pass == 2 ? b_lo : b_hi;
+        // all lanes run this (uniform registers); one elected lane issues inside umma_bf16_elect
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = desc_lo(st, 16), a_lo = desc_lo(st + a_plane, 16);
+        const uint32_t b_hi = desc_lo(st + nplanes * a_plane, 16), b_lo = desc_lo(st + nplanes * a_plane + b_plane, 16);
+        const uint32_t dhi = desc_hi_sw128(1024);
 #pragma unroll
-            for (int k16 = 0; k16 < BK / 16; ++k16)
-              umma_bf16(tacc, make_desc_sw128(ab + k16 * 32), make_desc_sw128(bb + k16 * 32), idesc, (kc | pass | k16) != 0);
-          }
-          umma_commit(&empty[s]);
-          if (kc == nk - 1) umma_commit(&tfull[as]);
+        for (int k16 = 0; k16 < BK / 16; ++k16) umma_bf16_elect(tacc, a_hi + 2 * k16, dhi, b_hi + 2 * k16, dhi, idesc, (kc | k16) != 0);
+        if (p.passes == 3) {
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) umma_bf16_elect(tacc, a_lo + 2 * k16, dhi, b_hi + 2 * k16, dhi, idesc, 1u);   // lo*hi
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) umma_bf16_elect(tacc, a_hi + 2 * k16, dhi, b_lo + 2 * k16, dhi, idesc, 1u);   // hi*lo
         }
+        umma_commit_elect(&empty[s]);
+        if (kc == nk - 1) umma_commit_elect(&tfull[as]);
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }

@@ -214,6 +214,41 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// ---- warp-convergent issue ---------------------------------------------------------------------
+// The MMA warp runs its loops with ALL lanes (warp-uniform values stay in uniform registers, which is what
+// UTCHMMA reads); one elected lane executes the tcgen05 instruction itself.  Wrapping the loop in
+// `if (lane == 0)` instead makes the compiler move every descriptor / TMEM address from vector to uniform
+// registers through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop per MMA (~100+ cycles: issue-bound at N <= 128).
+// 64-bit descriptors are passed as (lo, hi) words: hi is constant per layout, lo = start address field | LBO.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+// hi word: SBO>>4 | version 1 (bit 46) | layout (bits 61-63; 2 = SWIZZLE_128B)
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05 async ops of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -48,6 +48,12 @@ TC_CASES = [
     (2, 9, 9, 25, 12, 3, 2, 1, False, False, 0),      # bbox_net: 25 -> 12, odd spatial size
     (5, 1, 1, 181, 100, 1, 1, 0, False, False, 0),    # label Linear 181 -> 100
     (4, 4, 4, 64, 1, 4, 4, 0, False, True, 0),        # outlogits: Cout=1 (dgrad gathers 1 -> 8 channels)
+    # halo-tile weight gradient (wgrad_halo.cu): several M / N channel blocks, ragged pixel grids, views
+    (2, 24, 40, 192, 384, 3, 1, 1, False, False, 0),  # 3 M blocks x 2 N blocks of 96, 3 x 5 pixel tiles per image
+    (2, 16, 16, 200, 136, 3, 1, 1, True, False, 0),   # sub-pixel phases, channel blocks with ragged tails
+    (1, 32, 32, 64, 64, 4, 2, 1, False, False, 0),    # stride 2: x through its 4 parity views, 2 x 2 taps each
+    (2, 12, 20, 48, 3, 3, 1, 1, False, False, 0),     # Cout=3: operand roles swapped (x on M, dy on N)
+    (3, 20, 12, 24, 16, 1, 1, 0, False, False, 0),    # 1x1 conv: single tap, single group
 ]
 
 
