@@ -11,8 +11,9 @@
 //       * stride-s conv = s*s unit-stride convs over the parity views of x, accumulated (when the
 //         grid is big enough for the TMA kernel), its data gradient = one unit-stride problem per
 //         stride phase of dx.
-//       * each problem runs on the persistent TMA-staged kernel (conv_tma.cu) when its shape allows,
-//         else on the generic gather kernel with split-K (conv_tc.cu).
+//       * each problem runs on the persistent halo-tile TMA kernel (conv_halo.cu) when its shape allows
+//         (problems that accumulate into the same pixels - parity views - are merged into ONE launch whose
+//         K loop runs over all views), else on the generic gather kernel with split-K (conv_tc.cu).
 //     Operands are pre-split bf16 planes (mog_split_planes) or, for the generic kernel only, fp32
 //     tensors split on the fly (channel count multiple of 8).
 #include "conv_common.cuh"
@@ -213,7 +214,7 @@ static int build_fwd(const MogConvDesc* d, Problem* out) {
   }
   if (d->stride > 1 && !d->up2x && (d->H % d->stride) == 0 && (d->W % d->stride) == 0) {
     Problem probe;
-    if (strided_view(d, pmod(-d->pad, d->stride), pmod(-d->pad, d->stride), &probe) && tma_shape_eligible(probe.g)) {
+    if (strided_view(d, pmod(-d->pad, d->stride), pmod(-d->pad, d->stride), &probe) && halo_shape_eligible(probe.g)) {
       int n = 0;
       for (int a = 0; a < d->stride; ++a)
         for (int b = 0; b < d->stride; ++b)
@@ -246,13 +247,13 @@ static int build_dgrad(const MogConvDesc* d, Problem* out, int* hires) {
 }
 
 // tcgen05 path: k runs over (tap, channel); the channel pitch per tap is Cs rounded up to 8 for the
-// generic gather kernel and to 64 for the TMA kernel (whole 128-byte swizzle rows per box).
-static int tap_pitch(const Problem& q) { return tma_shape_eligible(q.g) ? tma_tap_pitch(q.CsReal) : p8(q.CsReal); }
+// generic gather kernel and to 32 for the halo kernel (whole 64-byte swizzle rows per box).
+static int tap_pitch(const Problem& q) { return halo_shape_eligible(q.g) ? halo_tap_pitch(q.CsReal) : p8(q.CsReal); }
 static size_t tc_bytes(const Problem& q, int passes) {
   return tc_packed_bytes(q.g.nth * q.g.ntw, tap_pitch(q), q.g.Cd, passes);
 }
 static size_t split_bytes(const Problem& q, int passes) {
-  if (tma_shape_eligible(q.g)) return 0;
+  if (halo_shape_eligible(q.g)) return 0;
   return tc_igemm_workspace_bytes(q.g.M, q.g.nth * q.g.ntw, p8(q.CsReal), q.g.Cd, passes);
 }
 
@@ -281,13 +282,53 @@ static int attach_source(Problem* q, const float* src_f32, const void* planes, i
   return MOG_OK;
 }
 
-static int run_tc_problem(Problem* q, const float* src_f32, const void* planes, int N, const void* wpacked, int passes,
-                          void* ws, size_t ws_bytes, cudaStream_t st, const char* who) {
-  const bool tma = tma_shape_eligible(q->g);
-  if (tma && !planes) return fail(MOG_ERR_BAD_ARG, "%s: this shape runs on the TMA kernel and needs pre-split planes", who);
-  int rc = attach_source(q, src_f32, planes, N, who);
-  if (rc) return rc;
-  return tma ? launch_igemm_tma(q->g, wpacked, passes, st) : launch_igemm_tc(q->g, wpacked, passes, ws, ws_bytes, st);
+// problems [0, n) write the same pixels through an accumulate chain (parity views): one merged halo launch?
+static bool mergeable(const Problem* q, int n) {
+  if (n < 2 || n > 4) return false;
+  for (int i = 0; i < n; ++i) {
+    const IGemmParams& g = q[i].g;
+    const IGemmParams& g0 = q[0].g;
+    if (!halo_shape_eligible(g)) return false;
+    if (g.accum_dst != (i > 0)) return false;
+    if (g.Hr != g0.Hr || g.Wr != g0.Wr || g.dsh != g0.dsh || g.doh != g0.doh || g.dsw != g0.dsw || g.dow != g0.dow ||
+        g.Cd != g0.Cd || q[i].CsReal != q[0].CsReal)
+      return false;
+  }
+  return true;
+}
+
+// runs the n problems of one conv (forward or data gradient) in a tcgen05 precision; `wp` = packed weight blocks back to back
+static int run_tc_problems(Problem* probs, int n, const float* src_f32, const void* planes, int N, const unsigned char* wp, int passes,
+                           const float* bias, bool bias_each, float* dst, void* ws, size_t ws_bytes, cudaStream_t st, const char* who) {
+  const void* blocks[16];
+  for (int i = 0; i < n; ++i) {
+    blocks[i] = wp;
+    wp += tc_bytes(probs[i], passes);
+  }
+  if (mergeable(probs, n)) {
+    if (!planes) return fail(MOG_ERR_BAD_ARG, "%s: this shape runs on the halo kernel and needs pre-split planes", who);
+    IGemmParams gs[4];
+    for (int i = 0; i < n; ++i) {
+      int rc = attach_source(&probs[i], src_f32, planes, N, who);
+      if (rc) return rc;
+      gs[i] = probs[i].g;
+    }
+    gs[0].dst = dst; gs[0].bias = bias; gs[0].act = probs[n - 1].g.act; gs[0].accum_dst = 0;
+    return launch_igemm_halo(gs, n, blocks, passes, st);
+  }
+  for (int i = 0; i < n; ++i) {
+    Problem& q = probs[i];
+    q.g.dst = dst;
+    // bias: problems writing their own pixels (sub-pixel phases) add it each; accumulate chains add it once, at the end
+    q.g.bias = bias_each ? bias : (i == n - 1 ? bias : nullptr);
+    const bool halo = halo_shape_eligible(q.g);
+    if (halo && !planes) return fail(MOG_ERR_BAD_ARG, "%s: this shape runs on the halo kernel and needs pre-split planes", who);
+    int rc = attach_source(&q, src_f32, planes, N, who);
+    if (rc) return rc;
+    rc = halo ? launch_igemm_halo(&q.g, 1, &blocks[i], passes, st) : launch_igemm_tc(q.g, blocks[i], passes, ws, ws_bytes, st);
+    if (rc) return rc;
+  }
+  return MOG_OK;
 }
 
 // ---- public API ---------------------------------------------------------------------------------
@@ -338,7 +379,7 @@ extern "C" int mog_packed_weight_layout(const MogConvDesc* d, int which) {
   const int n = build(d, which, probs, &hires);
   int tag = n << 20;
   for (int i = 0; i < n; ++i)
-    if (tma_shape_eligible(probs[i].g)) tag |= 1 << i;
+    if (halo_shape_eligible(probs[i].g)) tag |= 1 << i;
   return tag;
 }
 
@@ -409,18 +450,10 @@ extern "C" int mog_conv2d_fwd(const MogConvDesc* d, const float* x, const void* 
   const int n = build_fwd(d, probs);
   const size_t need = mog_conv_workspace_bytes(d, 0);
   if (need && (!workspace || ws_bytes < need)) return fail(MOG_ERR_WORKSPACE, "mog_conv2d_fwd: workspace %zu < %zu", ws_bytes, need);
-  const unsigned char* wp = static_cast<const unsigned char*>(w);
-  for (int i = 0; i < n; ++i) {
-    Problem& q = probs[i];
-    const size_t wbytes = tc_bytes(q, passes_of(d));
-    q.g.dst = y;
-    // bias: every sub-pixel phase writes its own pixels (bias each); accumulated parity views add it once, at the end
-    q.g.bias = (q.g.accum_dst || (n > 1 && q.g.vstep > 1)) ? (i == n - 1 ? bias : nullptr) : bias;
-    rc = run_tc_problem(&q, x, x_planes, d->N, wp, passes_of(d), workspace, ws_bytes, st, "mog_conv2d_fwd");
-    if (rc) return rc;
-    wp += wbytes;
-  }
-  return MOG_OK;
+  // bias: every sub-pixel phase writes its own pixels (bias each); accumulated parity views add it once, at the end
+  const bool bias_each = !(n > 1 && (probs[1].g.accum_dst || probs[0].g.vstep > 1));
+  return run_tc_problems(probs, n, x, x_planes, d->N, static_cast<const unsigned char*>(w), passes_of(d), bias, bias_each, y, workspace,
+                         ws_bytes, st, "mog_conv2d_fwd");
 }
 
 extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const void* dy_planes, const void* wt,
@@ -438,21 +471,20 @@ extern "C" int mog_conv2d_dgrad(const MogConvDesc* d, const float* dy, const voi
   float* target = hires ? static_cast<float*>(workspace) : dx;
   unsigned char* sws = workspace ? static_cast<unsigned char*>(workspace) + dgrad_up_bytes(d, hires) : nullptr;
   const size_t sbytes = need - dgrad_up_bytes(d, hires);
-  const unsigned char* wp = static_cast<const unsigned char*>(wt);
-  for (int i = 0; i < n; ++i) {
-    Problem& q = probs[i];
-    q.g.bias = nullptr; q.g.dst = target;
-    if (use_tc(d)) {
-      const size_t wbytes = tc_bytes(q, passes_of(d));
-      rc = run_tc_problem(&q, dy, dy_planes, d->N, wp, passes_of(d), sws, sbytes, st, "mog_conv2d_dgrad");
-      wp += wbytes;
-    } else {
-      MOG_REQUIRE(dy, "mog_conv2d_dgrad: fp32 precision needs the fp32 gradient");
+  if (use_tc(d)) {
+    rc = run_tc_problems(probs, n, dy, dy_planes, d->N, static_cast<const unsigned char*>(wt), passes_of(d), nullptr, true, target, sws,
+                         sbytes, st, "mog_conv2d_dgrad");
+    if (rc) return rc;
+  } else {
+    MOG_REQUIRE(dy, "mog_conv2d_dgrad: fp32 precision needs the fp32 gradient");
+    for (int i = 0; i < n; ++i) {
+      Problem& q = probs[i];
+      q.g.bias = nullptr; q.g.dst = target;
       q.g.src = dy;
       q.g.wmat = static_cast<const float*>(wt);
       rc = launch_igemm_ffma(q.g, st);
+      if (rc) return rc;
     }
-    if (rc) return rc;
   }
   if (hires) return launch_sumpool(target, dx, d->N, d->H, d->W, d->Cin, st);
   return MOG_OK;

@@ -50,10 +50,10 @@ size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int pass
 bool tc_wgrad_eligible(const MogConvDesc& d, bool planes);
 bool patch_dgrad_eligible(const MogConvDesc& d);
 int launch_patch_dgrad(const MogConvDesc& d, const float* dy, const void* packed, float* dx, int passes, cudaStream_t st);
-// TMA-staged persistent kernel (conv_tma.cu)
-bool tma_shape_eligible(const IGemmParams& g);
-int tma_tap_pitch(int Cs);
-int launch_igemm_tma(const IGemmParams& g, const void* packed, int passes, cudaStream_t st);
+// halo-tile TMA persistent kernel (conv_halo.cu)
+bool halo_shape_eligible(const IGemmParams& g);
+int halo_tap_pitch(int Cs);
+int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, int passes, cudaStream_t st);
 int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
                   const int (*taps)[4], int pitch, int passes, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);

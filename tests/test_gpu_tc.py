@@ -181,6 +181,12 @@ TMA_CASES = [
     (8, 32, 32, 24, 40, 3, 1, 1, True, True, 2),       # same with bias + LeakyReLU epilogue per phase
     (8, 64, 64, 3, 96, 4, 2, 1, False, False, 2),      # D first conv: stride 2 = 4 parity views of x accumulated, activation at the end
     (32, 32, 32, 24, 16, 3, 2, 1, False, True, 0),     # 3x3/s2: parity classes with 1 and 2 taps, bias once
+    # halo kernel specifics (conv_halo.cu): ragged grids, odd sub-tile counts, single-buffered accumulators
+    (4, 24, 40, 96, 96, 3, 1, 1, False, False, 0),     # 24 x 40 grid: 2 x 5 sub-tiles per image, last tile row half empty
+    (3, 48, 24, 32, 48, 3, 1, 1, False, True, 2),      # 27 sub-tiles (odd): the last pair has a padding sub-tile
+    (24, 16, 16, 84, 40, 4, 1, 1, False, False, 0),    # D_NET64.local: 16 -> 15, four row taps per filter column
+    (4, 32, 32, 64, 320, 3, 1, 1, False, False, 0),    # two N tiles of 160: accumulators single-buffered in TMEM
+    (8, 32, 32, 200, 72, 3, 1, 1, False, False, 0),    # 200 channels: 7 chunks of 32, the last one a quarter full
 ]
 
 
