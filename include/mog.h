@@ -119,6 +119,11 @@ int mog_bn_finalize(const double* sum, const double* sqsum, int S, int M, int C,
  * replaces: BN apply + GLU / ReLU / LeakyReLU / residual add (model.py:24-32,54,63,73,80,...). */
 int mog_affine_act_fwd(const float* x, const float* scale, const float* shift, const float* residual,
                        float* y, int S, int M, int C, int act, void* stream);
+/* Same, and additionally emits y as the pre-split bf16 planes the tcgen05 convolutions read
+ * (layout of mog_split_planes: hi [rows][C8], then lo for MOG_PREC_BF16X3), saving the separate
+ * split pass over y when the consumer is a convolution.  Output channel count must be a multiple of 4. */
+int mog_affine_act_fwd_planes(const float* x, const float* scale, const float* shift, const float* residual,
+                              float* y, void* y_planes, int precision, int S, int M, int C, int act, void* stream);
 /* Backward of BN(train)+act: pass 1 reduces dgamma=sum(dz*xhat), dbeta=sum(dz) per (segment,
  * channel) in double; pass 2 writes dx.  dy: [S*M][C or C/2].  With mean == invstd ==
  * dgamma_seg == dbeta_seg == NULL, mog_bn_act_bwd_apply is the backward of a plain activation

@@ -3,6 +3,8 @@
 // kernels over [S*M][C] row-major (NHWC) tensors: per-channel reductions run over rows with
 // 32 consecutive channels per warp row (128-byte coalesced), partials are combined with
 // warp/smem reductions and one double atomicAdd per (block, channel).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mog {
@@ -95,7 +97,8 @@ __device__ __forceinline__ float act_fwd(float z, int act) {
 template <int VEC>
 __global__ void affine_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const float* __restrict__ shift, const float* __restrict__ res,
-                                      float* __restrict__ y, int M, int C, int act, size_t total_out) {
+                                      float* __restrict__ y, int M, int C, int act, size_t total_out,
+                                      __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo, int CP) {
   const int Co = act == MOG_ACT_GLU ? C / 2 : C;
   size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (idx >= total_out) return;
@@ -133,6 +136,21 @@ __global__ void affine_act_fwd_kernel(const float* __restrict__ x, const float* 
       out[0] += r.x; out[1] += r.y; out[2] += r.z; out[3] += r.w;
     }
     *reinterpret_cast<float4*>(y + idx) = make_float4(out[0], out[1], out[2], out[3]);
+    if (phi) {
+      // bf16 hi (+ lo = bf16(v - hi)) planes [rows][CP] for the tensor-core convolutions; pad channels zero
+      __nv_bfloat162 h01 = __floats2bfloat162_rn(out[0], out[1]), h23 = __floats2bfloat162_rn(out[2], out[3]);
+      const size_t o = row * CP + c;
+      *reinterpret_cast<uint2*>(phi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+      if (plo) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        __nv_bfloat162 l01 = __floats2bfloat162_rn(out[0] - f01.x, out[1] - f01.y), l23 = __floats2bfloat162_rn(out[2] - f23.x, out[3] - f23.y);
+        *reinterpret_cast<uint2*>(plo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+      }
+      if (c + 4 == Co && CP > Co) {
+        *reinterpret_cast<uint2*>(phi + o + 4) = make_uint2(0u, 0u);
+        if (plo) *reinterpret_cast<uint2*>(plo + o + 4) = make_uint2(0u, 0u);
+      }
+    }
   } else {
     float a = xr[c];
     if (sc) a = fmaf(a, sc[c], sh[c]);
@@ -294,6 +312,237 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
   dz[i] = o;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised variants (channel width % 4 == 0): one thread owns 4 consecutive channels (for GLU: 4 value
+// channels AND their 4 gate partners), a block is GB column groups x R row lanes, every load / store is a
+// 16-byte access and consecutive threads cover a contiguous row segment; 4 rows are in flight per thread.
+// The scalar kernels above remain for odd channel counts.
+// ---------------------------------------------------------------------------------------------
+struct V4Geom { int Cv, GB, R, nxb, rpb; };
+static V4Geom v4_geom(int width, int M) {
+  V4Geom g;
+  g.Cv = width / 4;
+  g.nxb = ceil_div(g.Cv, 32);
+  g.GB = ceil_div(g.Cv, g.nxb);
+  g.R = 256 / g.GB;
+  if (g.R > 32) g.R = 32;
+  g.rpb = g.R * 32;
+  while (ceil_div(M, g.rpb) > 65535) g.rpb *= 2;
+  return g;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void to_arr(const float4& v, float (&a)[4]) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+
+// block-level sum over the R row lanes of NV per-thread values (4 channels each), then one double atomicAdd per channel
+template <int NV>
+__device__ __forceinline__ void v4_block_reduce(float (&v)[NV][4], int GB, int R, int cgl, int rl, bool valid, double* const (&dst)[NV]) {
+  __shared__ float red[NV][256 * 4];
+  const int t = rl * GB + cgl;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[k][t * 4 + j] = v[k][j];
+  __syncthreads();
+  if (rl == 0 && valid) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double acc = 0.0;
+        for (int i = 0; i < R; ++i) acc += (double)red[k][(i * GB + cgl) * 4 + j];
+        atomicAdd(dst[k] + j, acc);
+      }
+  }
+}
+
+__global__ void bn_stats_v4_kernel(const float* __restrict__ x, int M, int C, V4Geom g, double* __restrict__ sum, double* __restrict__ sqsum) {
+  const int cgl = threadIdx.x % g.GB, rl = threadIdx.x / g.GB;
+  const int cg = blockIdx.x * g.GB + cgl;
+  const bool valid = cg < g.Cv;
+  const int c = cg * 4, s = blockIdx.z;
+  const long long r_begin = (long long)blockIdx.y * g.rpb;
+  long long r_end = r_begin + g.rpb;
+  if (r_end > M) r_end = M;
+  float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  if (valid) {
+    const float* xp = x + ((size_t)s * M) * C + c;
+#pragma unroll 4
+    for (long long r = r_begin + rl; r < r_end; r += g.R) {
+      float a[4];
+      to_arr(ld4(xp + (size_t)r * C), a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[0][j] += a[j]; v[1][j] = fmaf(a[j], a[j], v[1][j]); }
+    }
+  }
+  double* const dst[2] = {sum + (size_t)s * C + c, sqsum + (size_t)s * C + c};
+  v4_block_reduce<2>(v, g.GB, g.R, cgl, rl, valid, dst);
+}
+
+// per-thread constants of 4 channels
+struct Aff4 { float sc[4], sh[4], mu[4], is[4]; };
+__device__ __forceinline__ void load_aff4(const BnBwdArgs& a, int s, int c, Aff4& k) {
+  if (!a.mean) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { k.sc[j] = 1.f; k.sh[j] = 0.f; k.mu[j] = 0.f; k.is[j] = 1.f; }
+    return;
+  }
+  float g[4] = {1.f, 1.f, 1.f, 1.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.gamma) to_arr(ld4(a.gamma + c), g);
+  if (a.beta) to_arr(ld4(a.beta + c), b);
+  to_arr(ld4(a.mean + (size_t)s * a.C + c), k.mu);
+  to_arr(ld4(a.invstd + (size_t)s * a.C + c), k.is);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { k.sc[j] = g[j] * k.is[j]; k.sh[j] = b[j] - k.mu[j] * k.sc[j]; }
+}
+
+template <int ACT>
+__device__ __forceinline__ float dact(float z, float g) {
+  if (ACT == MOG_ACT_RELU) return z > 0.f ? g : 0.f;
+  if (ACT == MOG_ACT_LRELU) return z > 0.f ? g : 0.2f * g;
+  if (ACT == MOG_ACT_TANH) { const float t = tanhf(z); return g * (1.f - t * t); }
+  if (ACT == MOG_ACT_SIGMOID) { const float t = sigmoidf_(z); return g * t * (1.f - t); }
+  return g;
+}
+
+// dz of the 4 value channels (and, GLU, of the 4 gate channels) of one row
+template <int ACT>
+__device__ __forceinline__ void dz_row(const Aff4& kv, const Aff4& kg, const float (&xv)[4], const float (&xg)[4], const float (&gy)[4],
+                                       float (&dzv)[4], float (&dzg)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float zv = fmaf(xv[j], kv.sc[j], kv.sh[j]);
+    if (ACT == MOG_ACT_GLU) {
+      const float zg = fmaf(xg[j], kg.sc[j], kg.sh[j]);
+      const float sg = sigmoidf_(zg);
+      dzv[j] = gy[j] * sg;
+      dzg[j] = gy[j] * zv * sg * (1.f - sg);
+    } else {
+      dzv[j] = dact<ACT>(zv, gy[j]);
+      dzg[j] = 0.f;
+    }
+  }
+}
+
+template <int ACT>
+__global__ void bn_bwd_reduce_v4_kernel(BnBwdArgs a, V4Geom g, double* __restrict__ dgamma, double* __restrict__ dbeta) {
+  constexpr bool GLU = ACT == MOG_ACT_GLU;
+  const int Co = GLU ? a.C / 2 : a.C;
+  const int cgl = threadIdx.x % g.GB, rl = threadIdx.x / g.GB;
+  const int cg = blockIdx.x * g.GB + cgl;
+  const bool valid = cg < g.Cv;
+  const int c = cg * 4, s = blockIdx.z;
+  const long long r_begin = (long long)blockIdx.y * g.rpb;
+  long long r_end = r_begin + g.rpb;
+  if (r_end > a.M) r_end = a.M;
+  float v[GLU ? 4 : 2][4];
+#pragma unroll
+  for (int k = 0; k < (GLU ? 4 : 2); ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[k][j] = 0.f;
+  if (valid) {
+    Aff4 kv, kg;
+    load_aff4(a, s, c, kv);
+    if (GLU) load_aff4(a, s, c + Co, kg); else kg = kv;
+    const float* xp = a.x + ((size_t)s * a.M) * a.C + c;
+    const float* yp = a.dy + ((size_t)s * a.M) * Co + c;
+#pragma unroll 2
+    for (long long r = r_begin + rl; r < r_end; r += g.R) {
+      float xv[4], xg[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], dzv[4], dzg[4];
+      to_arr(ld4(xp + (size_t)r * a.C), xv);
+      if (GLU) to_arr(ld4(xp + (size_t)r * a.C + Co), xg);
+      to_arr(ld4(yp + (size_t)r * Co), gy);
+      dz_row<ACT>(kv, kg, xv, xg, gy, dzv, dzg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[0][j] += dzv[j];
+        v[1][j] = fmaf(dzv[j], (xv[j] - kv.mu[j]) * kv.is[j], v[1][j]);
+        if (GLU) {
+          v[2][j] += dzg[j];
+          v[3][j] = fmaf(dzg[j], (xg[j] - kg.mu[j]) * kg.is[j], v[3][j]);
+        }
+      }
+    }
+  }
+  if constexpr (GLU) {
+    double* const dst[4] = {dbeta + (size_t)s * a.C + c, dgamma + (size_t)s * a.C + c, dbeta + (size_t)s * a.C + c + Co,
+                            dgamma + (size_t)s * a.C + c + Co};
+    v4_block_reduce<4>(v, g.GB, g.R, cgl, rl, valid, dst);
+  } else {
+    double* const dst[2] = {dbeta + (size_t)s * a.C + c, dgamma + (size_t)s * a.C + c};
+    v4_block_reduce<2>(v, g.GB, g.R, cgl, rl, valid, dst);
+  }
+}
+
+template <int ACT>
+__global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __restrict__ dgamma, const double* __restrict__ dbeta,
+                                       float* __restrict__ dx) {
+  constexpr bool GLU = ACT == MOG_ACT_GLU;
+  const int Co = GLU ? a.C / 2 : a.C;
+  const int cgl = threadIdx.x % g.GB, rl = threadIdx.x / g.GB;
+  const int cg = blockIdx.x * g.GB + cgl;
+  if (cg >= g.Cv) return;
+  const int c = cg * 4, s = blockIdx.z;
+  const long long r_begin = (long long)blockIdx.y * g.rpb;
+  long long r_end = r_begin + g.rpb;
+  if (r_end > a.M) r_end = a.M;
+  Aff4 kv, kg;
+  load_aff4(a, s, c, kv);
+  if (GLU) load_aff4(a, s, c + Co, kg); else kg = kv;
+  float k1v[4], k2v[4], k1g[4], k2g[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k1v[j] = dbeta ? (float)(dbeta[(size_t)s * a.C + c + j] / (double)a.M) : 0.f;
+    k2v[j] = dgamma ? (float)(dgamma[(size_t)s * a.C + c + j] / (double)a.M) : 0.f;
+    k1g[j] = (GLU && dbeta) ? (float)(dbeta[(size_t)s * a.C + c + Co + j] / (double)a.M) : 0.f;
+    k2g[j] = (GLU && dgamma) ? (float)(dgamma[(size_t)s * a.C + c + Co + j] / (double)a.M) : 0.f;
+  }
+  const float* xp = a.x + ((size_t)s * a.M) * a.C + c;
+  const float* yp = a.dy + ((size_t)s * a.M) * Co + c;
+  float* dp = dx + ((size_t)s * a.M) * a.C + c;
+#pragma unroll 2
+  for (long long r = r_begin + rl; r < r_end; r += g.R) {
+    float xv[4], xg[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], dzv[4], dzg[4], o[4];
+    to_arr(ld4(xp + (size_t)r * a.C), xv);
+    if (GLU) to_arr(ld4(xp + (size_t)r * a.C + Co), xg);
+    to_arr(ld4(yp + (size_t)r * Co), gy);
+    dz_row<ACT>(kv, kg, xv, xg, gy, dzv, dzg);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = kv.sc[j] * (dzv[j] - k1v[j] - (xv[j] - kv.mu[j]) * kv.is[j] * k2v[j]);
+    *reinterpret_cast<float4*>(dp + (size_t)r * a.C) = make_float4(o[0], o[1], o[2], o[3]);
+    if (GLU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = kg.sc[j] * (dzg[j] - k1g[j] - (xg[j] - kg.mu[j]) * kg.is[j] * k2g[j]);
+      *reinterpret_cast<float4*>(dp + (size_t)r * a.C + Co) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <int ACT>
+static void launch_bwd_v4(bool reduce, const BnBwdArgs& a, const V4Geom& g, double* dgamma, double* dbeta, float* dx, cudaStream_t st) {
+  dim3 grid(g.nxb, ceil_div(a.M, g.rpb), a.S);
+  if (reduce)
+    bn_bwd_reduce_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta);
+  else
+    bn_bwd_apply_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta, dx);
+}
+static bool bwd_v4(bool reduce, const BnBwdArgs& a, double* dgamma, double* dbeta, float* dx, cudaStream_t st) {
+  const int width = a.act == MOG_ACT_GLU ? a.C / 2 : a.C;
+  if ((width & 3) || (a.C & 3) || a.S > 65535) return false;
+  const V4Geom g = v4_geom(width, a.M);
+  switch (a.act) {
+    case MOG_ACT_NONE: launch_bwd_v4<MOG_ACT_NONE>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    case MOG_ACT_RELU: launch_bwd_v4<MOG_ACT_RELU>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    case MOG_ACT_LRELU: launch_bwd_v4<MOG_ACT_LRELU>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    case MOG_ACT_GLU: launch_bwd_v4<MOG_ACT_GLU>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    case MOG_ACT_TANH: launch_bwd_v4<MOG_ACT_TANH>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    case MOG_ACT_SIGMOID: launch_bwd_v4<MOG_ACT_SIGMOID>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    default: return false;
+  }
+  return true;
+}
+
 }  // namespace mog
 
 using namespace mog;
@@ -303,9 +552,14 @@ extern "C" int mog_bn_stats(const float* x, int S, int M, int C, double* sum, do
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(sum, 0, sizeof(double) * S * C, st);
   cudaMemsetAsync(sqsum, 0, sizeof(double) * S * C, st);
+  MOG_REQUIRE(S <= 65535, "mog_bn_stats: too many segments");
+  if ((C & 3) == 0) {
+    const V4Geom g = v4_geom(C, M);
+    bn_stats_v4_kernel<<<dim3(g.nxb, ceil_div(M, g.rpb), S), g.GB * g.R, 0, st>>>(x, M, C, g, sum, sqsum);
+    return check_launch("bn_stats_v4_kernel");
+  }
   const int rpb = rows_per_block(M);
   dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
-  MOG_REQUIRE(grid.z <= 65535, "mog_bn_stats: too many segments");
   bn_stats_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(x, M, C, rpb, sum, sqsum);
   return check_launch("bn_stats_kernel");
 }
@@ -322,17 +576,30 @@ extern "C" int mog_bn_finalize(const double* sum, const double* sqsum, int S, in
 
 extern "C" int mog_affine_act_fwd(const float* x, const float* scale, const float* shift, const float* residual,
                                   float* y, int S, int M, int C, int act, void* stream) {
+  return mog_affine_act_fwd_planes(x, scale, shift, residual, y, nullptr, MOG_PREC_FP32, S, M, C, act, stream);
+}
+
+extern "C" int mog_affine_act_fwd_planes(const float* x, const float* scale, const float* shift, const float* residual,
+                                         float* y, void* y_planes, int precision, int S, int M, int C, int act, void* stream) {
   MOG_REQUIRE(x && y && S > 0 && M > 0 && C > 0, "mog_affine_act_fwd: bad argument");
   MOG_REQUIRE((scale == nullptr) == (shift == nullptr), "mog_affine_act_fwd: scale/shift must both be given or NULL");
   MOG_REQUIRE(act != MOG_ACT_GLU || (C % 2) == 0, "mog_affine_act_fwd: GLU needs an even channel count");
   const int Co = act == MOG_ACT_GLU ? C / 2 : C;
   size_t total = (size_t)S * M * Co;
   cudaStream_t st = as_stream(stream);
+  __nv_bfloat16 *phi = nullptr, *plo = nullptr;
+  const int CP = ceil_div(Co, 8) * 8;
+  if (y_planes) {
+    MOG_REQUIRE(precision == MOG_PREC_BF16X3 || precision == MOG_PREC_BF16, "mog_affine_act_fwd_planes: precision must be a tcgen05 mode");
+    MOG_REQUIRE((Co & 3) == 0 && (C & 3) == 0, "mog_affine_act_fwd_planes: channel counts must be multiples of 4");
+    phi = static_cast<__nv_bfloat16*>(y_planes);
+    if (precision == MOG_PREC_BF16X3) plo = phi + (size_t)S * M * CP;
+  }
   if ((Co & 3) == 0 && (C & 3) == 0) {
     size_t nthreads = total / 4;
-    affine_act_fwd_kernel<4><<<(unsigned)ceil_div_ll((long long)nthreads, 256), 256, 0, st>>>(x, scale, shift, residual, y, M, C, act, total);
+    affine_act_fwd_kernel<4><<<(unsigned)ceil_div_ll((long long)nthreads, 256), 256, 0, st>>>(x, scale, shift, residual, y, M, C, act, total, phi, plo, CP);
   } else {
-    affine_act_fwd_kernel<1><<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(x, scale, shift, residual, y, M, C, act, total);
+    affine_act_fwd_kernel<1><<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(x, scale, shift, residual, y, M, C, act, total, nullptr, nullptr, CP);
   }
   return check_launch("affine_act_fwd_kernel");
 }
@@ -346,6 +613,7 @@ extern "C" int mog_bn_act_bwd_reduce(const float* x, const float* dy, const floa
   cudaMemsetAsync(dbeta_seg, 0, sizeof(double) * S * C, st);
   const int rpb = rows_per_block(M);
   BnBwdArgs a{x, dy, mean, invstd, gamma, beta, S, M, C, act, rpb};
+  if (bwd_v4(true, a, dgamma_seg, dbeta_seg, nullptr, st)) return check_launch("bn_bwd_reduce_v4_kernel");
   dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
   MOG_REQUIRE(grid.z <= 65535, "mog_bn_act_bwd_reduce: too many segments");
   bn_bwd_reduce_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, dgamma_seg, dbeta_seg);
@@ -363,10 +631,15 @@ extern "C" int mog_bn_act_bwd_apply(const float* x, const float* dy, const float
   cudaStream_t st = as_stream(stream);
   const int rpb = rows_per_block(M);
   BnBwdArgs a{x, dy, mean, invstd, gamma, beta, S, M, C, act, rpb};
-  dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
-  MOG_REQUIRE(grid.z <= 65535, "mog_bn_act_bwd_apply: too many segments");
-  bn_bwd_apply_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, dgamma_seg, dbeta_seg, dx);
-  int rc = check_launch("bn_bwd_apply_kernel");
+  int rc;
+  if (bwd_v4(false, a, const_cast<double*>(dgamma_seg), const_cast<double*>(dbeta_seg), dx, st)) {
+    rc = check_launch("bn_bwd_apply_v4_kernel");
+  } else {
+    dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
+    MOG_REQUIRE(grid.z <= 65535, "mog_bn_act_bwd_apply: too many segments");
+    bn_bwd_apply_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, dgamma_seg, dbeta_seg, dx);
+    rc = check_launch("bn_bwd_apply_kernel");
+  }
   if (rc) return rc;
   if (has_bn && (dgamma || dbeta)) {
     bn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dgamma_seg, dbeta_seg, S, C, dgamma, dbeta);

@@ -17,7 +17,9 @@
 //   * several *views* in one K loop: the parity views of a strided conv (or of dy in the data gradient of
 //     upsample+conv) are separate tensor maps over the same planes; their taps accumulate in TMEM instead of
 //     through read-modify-write passes over the fp32 output.
-//   * separate full/empty mbarrier rings for A boxes and B chunks; warp 0 = TMA producer; warps 1-2 = MMA
+//   * separate full/empty mbarrier rings for A boxes and B chunks, each fed by its own producer thread (warp 0:
+//     A; warp 11: B; explicit cp.async.bulk.prefetch of the next tile pair into L2 was measured and made both
+//     this kernel and the weight-gradient kernel SLOWER - the prefetches compete with the loads); warps 1-2 = MMA
 //     issuers, one per sub-tile accumulator (a single issuing thread needs ~40-50 cycles per tcgen05.mma and
 //     would bound the N <= 128 shapes; warp-convergent loops, one elected lane issues); warps 3-10 = epilogue,
 //     four per sub-tile; accumulators double-buffered in TMEM when 4 x BN <= 512 columns; CTAs persistent
@@ -38,7 +40,7 @@
 namespace mog {
 namespace tc {
 
-constexpr int HALO_THREADS = 352;          // producer + 2 MMA warps + 8 epilogue warps
+constexpr int HALO_THREADS = 384;          // A producer + 2 MMA warps + 8 epilogue warps + B producer
 constexpr int HT_W = 8, HT_H = 16;          // sub-tile: 8 x 16 = 128 output pixels
 constexpr int HCH = 32;                     // channels per chunk (64-byte rows, SWIZZLE_64B)
 constexpr int HALO_MAXGROUPS = 16;
@@ -176,14 +178,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer ==========================================================
+    // ===================== TMA producer of A (activation halo boxes) =============================
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
+      int sa = 0;
+      uint32_t pha = 0;
       const uint32_t bytesA = (uint32_t)(nplanes * 2 * (HCH * 2 * HT_W * p.HH));
-      const uint32_t bytesB = (uint32_t)slotB;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ntile = (int)(tile % p.n_ntiles);
         const long long pair = tile / p.n_ntiles;
         int n[2], h0[2], w0[2];
         halo_decode(p, pair * 2, &n[0], &h0[0], &w0[0]);
@@ -198,6 +198,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
               for (int s = 0; s < 2; ++s)
                 halo_tma_4d(stA + pl * planeA + s * p.subA, &maps.a[g.prob][pl], &fullA[sa], c * HCH, w0[s] + g.w_off, h0[s] + g.h_org, n[s]);
             if (++sa == p.stagesA) { sa = 0; pha ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    // ===================== TMA producer of B (weight chunks): its own thread, so that the deep B ring keeps
+    // running ahead while the A producer waits for a free A slot ===================================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      const uint32_t bytesB = (uint32_t)slotB;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int ntile = (int)(tile % p.n_ntiles);
+        for (int gi = 0; gi < p.ngroups; ++gi) {
+          const HaloGroup& g = p.grp[gi];
+          for (int c = 0; c < p.nchunk; ++c) {
             for (int a = 0; a < g.nth; ++a) {
               mbar_wait(&emptyB[sb], phb ^ 1u);
               const uint32_t stB = smem_u32(ringB + (size_t)sb * slotB);
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       __syncwarp();
       if (++as == p.nbuf) { as = 0; aph ^= 1u; }
     }
-  } else {
+  } else if (warp <= 10) {
     // ===================== epilogue: warps 3-6 drain sub-tile 0, warps 7-10 sub-tile 1 ==============
     const int s = (warp - 3) >> 2;      // sub-tile of this warp
     const int q4 = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp id % 4)
@@ -423,7 +439,13 @@ int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, i
   p.tiles_h = ceil_div(g0.Hr, HT_H);
   p.nsub = (long long)g0.N * p.tiles_w * p.tiles_h;
   p.npairs = (p.nsub + 1) / 2;
-  p.BN = tc_bn_for(g0.Cd);
+  // N tile <= 128 columns so that two sub-tiles x two accumulator buffers fit the 512 TMEM columns: the epilogue
+  // (fp32 stores at ~16 B/clk/SM) must overlap the MMAs of the next tile; N = 192 is issued as 2 x 96
+  {
+    const int cpad = ceil_div(g0.Cd, 16) * 16;
+    const int tiles = ceil_div(cpad, 128);
+    p.BN = ceil_div(ceil_div(cpad, tiles), 16) * 16;
+  }
   p.n_ntiles = ceil_div(g0.Cd, p.BN);
   p.total_tiles = p.npairs * p.n_ntiles;
   p.nbuf = 4 * p.BN <= 512 ? 2 : 1;
@@ -445,7 +467,7 @@ int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, i
   p.dsh = g0.dsh; p.doh = g0.doh; p.dsw = g0.dsw; p.dow = g0.dow;
 
   HaloMaps maps;
-  const int Npad = p.n_ntiles * p.BN;
+  const int Npad = ceil_div(g0.Cd, tc_bn_for(g0.Cd)) * tc_bn_for(g0.Cd);   // rows of the packed weight planes (tc_pack_pitch)
   for (int i = 0; i < HALO_MAXPROBS; ++i) {
     const IGemmParams& g = gs[i < n ? i : 0];
     const __nv_bfloat16* xa = static_cast<const __nv_bfloat16*>(g.src_planes);

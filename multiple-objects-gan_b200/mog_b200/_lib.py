@@ -48,6 +48,7 @@ SIGNATURES = {
     "mog_bn_stats": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "mog_bn_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "mog_affine_act_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "mog_affine_act_fwd_planes": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mog_bn_act_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "mog_bn_act_bwd_apply": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mog_act_bwd": (_i, [_p, _p, _p, _sz, _i, _p]),

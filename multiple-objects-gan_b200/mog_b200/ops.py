@@ -137,6 +137,28 @@ def _workspace(d, which, device):
     return ws, n
 
 
+def _alloc_planes(shape, precision, device):
+    Cc = shape[-1]
+    rows = 1
+    for v in shape[:-1]:
+        rows *= int(v)
+    n = _lib.lib().mog_planes_bytes(rows, Cc, precision)
+    return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
+
+
+def _attach_planes(y: torch.Tensor, planes: torch.Tensor, precision: int):
+    """Remember the pre-split planes of ``y`` (written by the producing kernel) for a consuming convolution."""
+    y._mog_planes = (planes, precision, y._version)
+
+
+def planes_of(x: torch.Tensor, precision: int):
+    """Planes of x: those its producer emitted (bn_act / activation epilogue) if still valid, else a split pass."""
+    cached = getattr(x, "_mog_planes", None)
+    if cached is not None and cached[1] == precision and cached[2] == x._version:
+        return cached[0]
+    return split_planes(x, precision)
+
+
 def split_planes(x: torch.Tensor, precision: int):
     """fp32 [..., C] -> bf16 planes buffer (hi [rows][C8], then lo for bf16x3) for the tcgen05 kernels."""
     Cc = x.shape[-1]
@@ -161,7 +183,7 @@ class Conv2dFn(torch.autograd.Function):
         y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
         ws, nws = _workspace(d, 0, x.device)
         b = None if bias is None else bias.detach().contiguous()
-        xp = split_planes(x, precision) if precision != PREC_FP32 else None
+        xp = planes_of(x, precision) if precision != PREC_FP32 else None
         call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _ptr(xp), _packed(weight, "fwd", d).data_ptr(), _ptr(b),
              y.data_ptr(), _ptr(ws), nws, _stream())
         ctx.cfg = (stride, pad, up2x, act, precision, tuple(x.shape))
@@ -222,7 +244,7 @@ class BnActFn(torch.autograd.Function):
     """y = act(BN_train(x)) (+ residual) over rows [S*M, C] with per-segment statistics."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, S, act, momentum, eps):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, S, act, momentum, eps, planes, precision):
         _chk(x, "bn input")
         Cc = x.shape[-1]
         rows = x.numel() // Cc
@@ -243,8 +265,8 @@ class BnActFn(torch.autograd.Function):
         y = torch.empty(x.shape[:-1] + (Co,), device=dev, dtype=torch.float32)
         if residual is not None:
             _chk(residual, "bn residual")
-        call("mog_affine_act_fwd", x.data_ptr(), mis[2].data_ptr(), mis[3].data_ptr(), _ptr(residual),
-             y.data_ptr(), S, M, Cc, act, st)
+        call("mog_affine_act_fwd_planes", x.data_ptr(), mis[2].data_ptr(), mis[3].data_ptr(), _ptr(residual),
+             y.data_ptr(), _ptr(planes), precision, S, M, Cc, act, st)
         ctx.cfg = (S, M, Cc, act)
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, g, b, mis)
@@ -266,7 +288,7 @@ class BnActFn(torch.autograd.Function):
              g.data_ptr(), b.data_ptr(), red[0].data_ptr(), red[1].data_ptr(), S, M, Cc, act, dx.data_ptr(),
              dgb[0].data_ptr(), dgb[1].data_ptr(), st)
         dres = dy if ctx.has_res else None
-        return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None
+        return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None, None, None
 
 
 def bn_act(x, bn, act=ACT_NONE, residual=None, segments=1):
@@ -276,8 +298,17 @@ def bn_act(x, bn, act=ACT_NONE, residual=None, segments=1):
         raise RuntimeError("libmog implements the training path (batch statistics) only")
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked += segments
-    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, segments, act,
-                         float(bn.momentum), float(bn.eps))
+    # in the tensor-core precisions the apply kernel also emits y as pre-split bf16 planes: the usual consumer is a conv
+    precision = _default_precision
+    Co = x.shape[-1] // 2 if act == ACT_GLU else x.shape[-1]
+    planes = None
+    if precision != PREC_FP32 and x.dim() == 4 and Co % 4 == 0 and x.shape[-1] % 4 == 0 and x.is_cuda:
+        planes = _alloc_planes(tuple(x.shape[:-1]) + (Co,), precision, x.device)
+    y = BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, segments, act,
+                      float(bn.momentum), float(bn.eps), planes, precision)
+    if planes is not None:
+        _attach_planes(y, planes, precision)
+    return y
 
 
 # ---------------------------------------------------------------------------------------------
