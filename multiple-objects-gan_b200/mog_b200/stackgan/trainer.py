@@ -1,0 +1,192 @@
+"""``GANTrainer`` -- libmog edition of ``code/coco/stackgan/trainer.py`` (training part).
+
+Keeps the reference's class surface (``GANTrainer(output_dir)``, ``load_network_stageI``,
+``load_network_stageII``, ``train(data_loader, stage, max_objects)``) and checkpoint format
+(``{epoch, netG, optimG, netD, optimD}``, miscc/utils.py:162-176).  The body of the hot loop
+(trainer.py:154-235) lives in :meth:`train_step`.
+
+Differences, all behind the same results: one process per GPU with an NCCL all-reduce per network
+(``mog_b200.parallel.GradBucket``) instead of ``nn.parallel.data_parallel``; the discriminator's
+weight gradients are not computed during the G step (the reference computes them and never uses
+them: ``netD.zero_grad()`` precedes the next D step, trainer.py:204); no ``.item()`` host syncs in
+the step.  TensorBoard summaries and image dumps (trainer.py:237-266) and ``sample`` (:285-420) are
+outside the hot path.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+import torch.optim as optim
+
+from .. import parallel
+from .miscc.config import cfg
+from .miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator_loss, compute_transformation_matrix,
+                          compute_transformation_matrix_inverse, mkdir_p, save_model, weights_init)
+
+
+class GANTrainer(object):
+    def __init__(self, output_dir):
+        if cfg.TRAIN.FLAG and output_dir:
+            self.model_dir = os.path.join(output_dir, 'Model')
+            self.image_dir = os.path.join(output_dir, 'Image')
+            self.log_dir = os.path.join(output_dir, 'Log')
+            for d in (self.model_dir, self.image_dir, self.log_dir):
+                mkdir_p(d)
+        self.max_epoch = cfg.TRAIN.MAX_EPOCH
+        self.snapshot_interval = cfg.TRAIN.SNAPSHOT_INTERVAL
+        self.gpus = [int(ix) for ix in str(cfg.GPU_ID).split(',')]
+        self.num_gpus = len(self.gpus)
+        self.batch_size = cfg.TRAIN.BATCH_SIZE
+
+    # ------------------------------------------------------------------ networks
+    def _finish(self, netG, netD):
+        if cfg.NET_D != '':
+            netD.load_state_dict(torch.load(cfg.NET_D, map_location='cpu'))
+        if cfg.CUDA:
+            netG.cuda()
+            netD.cuda()
+        netG.train()
+        netD.train()
+        parallel.broadcast_params(netG)
+        parallel.broadcast_params(netD)
+        return netG, netD
+
+    def load_network_stageI(self):
+        """trainer.py:50-72"""
+        from .model import STAGE1_D, STAGE1_G
+        netG = STAGE1_G()
+        netG.apply(weights_init)
+        netD = STAGE1_D()
+        netD.apply(weights_init)
+        if cfg.NET_G != '':
+            netG.load_state_dict(torch.load(cfg.NET_G, map_location='cpu')["netG"])
+        return self._finish(netG, netD)
+
+    def load_network_stageII(self):
+        """trainer.py:75-108 -- needs a stage-I generator (``cfg.STAGE1_G``) or a full stage-II checkpoint."""
+        from .model import STAGE1_G, STAGE2_D, STAGE2_G
+        netG = STAGE2_G(STAGE1_G())
+        netG.apply(weights_init)
+        if cfg.NET_G != '':
+            netG.load_state_dict(torch.load(cfg.NET_G, map_location='cpu')["netG"])
+        elif cfg.STAGE1_G != '':
+            netG.STAGE1_G.load_state_dict(torch.load(cfg.STAGE1_G, map_location='cpu')["netG"])
+        else:
+            print("Please give the Stage1_G path")
+            return
+        netD = STAGE2_D()
+        netD.apply(weights_init)
+        return self._finish(netG, netD)
+
+    def define_optimizers(self, netG, netD):
+        """trainer.py:131-137 -- Adam(betas=(0.5, 0.999)); only the trainable generator parameters."""
+        optimizerD = optim.Adam(netD.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, betas=(0.5, 0.999))
+        optimizerG = optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=cfg.TRAIN.GENERATOR_LR,
+                                betas=(0.5, 0.999))
+        return optimizerG, optimizerD
+
+    # ------------------------------------------------------------------ the hot loop body
+    def make_step_state(self, netG, netD, optimizerG, optimizerD, batch_size=None):
+        B = batch_size or self.batch_size
+        dev = next(netD.parameters()).device
+        st = {"netG": netG, "netD": netD, "optG": optimizerG, "optD": optimizerD,
+              "real_labels": torch.ones(B, device=dev), "fake_labels": torch.zeros(B, device=dev)}
+        if parallel.world() > 1:
+            st["bucketG"] = parallel.GradBucket(netG.parameters())
+            st["bucketD"] = parallel.GradBucket(netD.parameters())
+        return st
+
+    def train_step(self, st, real_imgs, txt_embedding, label_one_hot, transf_matrices_inv, transf_matrices=None,
+                   transf_matrices_s2=None, transf_matrices_inv_s2=None, noise=None, optimize=True, stage=None):
+        """One iteration of trainer.py:193-235.  Stage I: ``transf_matrices`` / ``transf_matrices_inv``; stage II
+        additionally the ``_s2`` pair (the D and the stage-II object pathway use it).  Returns
+        (errD, errG, kl_loss) as device scalars."""
+        stage = cfg.STAGE if stage is None else stage
+        netG, netD = st["netG"], st["netD"]
+        multi = parallel.world() > 1
+        B = real_imgs.shape[0]
+        if noise is None:
+            noise = torch.empty(B, cfg.Z_DIM, device=real_imgs.device).normal_(0, 1)
+        if stage == 1:
+            _, fake_imgs, mu, logvar, _ = netG(txt_embedding, noise, transf_matrices_inv, label_one_hot)
+            th, thi = transf_matrices, transf_matrices_inv
+        else:
+            _, fake_imgs, mu, logvar, _ = netG(txt_embedding, noise, transf_matrices_inv, transf_matrices_s2,
+                                               transf_matrices_inv_s2, label_one_hot)
+            th, thi = transf_matrices_s2, transf_matrices_inv_s2
+        # (3) update D
+        netD.zero_grad(set_to_none=True)
+        errD, _, _, _ = compute_discriminator_loss(netD, real_imgs, fake_imgs, st["real_labels"], st["fake_labels"],
+                                                   label_one_hot, th, thi, mu, self.gpus)
+        errD.backward()   # (the reference passes retain_graph=True; nothing of this graph is used again)
+        if multi:
+            st["bucketD"].launch()
+            st["bucketD"].finish()
+        if optimize:
+            st["optD"].step()
+        # (2) update G; D weights frozen so their (never used) wgrad is not computed
+        for p in netD.parameters():
+            p.requires_grad_(False)
+        netG.zero_grad(set_to_none=True)
+        errG = compute_generator_loss(netD, fake_imgs, st["real_labels"], label_one_hot, th, thi, mu, self.gpus)
+        kl_loss = KL_loss(mu, logvar)
+        (errG + kl_loss * cfg.TRAIN.COEFF.KL).backward()
+        for p in netD.parameters():
+            p.requires_grad_(True)
+        if multi:
+            st["bucketG"].launch()
+            st["bucketG"].finish()
+        if optimize:
+            st["optG"].step()
+        return errD.detach(), errG.detach(), kl_loss.detach()
+
+    # ------------------------------------------------------------------ epoch loop
+    def train(self, data_loader, stage=1, max_objects=3):
+        """trainer.py:110-283.  ``data_loader`` yields (real_img, bbox, label, txt_embedding) like the reference's
+        ``TextDataset`` (stage II: bbox is the [stage-I-scaled, stage-II-scaled] pair)."""
+        nets = self.load_network_stageI() if stage == 1 else self.load_network_stageII()
+        if nets is None:
+            return
+        netG, netD = nets
+        dev = next(netD.parameters()).device
+        optimizerG, optimizerD = self.define_optimizers(netG, netD)
+        st = self.make_step_state(netG, netD, optimizerG, optimizerD)
+        generator_lr, discriminator_lr = cfg.TRAIN.GENERATOR_LR, cfg.TRAIN.DISCRIMINATOR_LR
+        epoch = 0
+        for epoch in range(self.max_epoch):
+            start_t = time.time()
+            if epoch % cfg.TRAIN.LR_DECAY_EPOCH == 0 and epoch > 0:   # trainer.py:141-147
+                generator_lr *= 0.5
+                discriminator_lr *= 0.5
+                for g in optimizerG.param_groups:
+                    g['lr'] = generator_lr
+                for g in optimizerD.param_groups:
+                    g['lr'] = discriminator_lr
+            errD = errG = kl = torch.zeros(())
+            for real_img_cpu, bbox, label, txt_embedding in data_loader:
+                real_imgs = real_img_cpu.to(dev, non_blocking=True)
+                txt_embedding = txt_embedding.to(dev, non_blocking=True).float()
+                B = real_imgs.shape[0]
+                kw = {}
+                if stage == 1:
+                    bb = bbox.to(dev).view(-1, 4).float()
+                    tinv = compute_transformation_matrix_inverse(bb).view(B, max_objects, 2, 3)
+                    kw["transf_matrices"] = compute_transformation_matrix(bb).view(B, max_objects, 2, 3)
+                else:
+                    b1, b2 = bbox[0].to(dev).view(-1, 4).float(), bbox[1].to(dev).view(-1, 4).float()
+                    tinv = compute_transformation_matrix_inverse(b1).view(B, max_objects, 2, 3)
+                    kw["transf_matrices_inv_s2"] = compute_transformation_matrix_inverse(b2).view(B, max_objects, 2, 3)
+                    kw["transf_matrices_s2"] = compute_transformation_matrix(b2).view(B, max_objects, 2, 3)
+                _labels = label.to(dev).long().clone()
+                _labels[_labels < 0] = 80                                # trainer.py:186-189
+                label_one_hot = torch.zeros(B, max_objects, 81, device=dev).scatter_(2, _labels.view(B, max_objects, 1), 1.0)
+                errD, errG, kl = self.train_step(st, real_imgs, txt_embedding, label_one_hot, tinv, stage=stage, **kw)
+            if parallel.rank() == 0:
+                print('[%d/%d] Loss_D: %.4f Loss_G: %.4f Loss_KL: %.4f Total Time: %.2fsec'
+                      % (epoch, self.max_epoch, float(errD), float(errG), float(kl), time.time() - start_t))
+                if epoch % self.snapshot_interval == 0:
+                    save_model(netG, netD, optimizerG, optimizerD, epoch, self.model_dir)
+        if parallel.rank() == 0:
+            save_model(netG, netD, optimizerG, optimizerD, epoch, self.model_dir)

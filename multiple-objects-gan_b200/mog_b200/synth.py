@@ -185,3 +185,40 @@ def stage1_batch(program: str, B: int, nz: int = 100, seed: int = 1234) -> dict:
     out["transf_matrices"] = transformation_matrix(flat).reshape(B, S, 2, 3)
     out["transf_matrices_inv"] = transformation_matrix_inverse(flat).reshape(B, S, 2, 3)
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}
+
+
+def stackgan_batch(B: int, stage: int = 1, t_dim: int = 1024, nz: int = 100, c_dim: int = 128, seed: int = 1234) -> dict:
+    """Synthetic batch for the COCO StackGAN program: ``txt_embedding``
+    N(0,1) B x t_dim (char-CNN-RNN stand-in), real images U(-1,1) at 64^2 (stage I) or 256^2 (stage II),
+    up to 3 boxes per image with labels 0..79 (80 = empty slot).  Stage II carries two box sets like
+    ``stackgan/miscc/datasets.py:134-179``: the same objects scaled for the 64^2 stage-I generator
+    (76 -> 64 crop) and for the stage-II image; ``eps1`` / ``eps2`` are the CA_NET draws (stage-I net
+    first, ``stackgan/model.py:379,386``)."""
+    rng = np.random.RandomState(seed)
+    out = {"noise": rng.standard_normal((B, nz)).astype(np.float32),
+           "txt_embedding": rng.standard_normal((B, t_dim)).astype(np.float32)}
+    size = 64 if stage == 1 else 256
+    out["imgs"] = rng.uniform(-1, 1, size=(B, 3, size, size)).astype(np.float32)
+    bbox, label, onehot, theta, theta_inv = bboxes_and_labels(rng, B)
+    out["label_one_hot"] = onehot
+    if stage == 1:
+        out["transf_matrices"], out["transf_matrices_inv"] = theta, theta_inv
+    else:
+        # stage-I view of the same boxes: crop offset + 76/64 rescale, clipped like datasets.py:140-150
+        b1 = bbox.copy()
+        off = rng.uniform(0.0, 12.0 / 64.0, size=(B, 1, 2)).astype(np.float32)
+        valid = bbox[:, :, 0] >= 0
+        x = np.maximum(bbox[:, :, 0] * (76.0 / 64.0) - off[:, :, 0], 0.0)
+        y = np.maximum(bbox[:, :, 1] * (76.0 / 64.0) - off[:, :, 1], 0.0)
+        w = np.minimum(bbox[:, :, 2] * (76.0 / 64.0), 1.0)
+        h = np.minimum(bbox[:, :, 3] * (76.0 / 64.0), 1.0)
+        w = np.where(x + w > 0.999, 1.0 - x - 0.001, w)
+        h = np.where(y + h > 0.999, 1.0 - y - 0.001, h)
+        for i, v in enumerate((x, y, w, h)):
+            b1[:, :, i] = np.where(valid, v, -1.0)
+        flat1 = b1.reshape(-1, 4).astype(np.float32)
+        out["transf_matrices_inv"] = transformation_matrix_inverse(flat1).reshape(B, MAX_OBJECTS, 2, 3)
+        out["transf_matrices_s2"], out["transf_matrices_inv_s2"] = theta, theta_inv
+    out["eps1"] = rng.standard_normal((B, c_dim)).astype(np.float32)
+    out["eps2"] = rng.standard_normal((B, c_dim)).astype(np.float32)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}
