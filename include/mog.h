@@ -192,6 +192,21 @@ int mog_sigmoid_bce_fwd(const float* z, const float* target /*[n]*/, float weigh
 int mog_sigmoid_bce_bwd(const float* z, const float* target /*[n]*/, float weight, int n, const float* gscale,
                         float* dz, int with_logits, void* stream);
 
+/* ---- optimiser ----------------------------------------------------------------------------- */
+/* Fused multi-tensor Adam step (+ optional exponential moving average of the updated parameters).
+ * replaces: optim.Adam(betas=(0.5, 0.999)).step() per network (attngan/trainer.py:141-148,326,340;
+ *   stackgan/trainer.py:136-137,218,234; multi-mnist/trainer.py:103-104; clevr/trainer.py:100-101) and the EMA
+ *   loop `avg_p.mul_(0.999).add_(0.001, p.data)` (attngan/trainer.py:341-342).
+ * p/g/m/v/ema: HOST arrays of n device pointers (fp32 tensors of numel[i] elements; ema == NULL or ema[i] == NULL: no EMA);
+ * `step` is the 1-based index of the step being taken (bias corrections 1 - beta^step); gradients are multiplied by
+ * grad_scale first (1/world after an all-reduce(sum)).  Same arithmetic as torch's Adam (no weight decay, no amsgrad):
+ *   m = lerp(m, g, 1-beta1); v = beta2 v + (1-beta2) g^2; p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps);
+ *   ema = ema_decay * ema + (1 - ema_decay) * p.
+ * The pointer tables travel in kernel parameters (<= 56 tensors per launch): nothing is staged or allocated. */
+int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
+                   const long long* numel, float lr, float beta1, float beta2, float eps, long long step, float ema_decay,
+                   float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

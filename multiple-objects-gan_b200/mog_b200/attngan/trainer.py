@@ -26,6 +26,7 @@ import time
 import torch
 import torch.optim as optim
 
+from .. import optim as mog_optim
 from .. import parallel
 from .miscc.config import cfg
 from .miscc.losses import KL_loss, discriminator_loss, format_logs, generator_loss
@@ -101,10 +102,12 @@ class condGANTrainer(object):
         return [text_encoder, image_encoder, netG, netsD, epoch]
 
     def define_optimizers(self, netG, netsD):
-        """trainer.py:139-160 -- Adam(lr, betas=(0.5, 0.999)) per network."""
-        optimizersD = [optim.Adam(d.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, betas=(0.5, 0.999))
-                       for d in netsD]
-        optimizerG = optim.Adam(netG.parameters(), lr=cfg.TRAIN.GENERATOR_LR, betas=(0.5, 0.999))
+        """trainer.py:139-160 -- Adam(lr, betas=(0.5, 0.999)) per network: the fused libmog optimiser on a GPU
+        (same state_dict layout as torch.optim.Adam), torch's own for CPU-resident modules (host-side tests)."""
+        on_gpu = next(netG.parameters()).is_cuda
+        A = mog_optim.Adam if on_gpu else optim.Adam
+        optimizersD = [A(d.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, betas=(0.5, 0.999)) for d in netsD]
+        optimizerG = A(netG.parameters(), lr=cfg.TRAIN.GENERATOR_LR, betas=(0.5, 0.999))
         if self.resume:
             ckpts = sorted(glob.glob(self.model_dir + "/" + '*.pth'))
             sd = torch.load(ckpts[-1], map_location='cpu')
@@ -141,6 +144,13 @@ class condGANTrainer(object):
         for m in models_list:
             for p in m.parameters():
                 p.requires_grad = brequires
+
+    @staticmethod
+    def _opt_step(opt, grad_scale=1.0):
+        if isinstance(opt, mog_optim.Adam):
+            opt.step(grad_scale=grad_scale)
+        else:
+            opt.step()
 
     # ------------------------------------------------------------------ the hot loop body
     def make_step_state(self, netG, netsD, optimizerG, optimizersD):
@@ -180,13 +190,14 @@ class condGANTrainer(object):
             if multi:
                 st["bucketDs"][i].launch()       # async all-reduce; next D computes meanwhile
             elif optimize:
-                st["optDs"][i].step()
+                self._opt_step(st["optDs"][i])
             errD_total = errD_total + errD.detach()
         if multi:
             for i in range(len(netsD)):
-                st["bucketDs"][i].finish()
+                fused = isinstance(st["optDs"][i], mog_optim.Adam)
+                st["bucketDs"][i].finish(scale=not fused)     # 1/world folded into the fused optimiser pass
                 if optimize:
-                    st["optDs"][i].step()
+                    self._opt_step(st["optDs"][i], grad_scale=1.0 / parallel.world() if fused else 1.0)
 
         # (4) update the generator; D weights frozen so their (discarded) wgrad is never computed
         self.set_requires_grad_value(netsD, False)
@@ -199,15 +210,20 @@ class condGANTrainer(object):
         errG_total = errG_total + kl_loss
         errG_total.backward()
         self.set_requires_grad_value(netsD, True)
+        fusedG = isinstance(st["optG"], mog_optim.Adam)
         if multi:
             st["bucketG"].launch()
-            st["bucketG"].finish()
+            st["bucketG"].finish(scale=not fusedG)
         if optimize:
-            st["optG"].step()
-            with torch.no_grad():   # EMA, trainer.py:341-342
-                params = list(netG.parameters())
-                torch._foreach_mul_(st["avg_param_G"], 0.999)
-                torch._foreach_add_(st["avg_param_G"], [p.data for p in params], alpha=0.001)
+            if fusedG:   # Adam + EMA (trainer.py:340-342) in one pass over the parameters
+                st["optG"].step(ema_params=st["avg_param_G"], ema_decay=0.999,
+                                grad_scale=1.0 / parallel.world() if multi else 1.0)
+            else:
+                st["optG"].step()
+                with torch.no_grad():   # EMA, trainer.py:341-342
+                    params = list(netG.parameters())
+                    torch._foreach_mul_(st["avg_param_G"], 0.999)
+                    torch._foreach_add_(st["avg_param_G"], [p.data for p in params], alpha=0.001)
         st["last_logs"] = logs
         return errD_total, errG_total.detach(), kl_loss.detach()
 

@@ -1,0 +1,85 @@
+"""Fused Adam (+ EMA) on libmog -- drop-in for ``torch.optim.Adam`` as the reference uses it
+(``optim.Adam(params, lr, betas=(0.5, 0.999))``: attngan/trainer.py:141-148, stackgan/trainer.py:136-137,
+multi-mnist/trainer.py:103-104, clevr/trainer.py:100-101) and for the EMA loop of attngan/trainer.py:341-342.
+
+Same constructor, ``param_groups`` and ``state_dict`` layout as ``torch.optim.Adam`` (per-parameter ``step``,
+``exp_avg``, ``exp_avg_sq``), so checkpoints written by either load in the other.  ``step()`` is ONE
+``mog_adam_multi`` call per parameter group (a handful of launches for a whole network instead of ~7 foreach
+kernels per 30 tensors); the EMA copy of the generator is updated in the same pass when ``ema_params`` is given.
+There is no CPU path: parameters must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import call
+
+
+class Adam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        if weight_decay != 0 or amsgrad:
+            raise ValueError("mog_b200.optim.Adam implements the reference's configuration only (no weight decay / amsgrad)")
+        if not 0.0 <= lr or not 0.0 <= eps or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
+            raise ValueError("invalid Adam hyper-parameter")
+        # the extra keys mirror torch.optim.Adam's defaults so that state_dicts interchange
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                      foreach=None, capturable=False, differentiable=False, fused=None,
+                                      decoupled_weight_decay=False))
+
+    @torch.no_grad()
+    def step(self, closure=None, ema_params=None, ema_decay=0.999, grad_scale=1.0):
+        """``ema_params``: optional dict ``param -> EMA tensor`` (or a list parallel to all parameters of all groups):
+        ``ema = ema_decay * ema + (1 - ema_decay) * param_new`` fused into the same pass."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if ema_params is not None and not isinstance(ema_params, dict):
+            allp = [p for g in self.param_groups for p in g["params"]]
+            ema_params = dict(zip(allp, ema_params))
+        for group in self.param_groups:
+            ps, gs, ms, vs, es, ns = [], [], [], [], [], []
+            step = None
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("mog_b200.optim.Adam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)")
+                g = p.grad
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["step"] += 1
+                t = int(state["step"].item()) if state["step"].device.type == "cpu" else int(state["step"])
+                if step is None:
+                    step = t
+                elif step != t:   # parameters of one group at different step counts: flush what we have
+                    self._launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale)
+                    ps, gs, ms, vs, es, ns = [], [], [], [], [], []
+                    step = t
+                e = ema_params.get(p) if ema_params is not None else None
+                ps.append(p.data_ptr()); gs.append(g.data_ptr()); ms.append(state["exp_avg"].data_ptr())
+                vs.append(state["exp_avg_sq"].data_ptr()); es.append(e.data_ptr() if e is not None else None)
+                ns.append(p.numel())
+                state["_keep"] = g   # the gradient must outlive the asynchronous launch
+            if ps:
+                self._launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale)
+        for group in self.param_groups:
+            for p in group["params"]:
+                self.state[p].pop("_keep", None) if p in self.state else None
+        return loss
+
+    @staticmethod
+    def _launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale):
+        n = len(ps)
+        arr = lambda xs: (C.c_void_p * n)(*xs)
+        b1, b2 = group["betas"]
+        call("mog_adam_multi", n, arr(ps), arr(gs), arr(ms), arr(vs), arr(es) if any(e is not None for e in es) else None,
+             (C.c_longlong * n)(*ns), float(group["lr"]), float(b1), float(b2), float(group["eps"]), int(step),
+             float(ema_decay), float(grad_scale), torch.cuda.current_stream().cuda_stream)

@@ -48,33 +48,41 @@ class GradBucket:
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        # every view starts on a 16-byte boundary so the fused optimiser keeps its 128-bit path
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.views = []
         off = 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += (p.numel() + 3) // 4 * 4
         self.handle = None
 
     def launch(self):
         if world() == 1:
             return
+        src, dst = [], []
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
+                src.append(p.grad)
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)     # one multi-tensor launch instead of one copy per parameter
         self.handle = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
 
-    def finish(self):
+    def finish(self, scale=True):
+        """``scale=False`` leaves the bucket as the SUM over ranks (the caller folds 1/world into the optimiser:
+        ``mog_b200.optim.Adam.step(grad_scale=1/world)``)."""
         if world() == 1:
             return
         if self.handle is not None:
             self.handle.wait()
             self.handle = None
-        self.flat.mul_(1.0 / world())
+        if scale:
+            self.flat.mul_(1.0 / world())
         for p, v in zip(self.params, self.views):
             p.grad = v
 

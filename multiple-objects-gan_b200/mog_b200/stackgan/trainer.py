@@ -20,6 +20,7 @@ import time
 import torch
 import torch.optim as optim
 
+from .. import optim as mog_optim
 from .. import parallel
 from .miscc.config import cfg
 from .miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator_loss, compute_transformation_matrix,
@@ -82,9 +83,9 @@ class GANTrainer(object):
 
     def define_optimizers(self, netG, netD):
         """trainer.py:131-137 -- Adam(betas=(0.5, 0.999)); only the trainable generator parameters."""
-        optimizerD = optim.Adam(netD.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, betas=(0.5, 0.999))
-        optimizerG = optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=cfg.TRAIN.GENERATOR_LR,
-                                betas=(0.5, 0.999))
+        A = mog_optim.Adam if next(netD.parameters()).is_cuda else optim.Adam   # fused libmog Adam on a GPU
+        optimizerD = A(netD.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, betas=(0.5, 0.999))
+        optimizerG = A([p for p in netG.parameters() if p.requires_grad], lr=cfg.TRAIN.GENERATOR_LR, betas=(0.5, 0.999))
         return optimizerG, optimizerD
 
     # ------------------------------------------------------------------ the hot loop body
