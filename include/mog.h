@@ -204,8 +204,8 @@ int mog_sigmoid_bce_bwd(const float* z, const float* target /*[n]*/, float weigh
  *   ema = ema_decay * ema + (1 - ema_decay) * p.
  * The pointer tables travel in kernel parameters (<= 56 tensors per launch): nothing is staged or allocated. */
 int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
-                   const long long* numel, float lr, float beta1, float beta2, float eps, long long step, float ema_decay,
-                   float grad_scale, void* stream);
+                   const long long* numel, double lr, double beta1, double beta2, double eps, long long step,
+                   double ema_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

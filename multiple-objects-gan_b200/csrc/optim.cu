@@ -107,22 +107,24 @@ using namespace mog;
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 extern "C" int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
-                              const long long* numel, float lr, float beta1, float beta2, float eps, long long step, float ema_decay,
-                              float grad_scale, void* stream) {
+                              const long long* numel, double lr, double beta1, double beta2, double eps, long long step,
+                              double ema_decay, float grad_scale, void* stream) {
   MOG_REQUIRE(n >= 0 && (n == 0 || (p && g && m && v && numel)), "mog_adam_multi: null array");
   MOG_REQUIRE(step >= 1, "mog_adam_multi: step must be >= 1 (the step being taken)");
-  MOG_REQUIRE(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "mog_adam_multi: bad hyper-parameter");
+  MOG_REQUIRE(lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., "mog_adam_multi: bad hyper-parameter");
   cudaStream_t st = as_stream(stream);
   AdamScalars S;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  S.w1 = (float)(1.0 - (double)beta1);
-  S.beta2 = beta2;
-  S.omb2 = (float)(1.0 - (double)beta2);
+  // hyper-parameters arrive as doubles (Python floats): 1 - beta must be formed in double like torch does, not from
+  // the rounded fp32 beta (1 - float(0.999) is off by 1.3e-5 relative)
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  S.w1 = (float)(1.0 - beta1);
+  S.beta2 = (float)beta2;
+  S.omb2 = (float)(1.0 - beta2);
   S.bc2_sqrt = (float)sqrt(bc2);
-  S.eps = eps;
-  S.neg_step = (float)(-(double)lr / bc1);
-  S.ema_decay = ema_decay;
-  S.ema_in = (float)(1.0 - (double)ema_decay);
+  S.eps = (float)eps;
+  S.neg_step = (float)(-lr / bc1);
+  S.ema_decay = (float)ema_decay;
+  S.ema_in = (float)(1.0 - ema_decay);
   S.grad_scale = grad_scale;
   int i = 0;
   while (i < n) {

@@ -61,7 +61,7 @@ SIGNATURES = {
     "mog_damsm_words_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "mog_sigmoid_bce_fwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _i, _p]),
     "mog_sigmoid_bce_bwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _p]),
-    "mog_adam_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, C.c_longlong, _f, _f, _p]),
+    "mog_adam_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_longlong, C.c_double, _f, _p]),
 }
 
 _lib = None

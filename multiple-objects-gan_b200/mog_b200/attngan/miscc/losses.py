@@ -22,20 +22,40 @@ def _features(netD, imgs, local_labels, transf_matrices, transf_matrices_inv):
     return netD(imgs)
 
 
+PAIR_PASS = True   # discriminator_loss: real + fake batch in one two-segment pass
+
+
 def discriminator_loss(netD, real_imgs, fake_imgs, conditions, real_labels, fake_labels, gpus=None,
                        local_labels=None, transf_matrices=None, transf_matrices_inv=None):
-    """losses.py:136-174"""
-    real_features = _features(netD, real_imgs, local_labels, transf_matrices, transf_matrices_inv)
-    fake_features = _features(netD, fake_imgs.detach(), local_labels, transf_matrices, transf_matrices_inv)
+    """losses.py:136-174.  The real and the fake batch (same size) go through the discriminator and its conditional
+    head in ONE pass as two BatchNorm segments -- the statistics, running-stat updates and results of the reference's
+    separate calls, with every weight streamed once (``PAIR_PASS = False`` restores the call-by-call form)."""
     bce = ops.sigmoid_bce
-    cond_real_errD = bce(netD.COND_DNET.logits(real_features, conditions), real_labels)
-    cond_fake_errD = bce(netD.COND_DNET.logits(fake_features, conditions), fake_labels)
-    batch_size = real_features.size(0)
+    batch_size = real_imgs.size(0)
+    if PAIR_PASS and hasattr(netD, "forward_pair") and fake_imgs.shape == real_imgs.shape:
+        if local_labels is not None:
+            both = netD.forward_pair(real_imgs, fake_imgs.detach(), local_labels, transf_matrices, transf_matrices_inv)
+        else:
+            both = netD.forward_pair(real_imgs, fake_imgs.detach())
+        real_features, fake_features = both[:batch_size], both[batch_size:]
+        cond = netD.COND_DNET.logits(both, torch.cat((conditions, conditions), 0), segments=2)
+        cond_real_errD = bce(cond[:batch_size], real_labels)
+        cond_fake_errD = bce(cond[batch_size:], fake_labels)
+        uncond = netD.UNCOND_DNET.logits(both) if netD.UNCOND_DNET is not None else None
+    else:
+        real_features = _features(netD, real_imgs, local_labels, transf_matrices, transf_matrices_inv)
+        fake_features = _features(netD, fake_imgs.detach(), local_labels, transf_matrices, transf_matrices_inv)
+        cond_real_errD = bce(netD.COND_DNET.logits(real_features, conditions), real_labels)
+        cond_fake_errD = bce(netD.COND_DNET.logits(fake_features, conditions), fake_labels)
+        uncond = None
     cond_wrong_errD = bce(netD.COND_DNET.logits(real_features[:(batch_size - 1)], conditions[1:batch_size]),
                           fake_labels[1:batch_size])
     if netD.UNCOND_DNET is not None:
-        real_errD = bce(netD.UNCOND_DNET.logits(real_features), real_labels)
-        fake_errD = bce(netD.UNCOND_DNET.logits(fake_features), fake_labels)
+        if uncond is not None:
+            real_errD, fake_errD = bce(uncond[:batch_size], real_labels), bce(uncond[batch_size:], fake_labels)
+        else:
+            real_errD = bce(netD.UNCOND_DNET.logits(real_features), real_labels)
+            fake_errD = bce(netD.UNCOND_DNET.logits(fake_features), fake_labels)
         errD = ((real_errD + cond_real_errD) / 2. + (fake_errD + cond_fake_errD + cond_wrong_errD) / 3.)
     else:
         errD = cond_real_errD + (cond_fake_errD + cond_wrong_errD) / 2.

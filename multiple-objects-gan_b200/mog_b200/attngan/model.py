@@ -303,11 +303,11 @@ def downBlock(in_planes, out_planes):
 class _Encode16(nn.Sequential):
     """model.py:595-613 (Sequential indices 0..10 as in the reference)."""
 
-    def forward(self, x):
+    def forward(self, x, segments=1):
         x = self[0](x, act=ACT_LRELU)
-        x = ops.bn_act(self[2](x), self[3], ACT_LRELU)
-        x = ops.bn_act(self[5](x), self[6], ACT_LRELU)
-        return ops.bn_act(self[8](x), self[9], ACT_LRELU)
+        x = ops.bn_act(self[2](x), self[3], ACT_LRELU, segments=segments)
+        x = ops.bn_act(self[5](x), self[6], ACT_LRELU, segments=segments)
+        return ops.bn_act(self[8](x), self[9], ACT_LRELU, segments=segments)
 
 
 def encode_image_by_16times(ndf):
@@ -329,16 +329,18 @@ class D_GET_LOGITS(nn.Module):
             self.jointConv = Block3x3_leakRelu(ndf * 8 + nef, ndf * 8)
         self.outlogits = nn.Sequential(Conv2d(ndf * 8, 1, 4, 4, 0, bias=True), Sigmoid())
 
-    def _joint(self, h_code, c_code):
+    def _joint(self, h_code, c_code, segments=1):
         h = ops.nhwc(h_code)
         if self.bcondition and c_code is not None:
             B = h.shape[0]
             c = c_code.reshape(B, 1, 1, self.ef_dim).expand(B, 4, 4, self.ef_dim)
-            h = self.jointConv(torch.cat((h, c), 3))
+            h = self.jointConv(torch.cat((h, c), 3), segments=segments)
         return h
 
-    def logits(self, h_code, c_code=None):
-        return self.outlogits[0](self._joint(h_code, c_code)).reshape(-1)
+    def logits(self, h_code, c_code=None, segments=1):
+        """``segments`` > 1: ``h_code`` holds that many equally sized batches back to back, each normalised with its
+        own BatchNorm statistics -- numerically what consecutive calls on the separate batches do."""
+        return self.outlogits[0](self._joint(h_code, c_code, segments)).reshape(-1)
 
     def forward(self, h_code, c_code=None):
         return self.outlogits[0](self._joint(h_code, c_code), act=ACT_SIGMOID).reshape(-1)
@@ -367,22 +369,36 @@ class D_NET64(nn.Module):
         self.local = _CBLeaky(Conv2d(3 + 81, ndf * 2, 4, 1, 1, bias=False), nn.BatchNorm2d(ndf * 2),
                                   LeakyReLU(0.2, inplace=True))
 
-    def forward(self, image, label, transf_matrices, transf_matrices_inv):
-        x = ops.nhwc(image)
-        B, S = x.shape[0], MAX_OBJECTS
+    def _locals(self, x, label, transf_matrices, transf_matrices_inv):
         # object pathway: crop each box to 16x16 (+81 label planes), 4x4/s1 conv -> 15x15, BN per
         # object, LeakyReLU, paste back to 16x16 by theta^-1 and sum over objects
+        B, S = x.shape[0], MAX_OBJECTS
         h = ops.stn_crop(x, transf_matrices.contiguous(), S, (16, 16), extra=label.contiguous(),
                          align_corners=cfg.MOG.ALIGN_CORNERS)
         h = self.local(h, segments=S)
-        h_code_locals = ops.stn_scatter_sum(h, transf_matrices_inv.contiguous(), B, S, (16, 16),
-                                            cfg.MOG.ALIGN_CORNERS)
+        return ops.stn_scatter_sum(h, transf_matrices_inv.contiguous(), B, S, (16, 16), cfg.MOG.ALIGN_CORNERS)
+
+    def _trunk(self, x, h_code_locals, segments=1):
         h = self.conv1(x, act=ACT_LRELU)
-        h = ops.bn_act(self.conv2(h), self.bn2, ACT_LRELU)
+        h = ops.bn_act(self.conv2(h), self.bn2, ACT_LRELU, segments=segments)
         h = torch.cat((h, h_code_locals), 3)
-        h = ops.bn_act(self.conv3(h), self.bn3, ACT_LRELU)
-        h = ops.bn_act(self.conv4(h), self.bn4, ACT_LRELU)
+        h = ops.bn_act(self.conv3(h), self.bn3, ACT_LRELU, segments=segments)
+        h = ops.bn_act(self.conv4(h), self.bn4, ACT_LRELU, segments=segments)
         return ops.to_nchw_view(h)
+
+    def forward(self, image, label, transf_matrices, transf_matrices_inv):
+        x = ops.nhwc(image)
+        return self._trunk(x, self._locals(x, label, transf_matrices, transf_matrices_inv))
+
+    def forward_pair(self, real, fake, label, transf_matrices, transf_matrices_inv):
+        """``(self(real, ...), self(fake, ...))`` in one pass: both batches run through every layer back to back as two
+        BatchNorm *segments* (own batch statistics, running stats updated real-then-fake like the two calls of
+        losses.py:146-152), so each weight is streamed once and its gradient is one reduction over 2B samples.
+        The object pathway keeps the reference's order of its six BatchNorm updates (real objects, then fake)."""
+        xr, xf = ops.nhwc(real), ops.nhwc(fake)
+        loc = torch.cat((self._locals(xr, label, transf_matrices, transf_matrices_inv),
+                         self._locals(xf, label, transf_matrices, transf_matrices_inv)), 0)
+        return self._trunk(torch.cat((xr, xf), 0), loc, segments=2)
 
 
 class D_NET128(nn.Module):
@@ -397,10 +413,14 @@ class D_NET128(nn.Module):
         self.UNCOND_DNET = D_GET_LOGITS(ndf, nef, bcondition=False) if b_jcu else None
         self.COND_DNET = D_GET_LOGITS(ndf, nef, bcondition=True)
 
-    def forward(self, x_var):
-        x = self.img_code_s16(ops.nhwc(x_var))
-        x = self.img_code_s32(x)
-        return ops.to_nchw_view(self.img_code_s32_1(x))
+    def forward(self, x_var, segments=1):
+        x = self.img_code_s16(ops.nhwc(x_var), segments=segments)
+        x = self.img_code_s32(x, segments=segments)
+        return ops.to_nchw_view(self.img_code_s32_1(x, segments=segments))
+
+    def forward_pair(self, real, fake):
+        """Both batches in one pass as two BatchNorm segments (see D_NET64.forward_pair)."""
+        return self.forward(torch.cat((ops.nhwc(real), ops.nhwc(fake)), 0).permute(0, 3, 1, 2), segments=2)
 
 
 class D_NET256(nn.Module):
@@ -417,9 +437,13 @@ class D_NET256(nn.Module):
         self.UNCOND_DNET = D_GET_LOGITS(ndf, nef, bcondition=False) if b_jcu else None
         self.COND_DNET = D_GET_LOGITS(ndf, nef, bcondition=True)
 
-    def forward(self, x_var):
-        x = self.img_code_s16(ops.nhwc(x_var))
-        x = self.img_code_s32(x)
-        x = self.img_code_s64(x)
-        x = self.img_code_s64_1(x)
-        return ops.to_nchw_view(self.img_code_s64_2(x))
+    def forward(self, x_var, segments=1):
+        x = self.img_code_s16(ops.nhwc(x_var), segments=segments)
+        x = self.img_code_s32(x, segments=segments)
+        x = self.img_code_s64(x, segments=segments)
+        x = self.img_code_s64_1(x, segments=segments)
+        return ops.to_nchw_view(self.img_code_s64_2(x, segments=segments))
+
+    def forward_pair(self, real, fake):
+        """Both batches in one pass as two BatchNorm segments (see D_NET64.forward_pair)."""
+        return self.forward(torch.cat((ops.nhwc(real), ops.nhwc(fake)), 0).permute(0, 3, 1, 2), segments=2)
