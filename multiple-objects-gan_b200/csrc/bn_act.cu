@@ -5,6 +5,8 @@
 // warp/smem reductions and one double atomicAdd per (block, channel).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mog {
@@ -319,8 +321,12 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 // 16-byte access and consecutive threads cover a contiguous row segment; 4 rows are in flight per thread.
 // The scalar kernels above remain for odd channel counts.
 // ---------------------------------------------------------------------------------------------
-struct V4Geom { int Cv, GB, R, nxb, rpb; };
-static V4Geom v4_geom(int width, int M) {
+struct V4Geom { int Cv, GB, R, nxb, rpb, nyb; };
+// reduce = true: the reducing kernels (statistics, backward sums) end in one double atomicAdd per channel per block.
+// Same-address fp64 atomics serialise in L2 at ~55 ns each (measured: 6554 blocks -> 320 us for a pass that streams in
+// 125 us), so those kernels run a fixed, small number of blocks (about two per SM over all column groups and segments),
+// each looping over its row chunks with the sums kept in registers.
+static V4Geom v4_geom(int width, int M, int S = 1, bool reduce = false) {
   V4Geom g;
   g.Cv = width / 4;
   g.nxb = ceil_div(g.Cv, 32);
@@ -329,6 +335,18 @@ static V4Geom v4_geom(int width, int M) {
   if (g.R > 32) g.R = 32;
   g.rpb = g.R * 32;
   while (ceil_div(M, g.rpb) > 65535) g.rpb *= 2;
+  g.nyb = ceil_div(M, g.rpb);
+  if (reduce) {
+    static int per_sm = -1;
+    if (per_sm < 0) {
+      const char* e = getenv("MOG_BN_BLOCKS_PER_SM");   // tuning knob; 0 = one block per row chunk (no cap)
+      per_sm = e ? atoi(e) : 2;
+    }
+    if (per_sm == 0) return g;
+    int cap = (per_sm * kNumSMs) / (g.nxb * (S > 0 ? S : 1));
+    if (cap < 1) cap = 1;
+    if (g.nyb > cap) g.nyb = cap;
+  }
   return g;
 }
 
@@ -337,8 +355,8 @@ __device__ __forceinline__ void to_arr(const float4& v, float (&a)[4]) { a[0] = 
 
 // block-level sum over the R row lanes of NV per-thread values (4 channels each), then one double atomicAdd per channel
 template <int NV>
-__device__ __forceinline__ void v4_block_reduce(float (&v)[NV][4], int GB, int R, int cgl, int rl, bool valid, double* const (&dst)[NV]) {
-  __shared__ float red[NV][256 * 4];
+__device__ __forceinline__ void v4_block_reduce(double (&v)[NV][4], int GB, int R, int cgl, int rl, bool valid, double* const (&dst)[NV]) {
+  __shared__ double red[NV][256 * 4];
   const int t = rl * GB + cgl;
 #pragma unroll
   for (int k = 0; k < NV; ++k)
@@ -351,7 +369,7 @@ __device__ __forceinline__ void v4_block_reduce(float (&v)[NV][4], int GB, int R
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         double acc = 0.0;
-        for (int i = 0; i < R; ++i) acc += (double)red[k][(i * GB + cgl) * 4 + j];
+        for (int i = 0; i < R; ++i) acc += red[k][(i * GB + cgl) * 4 + j];
         atomicAdd(dst[k] + j, acc);
       }
   }
@@ -362,18 +380,22 @@ __global__ void bn_stats_v4_kernel(const float* __restrict__ x, int M, int C, V4
   const int cg = blockIdx.x * g.GB + cgl;
   const bool valid = cg < g.Cv;
   const int c = cg * 4, s = blockIdx.z;
-  const long long r_begin = (long long)blockIdx.y * g.rpb;
-  long long r_end = r_begin + g.rpb;
-  if (r_end > M) r_end = M;
-  float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  double v[2][4] = {{0., 0., 0., 0.}, {0., 0., 0., 0.}};
   if (valid) {
     const float* xp = x + ((size_t)s * M) * C + c;
-#pragma unroll 4
-    for (long long r = r_begin + rl; r < r_end; r += g.R) {
-      float a[4];
-      to_arr(ld4(xp + (size_t)r * C), a);
+    for (long long r_begin = (long long)blockIdx.y * g.rpb; r_begin < M; r_begin += (long long)gridDim.y * g.rpb) {
+      long long r_end = r_begin + g.rpb;
+      if (r_end > M) r_end = M;
+      float f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // fp32 over <= rpb / R rows, then folded into the doubles
+#pragma unroll 8
+      for (long long r = r_begin + rl; r < r_end; r += g.R) {
+        float a[4];
+        to_arr(ld4(xp + (size_t)r * C), a);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[0][j] += a[j]; v[1][j] = fmaf(a[j], a[j], v[1][j]); }
+        for (int j = 0; j < 4; ++j) { f[0][j] += a[j]; f[1][j] = fmaf(a[j], a[j], f[1][j]); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[0][j] += (double)f[0][j]; v[1][j] += (double)f[1][j]; }
     }
   }
   double* const dst[2] = {sum + (size_t)s * C + c, sqsum + (size_t)s * C + c};
@@ -433,36 +455,47 @@ __global__ void bn_bwd_reduce_v4_kernel(BnBwdArgs a, V4Geom g, double* __restric
   const int cg = blockIdx.x * g.GB + cgl;
   const bool valid = cg < g.Cv;
   const int c = cg * 4, s = blockIdx.z;
-  const long long r_begin = (long long)blockIdx.y * g.rpb;
-  long long r_end = r_begin + g.rpb;
-  if (r_end > a.M) r_end = a.M;
-  float v[GLU ? 4 : 2][4];
+  constexpr int NV = GLU ? 4 : 2;
+  double v[NV][4];
 #pragma unroll
-  for (int k = 0; k < (GLU ? 4 : 2); ++k)
+  for (int k = 0; k < NV; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[k][j] = 0.f;
+    for (int j = 0; j < 4; ++j) v[k][j] = 0.;
   if (valid) {
     Aff4 kv, kg;
     load_aff4(a, s, c, kv);
     if (GLU) load_aff4(a, s, c + Co, kg); else kg = kv;
     const float* xp = a.x + ((size_t)s * a.M) * a.C + c;
     const float* yp = a.dy + ((size_t)s * a.M) * Co + c;
-#pragma unroll 2
-    for (long long r = r_begin + rl; r < r_end; r += g.R) {
-      float xv[4], xg[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], dzv[4], dzg[4];
-      to_arr(ld4(xp + (size_t)r * a.C), xv);
-      if (GLU) to_arr(ld4(xp + (size_t)r * a.C + Co), xg);
-      to_arr(ld4(yp + (size_t)r * Co), gy);
-      dz_row<ACT>(kv, kg, xv, xg, gy, dzv, dzg);
+    for (long long r_begin = (long long)blockIdx.y * g.rpb; r_begin < a.M; r_begin += (long long)gridDim.y * g.rpb) {
+      long long r_end = r_begin + g.rpb;
+      if (r_end > a.M) r_end = a.M;
+      float f[NV][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[0][j] += dzv[j];
-        v[1][j] = fmaf(dzv[j], (xv[j] - kv.mu[j]) * kv.is[j], v[1][j]);
-        if (GLU) {
-          v[2][j] += dzg[j];
-          v[3][j] = fmaf(dzg[j], (xg[j] - kg.mu[j]) * kg.is[j], v[3][j]);
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[k][j] = 0.f;
+#pragma unroll 4
+      for (long long r = r_begin + rl; r < r_end; r += g.R) {
+        float xv[4], xg[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], dzv[4], dzg[4];
+        to_arr(ld4(xp + (size_t)r * a.C), xv);
+        if (GLU) to_arr(ld4(xp + (size_t)r * a.C + Co), xg);
+        to_arr(ld4(yp + (size_t)r * Co), gy);
+        dz_row<ACT>(kv, kg, xv, xg, gy, dzv, dzg);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[0][j] += dzv[j];
+          f[1][j] = fmaf(dzv[j], (xv[j] - kv.mu[j]) * kv.is[j], f[1][j]);
+          if (GLU) {
+            f[2 % NV][j] += dzg[j];
+            f[3 % NV][j] = fmaf(dzg[j], (xg[j] - kg.mu[j]) * kg.is[j], f[3 % NV][j]);
+          }
         }
       }
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[k][j] += (double)f[k][j];
     }
   }
   if constexpr (GLU) {
@@ -501,7 +534,7 @@ __global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __re
   const float* xp = a.x + ((size_t)s * a.M) * a.C + c;
   const float* yp = a.dy + ((size_t)s * a.M) * Co + c;
   float* dp = dx + ((size_t)s * a.M) * a.C + c;
-#pragma unroll 2
+#pragma unroll 4
   for (long long r = r_begin + rl; r < r_end; r += g.R) {
     float xv[4], xg[4] = {0.f, 0.f, 0.f, 0.f}, gy[4], dzv[4], dzg[4], o[4];
     to_arr(ld4(xp + (size_t)r * a.C), xv);
@@ -521,7 +554,7 @@ __global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __re
 
 template <int ACT>
 static void launch_bwd_v4(bool reduce, const BnBwdArgs& a, const V4Geom& g, double* dgamma, double* dbeta, float* dx, cudaStream_t st) {
-  dim3 grid(g.nxb, ceil_div(a.M, g.rpb), a.S);
+  dim3 grid(g.nxb, g.nyb, a.S);
   if (reduce)
     bn_bwd_reduce_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta);
   else
@@ -530,7 +563,7 @@ static void launch_bwd_v4(bool reduce, const BnBwdArgs& a, const V4Geom& g, doub
 static bool bwd_v4(bool reduce, const BnBwdArgs& a, double* dgamma, double* dbeta, float* dx, cudaStream_t st) {
   const int width = a.act == MOG_ACT_GLU ? a.C / 2 : a.C;
   if ((width & 3) || (a.C & 3) || a.S > 65535) return false;
-  const V4Geom g = v4_geom(width, a.M);
+  const V4Geom g = v4_geom(width, a.M, a.S, reduce);
   switch (a.act) {
     case MOG_ACT_NONE: launch_bwd_v4<MOG_ACT_NONE>(reduce, a, g, dgamma, dbeta, dx, st); break;
     case MOG_ACT_RELU: launch_bwd_v4<MOG_ACT_RELU>(reduce, a, g, dgamma, dbeta, dx, st); break;
@@ -554,8 +587,8 @@ extern "C" int mog_bn_stats(const float* x, int S, int M, int C, double* sum, do
   cudaMemsetAsync(sqsum, 0, sizeof(double) * S * C, st);
   MOG_REQUIRE(S <= 65535, "mog_bn_stats: too many segments");
   if ((C & 3) == 0) {
-    const V4Geom g = v4_geom(C, M);
-    bn_stats_v4_kernel<<<dim3(g.nxb, ceil_div(M, g.rpb), S), g.GB * g.R, 0, st>>>(x, M, C, g, sum, sqsum);
+    const V4Geom g = v4_geom(C, M, S, true);
+    bn_stats_v4_kernel<<<dim3(g.nxb, g.nyb, S), g.GB * g.R, 0, st>>>(x, M, C, g, sum, sqsum);
     return check_launch("bn_stats_v4_kernel");
   }
   const int rpb = rows_per_block(M);
