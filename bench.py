@@ -267,7 +267,7 @@ def run_mog(args):
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": ws * B, "words": CFG5["T"],
                            "parallelism": "dp%d (NCCL grad all-reduce per net)" % ws,
                            "precision": args.precision, "l2": "working set per step (>5 GB) exceeds the 126 MB L2; no flush needed",
-                           "optimizer": "torch Adam + EMA inside the timed region",
+                           "optimizer": "fused libmog Adam + EMA (mog_adam_multi) inside the timed region",
                            "algorithmic_gflop_per_image": 2 * GMAC_PER_IMAGE_GD,
                            "step_tflops_achieved": 2 * GMAC_PER_IMAGE_GD * 1e9 * value / 1e12},
                 "clocks": clocks, "gpu_launches": launches,

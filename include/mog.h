@@ -55,6 +55,8 @@ typedef struct MogConvDesc {
   int32_t up2x;          /* 1: the conv reads nearest-neighbour 2x upsampled input (upBlock)     */
   int32_t act;           /* fused epilogue: MOG_ACT_NONE / LRELU / TANH (bias added first)       */
   int32_t precision;     /* MOG_PREC_*                                                           */
+  int32_t pad_w1;        /* 0: `pad` applies to both axes; else 1 + padding along W (`pad` = along H):
+                            the 1x7 / 7x1 / 1x3 / 3x1 filters of the DAMSM image encoder (forward + dgrad) */
 } MogConvDesc;
 
 int mog_version(void);
@@ -206,6 +208,23 @@ int mog_sigmoid_bce_bwd(const float* z, const float* target /*[n]*/, float weigh
 int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
                    const long long* numel, double lr, double beta1, double beta2, double eps, long long step,
                    double ema_decay, float grad_scale, void* stream);
+
+/* ---- pooling / resize of the DAMSM image encoder -------------------------------------------- */
+/* replaces: F.max_pool2d(x, 3, 2) (attngan/model.py:264,271; Mixed_6a/7a of torchvision's Inception-v3),
+ *   F.avg_pool2d(x, 3, 1, 1) (Inception branch_pool; divisor k*k, count_include_pad), F.avg_pool2d(x, 8) (model.py:301)
+ *   and their autograd.  NHWC fp32; mode 0 = max, 1 = average; output size floor((H + 2 pad - k) / stride) + 1.
+ * Backward is a deterministic gather; for max pooling it recomputes each window's arg-max from the forward input x
+ * with torch's tie rule (first maximum in scan order). */
+int mog_pool2d_out_hw(int H, int W, int k, int stride, int pad, int* Ho, int* Wo);
+int mog_pool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad, int mode, void* stream);
+int mog_pool2d_bwd(const float* x /*NULL for average*/, const float* dy, float* dx, int N, int H, int W, int C, int k,
+                   int stride, int pad, int mode, void* stream);
+/* replaces: nn.Upsample(size=(299, 299), mode='bilinear')(x) (attngan/model.py:256) = torch upsample_bilinear2d
+ *   (source index scale*(o + 0.5) - 0.5 clamped at 0 for align_corners = 0) and its autograd (upsampling only). */
+int mog_resize_bilinear_fwd(const float* x, float* y, int N, int Hi, int Wi, int C, int Ho, int Wo, int align_corners,
+                            void* stream);
+int mog_resize_bilinear_bwd(const float* dy, float* dx, int N, int Hi, int Wi, int C, int Ho, int Wo, int align_corners,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,22 +26,25 @@ __global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int KHW);
 }  // namespace mog
 
+// padding along W: MogConvDesc.pad_w1 = 1 + pad_w, or 0 for "same as pad" (the 1x7 / 7x1 / 1x3 / 3x1 filters of the DAMSM image encoder)
+static int padw(const MogConvDesc* d) { return d->pad_w1 > 0 ? d->pad_w1 - 1 : d->pad; }
+
 static int validate(const MogConvDesc* d, const char* who) {
   MOG_REQUIRE(d, "%s: null descriptor", who);
   MOG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "%s: non-positive dims", who);
   MOG_REQUIRE(d->KH > 0 && d->KW > 0 && d->KH <= 8 && d->KW <= 8 && d->KH * d->KW <= 64, "%s: filter %dx%d unsupported", who, d->KH, d->KW);
-  MOG_REQUIRE(d->stride >= 1 && d->stride <= 4 && d->pad >= 0, "%s: bad stride/pad", who);
+  MOG_REQUIRE(d->stride >= 1 && d->stride <= 4 && d->pad >= 0 && d->pad_w1 >= 0, "%s: bad stride/pad", who);
   MOG_REQUIRE(d->up2x == 0 || d->up2x == 1, "%s: up2x must be 0/1", who);
   MOG_REQUIRE(d->precision >= MOG_PREC_FP32 && d->precision <= MOG_PREC_BF16, "%s: unknown precision %d", who, d->precision);
   int HL = d->H << d->up2x, WL = d->W << d->up2x;
-  MOG_REQUIRE(HL + 2 * d->pad >= d->KH && WL + 2 * d->pad >= d->KW, "%s: filter larger than padded input", who);
+  MOG_REQUIRE(HL + 2 * d->pad >= d->KH && WL + 2 * padw(d) >= d->KW, "%s: filter larger than padded input", who);
   return MOG_OK;
 }
 
 static void out_hw(const MogConvDesc* d, int* Ho, int* Wo) {
   int HL = d->H << d->up2x, WL = d->W << d->up2x;
   *Ho = (HL + 2 * d->pad - d->KH) / d->stride + 1;
-  *Wo = (WL + 2 * d->pad - d->KW) / d->stride + 1;
+  *Wo = (WL + 2 * padw(d) - d->KW) / d->stride + 1;
 }
 
 static int passes_of(const MogConvDesc* d) { return d->precision == MOG_PREC_BF16X3 ? 3 : 1; }
@@ -73,7 +76,7 @@ static void fwd_single(const MogConvDesc* d, Problem* q) {
   p.Hr = Ho; p.Wr = Wo; p.rs = d->stride;
   p.nth = d->KH; p.ntw = d->KW;
   for (int i = 0; i < d->KH; ++i) p.off_h[i] = i - d->pad;
-  for (int i = 0; i < d->KW; ++i) p.off_w[i] = i - d->pad;
+  for (int i = 0; i < d->KW; ++i) p.off_w[i] = i - padw(d);
   for (int i = 0; i < d->KH * d->KW; ++i) p.tapw[i] = i;
   p.Cd = d->Cout; p.Hd = Ho; p.Wd = Wo; p.dsh = 1; p.doh = 0; p.dsw = 1; p.dow = 0;
   p.act = d->act;
@@ -100,7 +103,7 @@ static bool dgrad_phase(const MogConvDesc* d, int ph, int pw, Problem* q) {
   for (int kh = 0; kh < d->KH; ++kh)
     if (pmod(ph + d->pad - kh, s) == 0) { khs[nth] = kh; p.off_h[nth] = (ph + d->pad - kh) / s; ++nth; }
   for (int kw = 0; kw < d->KW; ++kw)
-    if (pmod(pw + d->pad - kw, s) == 0) { kws[ntw] = kw; p.off_w[ntw] = (pw + d->pad - kw) / s; ++ntw; }
+    if (pmod(pw + padw(d) - kw, s) == 0) { kws[ntw] = kw; p.off_w[ntw] = (pw + padw(d) - kw) / s; ++ntw; }
   if (nth == 0 || ntw == 0) { nth = 0; ntw = 1; }  // no tap reaches this phase: K = 0, zeros are written
   p.nth = nth; p.ntw = ntw;
   clear_taps(q);
@@ -139,7 +142,7 @@ static int phase_axis(int a, int K, int pad, int* offs, int (*members)[2]) {
 }
 static void up2x_phase(const MogConvDesc* d, int a, int b, bool dgrad, Problem* q) {
   int oh[4], ow[4], mh[4][2], mw[4][2];
-  const int nth = phase_axis(a, d->KH, d->pad, oh, mh), ntw = phase_axis(b, d->KW, d->pad, ow, mw);
+  const int nth = phase_axis(a, d->KH, d->pad, oh, mh), ntw = phase_axis(b, d->KW, padw(d), ow, mw);
   IGemmParams p{};
   p.N = d->N; p.up2x = 0; p.rs = 1; p.nth = nth; p.ntw = ntw;
   p.Hr = d->H; p.Wr = d->W;
@@ -189,7 +192,7 @@ static bool strided_view(const MogConvDesc* d, int a, int b, Problem* q) {
   for (int kh = 0; kh < d->KH; ++kh)
     if (pmod(kh - d->pad, s) == a) { khs[nth] = kh; p.off_h[nth] = fdiv(kh - d->pad - a, s); ++nth; }
   for (int kw = 0; kw < d->KW; ++kw)
-    if (pmod(kw - d->pad, s) == b) { kws[ntw] = kw; p.off_w[ntw] = fdiv(kw - d->pad - b, s); ++ntw; }
+    if (pmod(kw - padw(d), s) == b) { kws[ntw] = kw; p.off_w[ntw] = fdiv(kw - padw(d) - b, s); ++ntw; }
   if (nth == 0 || ntw == 0) return false;
   p.nth = nth; p.ntw = ntw;
   clear_taps(q);
@@ -214,7 +217,7 @@ static int build_fwd(const MogConvDesc* d, Problem* out) {
   }
   if (d->stride > 1 && !d->up2x && (d->H % d->stride) == 0 && (d->W % d->stride) == 0) {
     Problem probe;
-    if (strided_view(d, pmod(-d->pad, d->stride), pmod(-d->pad, d->stride), &probe) && halo_shape_eligible(probe.g)) {
+    if (strided_view(d, pmod(-d->pad, d->stride), pmod(-padw(d), d->stride), &probe) && halo_shape_eligible(probe.g)) {
       int n = 0;
       for (int a = 0; a < d->stride; ++a)
         for (int b = 0; b < d->stride; ++b)
@@ -497,6 +500,7 @@ extern "C" int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const void
   if (rc) return rc;
   MOG_REQUIRE((x || x_planes) && (dy || dy_planes) && dw, "mog_conv2d_wgrad: null tensor");
   MOG_REQUIRE(!dbias || dy, "mog_conv2d_wgrad: the bias gradient needs the fp32 dy");
+  if (padw(d) != d->pad) return fail(MOG_ERR_UNSUPPORTED, "mog_conv2d_wgrad: different padding along H and W is implemented for the forward conv and the data gradient only");
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
   size_t need = mog_conv_workspace_bytes(d, 2);

@@ -1,0 +1,234 @@
+// pool.cu -- pooling and bilinear resize of the DAMSM image encoder (NHWC fp32, HBM-bound streaming kernels).
+//
+// replaces (code/coco/attngan/model.py): nn.Upsample(size=(299, 299), mode='bilinear') (:256), F.max_pool2d(x, 3, 2)
+// (:264,271 and inside Mixed_6a / Mixed_7a), F.avg_pool2d(x, 3, 1, 1) of the Inception branch_pool paths,
+// F.avg_pool2d(x, 8) (:301) -- and their autograd (the encoder is frozen, but the gradient w.r.t. the generated image
+// flows through every one of them, losses.py:205-224).
+//
+// One thread per output element, channel fastest (coalesced 4-byte accesses over C).  Backward passes are deterministic
+// gathers: every input element sums the contributions of the (few) output windows that cover it; max pooling recomputes
+// each covering window's arg-max with torch's tie rule (first maximum in (kh, kw) scan order wins).
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace mog {
+
+struct PoolArgs {
+  const float* x;
+  const float* dy;
+  float* out;
+  int N, H, W, C, Ho, Wo, k, s, p, mode;   // mode 0: max, 1: average (divisor k*k, count_include_pad)
+  long long total;
+};
+
+__global__ void pool_fwd_kernel(PoolArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  const int c = (int)(i % a.C);
+  long long q = i / a.C;
+  const int wo = (int)(q % a.Wo);
+  q /= a.Wo;
+  const int ho = (int)(q % a.Ho);
+  const int n = (int)(q / a.Ho);
+  const float* xn = a.x + (size_t)n * a.H * a.W * a.C + c;
+  float acc = a.mode == 0 ? -FLT_MAX : 0.f;
+  for (int kh = 0; kh < a.k; ++kh) {
+    const int h = ho * a.s - a.p + kh;
+    if (h < 0 || h >= a.H) continue;
+    for (int kw = 0; kw < a.k; ++kw) {
+      const int w = wo * a.s - a.p + kw;
+      if (w < 0 || w >= a.W) continue;
+      const float v = __ldg(xn + ((size_t)h * a.W + w) * a.C);
+      if (a.mode == 0) acc = (v > acc || v != v) ? v : acc;
+      else acc += v;
+    }
+  }
+  a.out[i] = a.mode == 0 ? acc : acc / (float)(a.k * a.k);
+}
+
+__device__ __forceinline__ int fdiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+__global__ void pool_bwd_kernel(PoolArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  const int c = (int)(i % a.C);
+  long long q = i / a.C;
+  const int w = (int)(q % a.W);
+  q /= a.W;
+  const int h = (int)(q % a.H);
+  const int n = (int)(q / a.H);
+  // output windows covering (h, w): ho*s - p <= h <= ho*s - p + k - 1
+  int ho_lo = fdiv_i(h + a.p - a.k + a.s, a.s), ho_hi = fdiv_i(h + a.p, a.s);
+  int wo_lo = fdiv_i(w + a.p - a.k + a.s, a.s), wo_hi = fdiv_i(w + a.p, a.s);
+  ho_lo = max(ho_lo, 0); wo_lo = max(wo_lo, 0);
+  ho_hi = min(ho_hi, a.Ho - 1); wo_hi = min(wo_hi, a.Wo - 1);
+  const float* xn = a.x ? a.x + (size_t)n * a.H * a.W * a.C + c : nullptr;
+  const float* dyn = a.dy + (size_t)n * a.Ho * a.Wo * a.C + c;
+  float acc = 0.f;
+  for (int ho = ho_lo; ho <= ho_hi; ++ho)
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      const float g = __ldg(dyn + ((size_t)ho * a.Wo + wo) * a.C);
+      if (a.mode == 1) {
+        acc += g;
+      } else {
+        // arg-max of this window, first maximum wins (torch: `val > maxval || isnan(val)`)
+        float best = -FLT_MAX;
+        int bh = -1, bw = -1;
+        for (int kh = 0; kh < a.k; ++kh) {
+          const int hh = ho * a.s - a.p + kh;
+          if (hh < 0 || hh >= a.H) continue;
+          for (int kw = 0; kw < a.k; ++kw) {
+            const int ww = wo * a.s - a.p + kw;
+            if (ww < 0 || ww >= a.W) continue;
+            const float v = __ldg(xn + ((size_t)hh * a.W + ww) * a.C);
+            if (v > best || v != v || bh < 0) { best = v; bh = hh; bw = ww; }
+          }
+        }
+        if (bh == h && bw == w) acc += g;
+      }
+    }
+  a.out[i] = a.mode == 1 ? acc / (float)(a.k * a.k) : acc;
+}
+
+// ---- bilinear resize (torch upsample_bilinear2d) ------------------------------------------------
+struct ResizeArgs {
+  const float* src;
+  float* dst;
+  int N, Hi, Wi, C, Ho, Wo, align;
+  float sh, sw;   // source step per output pixel
+  long long total;
+};
+
+// source coordinate of output index o: (index of the first tap, 0/1 offset of the second tap, weight of the second tap)
+__device__ __forceinline__ void bil_src(int o, float scale, int align, int in, int* i0, int* ip, float* l1) {
+  float s = align ? scale * (float)o : scale * ((float)o + 0.5f) - 0.5f;
+  if (!align && s < 0.f) s = 0.f;
+  int i = (int)s;
+  if (i > in - 1) i = in - 1;
+  *i0 = i;
+  *ip = i < in - 1 ? 1 : 0;
+  *l1 = s - (float)i;
+}
+
+__global__ void resize_fwd_kernel(ResizeArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  const int c = (int)(i % a.C);
+  long long q = i / a.C;
+  const int wo = (int)(q % a.Wo);
+  q /= a.Wo;
+  const int ho = (int)(q % a.Ho);
+  const int n = (int)(q / a.Ho);
+  int h0, hp, w0, wp;
+  float lh, lw;
+  bil_src(ho, a.sh, a.align, a.Hi, &h0, &hp, &lh);
+  bil_src(wo, a.sw, a.align, a.Wi, &w0, &wp, &lw);
+  const float* p = a.src + (((size_t)n * a.Hi + h0) * a.Wi + w0) * a.C + c;
+  const size_t dw = (size_t)wp * a.C, dh = (size_t)hp * a.Wi * a.C;
+  const float h0l = 1.f - lh, w0l = 1.f - lw;
+  a.dst[i] = h0l * (w0l * __ldg(p) + lw * __ldg(p + dw)) + lh * (w0l * __ldg(p + dh) + lw * __ldg(p + dh + dw));
+}
+
+// total weight with which output index o reads input index t along one axis
+__device__ __forceinline__ float bil_weight(int o, int t, float scale, int align, int in) {
+  int i0, ip;
+  float l1;
+  bil_src(o, scale, align, in, &i0, &ip, &l1);
+  float w = 0.f;
+  if (i0 == t) w += 1.f - l1;
+  if (i0 + ip == t) w += l1;
+  return w;
+}
+
+__global__ void resize_bwd_kernel(ResizeArgs a) {
+  // a.src = dy [N,Ho,Wo,C], a.dst = dx [N,Hi,Wi,C]; one thread per input element gathers its outputs
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  const int c = (int)(i % a.C);
+  long long q = i / a.C;
+  const int w = (int)(q % a.Wi);
+  q /= a.Wi;
+  const int h = (int)(q % a.Hi);
+  const int n = (int)(q / a.Hi);
+  // outputs whose first tap is h-1 .. h: o in about [(h - 1 + 0.5)/scale - 0.5, (h + 1 + 0.5)/scale - 0.5]; two extra on each side
+  const float ish = 1.f / a.sh, isw = 1.f / a.sw;
+  int ho_lo = (int)floorf(((float)h - 1.f) * ish) - 2, ho_hi = (int)ceilf(((float)h + 1.5f) * ish) + 2;
+  int wo_lo = (int)floorf(((float)w - 1.f) * isw) - 2, wo_hi = (int)ceilf(((float)w + 1.5f) * isw) + 2;
+  ho_lo = max(ho_lo, 0); wo_lo = max(wo_lo, 0);
+  ho_hi = min(ho_hi, a.Ho - 1); wo_hi = min(wo_hi, a.Wo - 1);
+  const float* dyn = a.src + (size_t)n * a.Ho * a.Wo * a.C + c;
+  float acc = 0.f;
+  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    const float wh = bil_weight(ho, h, a.sh, a.align, a.Hi);
+    if (wh == 0.f) continue;
+    float row = 0.f;
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      const float ww = bil_weight(wo, w, a.sw, a.align, a.Wi);
+      if (ww != 0.f) row += ww * __ldg(dyn + ((size_t)ho * a.Wo + wo) * a.C);
+    }
+    acc += wh * row;
+  }
+  a.dst[i] = acc;
+}
+
+}  // namespace mog
+
+using namespace mog;
+
+static int pool_out(int H, int k, int s, int p) { return (H + 2 * p - k) / s + 1; }
+
+extern "C" int mog_pool2d_out_hw(int H, int W, int k, int stride, int pad, int* Ho, int* Wo) {
+  MOG_REQUIRE(H > 0 && W > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && H + 2 * pad >= k && W + 2 * pad >= k,
+              "mog_pool2d_out_hw: bad geometry");
+  if (Ho) *Ho = pool_out(H, k, stride, pad);
+  if (Wo) *Wo = pool_out(W, k, stride, pad);
+  return MOG_OK;
+}
+
+extern "C" int mog_pool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad, int mode,
+                              void* stream) {
+  MOG_REQUIRE(x && y && N > 0 && C > 0 && (mode == 0 || mode == 1), "mog_pool2d_fwd: bad argument");
+  int Ho, Wo;
+  int rc = mog_pool2d_out_hw(H, W, k, stride, pad, &Ho, &Wo);
+  if (rc) return rc;
+  PoolArgs a{x, nullptr, y, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * Ho * Wo * C};
+  pool_fwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  return check_launch("pool_fwd_kernel");
+}
+
+extern "C" int mog_pool2d_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C, int k, int stride,
+                              int pad, int mode, void* stream) {
+  MOG_REQUIRE(dy && dx && N > 0 && C > 0 && (mode == 0 || mode == 1), "mog_pool2d_bwd: bad argument");
+  MOG_REQUIRE(mode == 1 || x, "mog_pool2d_bwd: max pooling needs the forward input");
+  int Ho, Wo;
+  int rc = mog_pool2d_out_hw(H, W, k, stride, pad, &Ho, &Wo);
+  if (rc) return rc;
+  PoolArgs a{x, dy, dx, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * H * W * C};
+  pool_bwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  return check_launch("pool_bwd_kernel");
+}
+
+static float resize_scale(int in, int out, int align) {
+  if (align) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  return (float)in / (float)out;
+}
+
+extern "C" int mog_resize_bilinear_fwd(const float* x, float* y, int N, int Hi, int Wi, int C, int Ho, int Wo, int align_corners,
+                                       void* stream) {
+  MOG_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0, "mog_resize_bilinear_fwd: bad argument");
+  ResizeArgs a{x, y, N, Hi, Wi, C, Ho, Wo, align_corners ? 1 : 0, resize_scale(Hi, Ho, align_corners), resize_scale(Wi, Wo, align_corners),
+               (long long)N * Ho * Wo * C};
+  resize_fwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  return check_launch("resize_fwd_kernel");
+}
+
+extern "C" int mog_resize_bilinear_bwd(const float* dy, float* dx, int N, int Hi, int Wi, int C, int Ho, int Wo, int align_corners,
+                                       void* stream) {
+  MOG_REQUIRE(dy && dx && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0, "mog_resize_bilinear_bwd: bad argument");
+  MOG_REQUIRE(Ho >= Hi && Wo >= Wi, "mog_resize_bilinear_bwd: implemented for upsampling (the 256 -> 299 resize of the image encoder)");
+  ResizeArgs a{dy, dx, N, Hi, Wi, C, Ho, Wo, align_corners ? 1 : 0, resize_scale(Hi, Ho, align_corners), resize_scale(Wi, Wo, align_corners),
+               (long long)N * Hi * Wi * C};
+  resize_bwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  return check_launch("resize_bwd_kernel");
+}

@@ -19,7 +19,7 @@ PREC_NAMES = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 class MogConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "up2x", "act", "precision")]
+                ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "up2x", "act", "precision", "pad_w1")]
 
 
 _p = C.c_void_p
@@ -61,6 +61,11 @@ SIGNATURES = {
     "mog_damsm_words_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "mog_sigmoid_bce_fwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _i, _p]),
     "mog_sigmoid_bce_bwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _p]),
+    "mog_pool2d_out_hw": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "mog_pool2d_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_pool2d_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_resize_bilinear_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_resize_bilinear_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_adam_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_longlong, C.c_double, _f, _p]),
 }
 

@@ -134,6 +134,50 @@ class BBOX_NET(nn.Module):
                                      transf_matr_inv, B)
 
 
+# ############## DAMSM image encoder ###################
+class CNN_ENCODER(nn.Module):
+    """model.py:207-313 -- frozen Inception-v3 trunk (torchvision layer names, see ``inception.py``) + the two
+    trainable-in-DAMSM-pretraining projections ``emb_features`` (1x1 conv 768 -> nef on the 17x17 region map) and
+    ``emb_cnn_code`` (Linear 2048 -> nef on the pooled 8x8 map).  The reference downloads the ImageNet weights
+    (``model_zoo.load_url``, :215-217); here they are loaded through ``load_state_dict`` (same keys) by the caller --
+    there is no network access on the hot path.  ``forward`` -> (region features B x nef x 17 x 17, cnn_code B x nef)."""
+
+    def __init__(self, nef):
+        super().__init__()
+        self.nef = nef if cfg.TRAIN.FLAG else 256
+        from . import inception
+        inception.build_trunk(self)
+        for param in self.parameters():     # model.py:218-219
+            param.requires_grad = False
+        self.emb_features = conv1x1(768, self.nef)
+        self.emb_cnn_code = nn.Linear(2048, self.nef)
+        self.init_trainable_weights()
+
+    def init_trainable_weights(self):
+        initrange = 0.1
+        self.emb_features.weight.data.uniform_(-initrange, initrange)
+        self.emb_cnn_code.weight.data.uniform_(-initrange, initrange)
+
+    def forward(self, x):
+        x = ops.resize_bilinear(ops.nhwc(x), (299, 299), align_corners=False)    # :256
+        x = self.Conv2d_1a_3x3(x)                 # 149 x 149 x 32
+        x = self.Conv2d_2a_3x3(x)                 # 147 x 147 x 32
+        x = self.Conv2d_2b_3x3(x)                 # 147 x 147 x 64
+        x = ops.max_pool2d(x, 3, 2)               # 73 x 73 x 64
+        x = self.Conv2d_3b_1x1(x)                 # 73 x 73 x 80
+        x = self.Conv2d_4a_3x3(x)                 # 71 x 71 x 192
+        x = ops.max_pool2d(x, 3, 2)               # 35 x 35 x 192
+        x = self.Mixed_5d(self.Mixed_5c(self.Mixed_5b(x)))                      # 35 x 35 x 288
+        x = self.Mixed_6a(x)                      # 17 x 17 x 768
+        x = self.Mixed_6e(self.Mixed_6d(self.Mixed_6c(self.Mixed_6b(x))))
+        features = x                              # image region features, 17 x 17 x 768
+        x = self.Mixed_7c(self.Mixed_7b(self.Mixed_7a(x)))                      # 8 x 8 x 2048
+        x = ops.avg_pool2d(x, 8)                  # 1 x 1 x 2048
+        cnn_code = ops.linear(x.reshape(x.shape[0], -1), self.emb_cnn_code.weight, self.emb_cnn_code.bias)
+        features = ops.to_nchw_view(self.emb_features(features))
+        return features, cnn_code
+
+
 # ############## G networks ###################
 class CA_NET(nn.Module):
     """model.py:317-345"""

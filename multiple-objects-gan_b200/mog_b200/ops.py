@@ -104,7 +104,7 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc) -> torch.Tensor:
     # the dgrad packing depends on stride/pad (phase tap subsets) and, with odd sizes, on H/W parity
     wi = 0 if which == "fwd" else 1
     tag = _lib.lib().mog_packed_weight_layout(C.byref(d), wi)
-    key = (which, tag, d.precision, d.stride, d.pad, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
+    key = (which, tag, d.precision, d.stride, d.pad, d.pad_w1, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
     if key not in cache:
         w = weight.detach()
         if w.dim() == 2:
@@ -123,7 +123,10 @@ def _desc(x_shape, w_shape, stride, pad, up2x, act, precision):
     Co, Ci2, KH, KW = w_shape
     if Ci != Ci2:
         raise RuntimeError("conv: input has %d channels, weight expects %d" % (Ci, Ci2))
-    d = MogConvDesc(N, H, W, Ci, Co, KH, KW, stride, pad, int(up2x), act, precision)
+    if isinstance(pad, (tuple, list)):   # (pad_h, pad_w): the 1x7 / 7x1 / 1x3 / 3x1 filters of the image encoder
+        d = MogConvDesc(N, H, W, Ci, Co, KH, KW, stride, int(pad[0]), int(up2x), act, precision, int(pad[1]) + 1)
+    else:
+        d = MogConvDesc(N, H, W, Ci, Co, KH, KW, stride, pad, int(up2x), act, precision, 0)
     ho, wo = C.c_int(), C.c_int()
     call("mog_conv_out_hw", C.byref(d), C.byref(ho), C.byref(wo))
     return d, ho.value, wo.value
@@ -188,7 +191,10 @@ class Conv2dFn(torch.autograd.Function):
              y.data_ptr(), _ptr(ws), nws, _stream())
         ctx.cfg = (stride, pad, up2x, act, precision, tuple(x.shape))
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x if xp is None else None, xp, weight, y if act != ACT_NONE else None)
+        # the input is only needed again for the weight / bias gradient: a frozen conv (image encoder) keeps nothing of it
+        need_w = weight.requires_grad or (bias is not None and bias.requires_grad)
+        ctx.save_for_backward(x if (xp is None and need_w) else None, xp if need_w else None, weight,
+                              y if act != ACT_NONE else None)
         return y
 
     @staticmethod
@@ -521,3 +527,63 @@ def func_attention_paired(query, context_nhwc, gamma1):
     call("mog_damsm_words_fwd", context_nhwc.detach().contiguous().data_ptr(), q.data_ptr(), lens.data_ptr(), None,
          wei.data_ptr(), attn.data_ptr(), B, B, R, D, Tq, 1, float(gamma1), 1.0, _stream())
     return wei, attn
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling / bilinear resize (DAMSM image encoder)
+# ---------------------------------------------------------------------------------------------
+class Pool2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad, mode):
+        _chk(x, "pool input")
+        N, H, W, Cc = x.shape
+        ho, wo = C.c_int(), C.c_int()
+        call("mog_pool2d_out_hw", H, W, k, stride, pad, C.byref(ho), C.byref(wo))
+        y = torch.empty((N, ho.value, wo.value, Cc), device=x.device, dtype=torch.float32)
+        call("mog_pool2d_fwd", x.data_ptr(), y.data_ptr(), N, H, W, Cc, k, stride, pad, mode, _stream())
+        ctx.cfg = (N, H, W, Cc, k, stride, pad, mode)
+        ctx.save_for_backward(x if mode == 0 else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, H, W, Cc, k, stride, pad, mode = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty((N, H, W, Cc), device=dy.device, dtype=torch.float32)
+        call("mog_pool2d_bwd", _ptr(x), dy.data_ptr(), dx.data_ptr(), N, H, W, Cc, k, stride, pad, mode, _stream())
+        return dx, None, None, None, None
+
+
+def max_pool2d(x, kernel_size, stride=None, padding=0):
+    """F.max_pool2d on NHWC."""
+    return Pool2dFn.apply(x, kernel_size, stride or kernel_size, padding, 0)
+
+
+def avg_pool2d(x, kernel_size, stride=None, padding=0):
+    """F.avg_pool2d (count_include_pad=True) on NHWC."""
+    return Pool2dFn.apply(x, kernel_size, stride or kernel_size, padding, 1)
+
+
+class ResizeBilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo, align):
+        _chk(x, "resize input")
+        N, Hi, Wi, Cc = x.shape
+        y = torch.empty((N, Ho, Wo, Cc), device=x.device, dtype=torch.float32)
+        call("mog_resize_bilinear_fwd", x.data_ptr(), y.data_ptr(), N, Hi, Wi, Cc, Ho, Wo, int(align), _stream())
+        ctx.cfg = (N, Hi, Wi, Cc, Ho, Wo, int(align))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, Hi, Wi, Cc, Ho, Wo, align = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty((N, Hi, Wi, Cc), device=dy.device, dtype=torch.float32)
+        call("mog_resize_bilinear_bwd", dy.data_ptr(), dx.data_ptr(), N, Hi, Wi, Cc, Ho, Wo, align, _stream())
+        return dx, None, None, None
+
+
+def resize_bilinear(x, size, align_corners=False):
+    """nn.Upsample(size=size, mode='bilinear') on NHWC."""
+    return ResizeBilinearFn.apply(x, int(size[0]), int(size[1]), bool(align_corners))

@@ -222,3 +222,39 @@ def stackgan_batch(B: int, stage: int = 1, t_dim: int = 1024, nz: int = 100, c_d
     out["eps1"] = rng.standard_normal((B, c_dim)).astype(np.float32)
     out["eps2"] = rng.standard_normal((B, c_dim)).astype(np.float32)
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}
+
+
+def fill_encoder_state_dict(sd: dict, seed: int) -> dict:
+    """Deterministic stand-in for the ImageNet weights of the DAMSM image encoder (``CNN_ENCODER`` /
+    torchvision ``inception_v3`` keys): He-scaled conv/linear weights so activations survive the ReLU depth,
+    and NON-trivial BatchNorm affine + running statistics so the eval-mode folding is exercised."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for k in sorted(sd.keys()):
+        shape = tuple(sd[k].shape)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros(shape, dtype=torch.long)
+        elif k.endswith("running_mean"):
+            out[k] = torch.from_numpy((0.1 * rng.standard_normal(shape)).astype(np.float32))
+        elif k.endswith("running_var"):
+            out[k] = torch.from_numpy(rng.uniform(0.5, 1.5, size=shape).astype(np.float32))
+        elif k.endswith("weight") and len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            out[k] = torch.from_numpy((rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32))
+        elif k.endswith("weight"):
+            out[k] = torch.from_numpy(rng.uniform(0.5, 1.5, size=shape).astype(np.float32))
+        elif k.endswith("bias"):
+            out[k] = torch.from_numpy((0.1 * rng.standard_normal(shape)).astype(np.float32))
+        else:
+            raise KeyError("unexpected state_dict entry %s" % k)
+    return out
+
+
+def encoder_probe(B: int, nef: int, seed: int):
+    """Input images U(-1,1) B x 3 x 256 x 256 and fixed projections that turn the encoder outputs into a scalar
+    (so a gradient w.r.t. the image exists): loss = sum(features * pf) + sum(cnn_code * pc)."""
+    rng = np.random.RandomState(seed)
+    img = rng.uniform(-1, 1, size=(B, 3, 256, 256)).astype(np.float32)
+    pf = rng.standard_normal((B, nef, 17, 17)).astype(np.float32)
+    pc = rng.standard_normal((B, nef)).astype(np.float32)
+    return torch.from_numpy(img), torch.from_numpy(pf), torch.from_numpy(pc)
