@@ -391,23 +391,25 @@ struct PackArgs {
 // 3.8 ms per training step for the 236 M parameters of the four networks.)
 constexpr int PK_N = 16, PK_C = 32;
 // KHW_T: filter taps as a compile-time constant (index arithmetic without integer division); 0 = generic (<= 16 taps)
-template <int KHW_T>
+// NR: rows n per block, TP: tap pitch of the tile (odd: conflict-free; >= taps).  <.., 16, 17> serves filters up to 16 taps,
+// <25, 8, 25> the 5x5 filters of the image encoder.
+template <int KHW_T, int NR = PK_N, int TP = 17>
 __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
-  __shared__ float tile[PK_N * PK_C * 17];   // [n][c][tap (pitch 17: conflict-free)]
-  const int n0 = blockIdx.y * PK_N, c0 = blockIdx.x * PK_C;
+  __shared__ float tile[NR * PK_C * TP];   // [n][c][tap]
+  const int n0 = blockIdx.y * NR, c0 = blockIdx.x * PK_C;
   const int KHW = KHW_T ? KHW_T : a.KHW;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   // ---- load: element (nl, cl, t) <- w[co][ci][t]
   if (!a.transpose) {
     // n = co, c = ci: for a fixed n the (c, t) block of PK_C * KHW floats is contiguous in memory
-    for (int nl = ty; nl < PK_N; nl += 8) {
+    for (int nl = ty; nl < NR; nl += 8) {
       const int n = n0 + nl;
       const float* src = a.w + ((size_t)n * a.Cin + c0) * KHW;
       for (int j = tx; j < PK_C * KHW; j += 32) {
         const int cl = j / KHW, t = j - cl * KHW;
         float v = 0.f;
         if (n < a.Nreal && c0 + cl < a.CsReal) v = __ldg(src + j);
-        tile[(nl * PK_C + cl) * 17 + t] = v;
+        tile[(nl * PK_C + cl) * TP + t] = v;
       }
     }
   } else {
@@ -415,11 +417,11 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
     for (int cl = ty; cl < PK_C; cl += 8) {
       const int c = c0 + cl;
       const float* src = a.w + ((size_t)c * a.Cin + n0) * KHW;
-      for (int j = tx; j < PK_N * KHW; j += 32) {
+      for (int j = tx; j < NR * KHW; j += 32) {
         const int nl = j / KHW, t = j - nl * KHW;
         float v = 0.f;
         if (n0 + nl < a.Nreal && c < a.CsReal) v = __ldg(src + j);
-        tile[(nl * PK_C + cl) * 17 + t] = v;
+        tile[(nl * PK_C + cl) * TP + t] = v;
       }
     }
   }
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
   // ---- store: out[n][tl * Cs + c] = sum of the filter taps folded into local tap tl; 32 consecutive c per warp
   const int c = c0 + tx;
   if (c < a.Cs) {
-    for (int nl = ty; nl < PK_N; nl += 8) {
+    for (int nl = ty; nl < NR; nl += 8) {
       const int n = n0 + nl;
       if (n >= a.Npad) break;
       for (int tl = 0; tl < a.ntaps; ++tl) {
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int tp = a.taps[tl][u];
-          if (tp >= 0) v += tile[(nl * PK_C + tx) * 17 + tp];
+          if (tp >= 0) v += tile[(nl * PK_C + tx) * TP + tp];
         }
         const size_t o = (size_t)n * a.Kpad + (size_t)tl * a.Cs + c;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
   // ---- zero the K tail [K, Kpad) of this block's rows (once per row block)
   if (blockIdx.x == 0) {
     const int tail = a.Kpad - a.K;
-    for (int nl = ty; nl < PK_N; nl += 8) {
+    for (int nl = ty; nl < NR; nl += 8) {
       const int n = n0 + nl;
       if (n >= a.Npad) break;
       for (int k = a.K + tx; k < a.Kpad; k += 32) {
@@ -603,7 +605,11 @@ int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int
   for (int i = 0; i < ntaps; ++i)
     for (int u = 0; u < 4; ++u) a.taps[i][u] = taps[i][u];
   a.Nreal = Cd; a.Npad = L.Npad; a.Cs = Cs; a.CsReal = CsReal; a.K = L.K; a.Kpad = L.Kpad;
-  if (KH * KW > 16) return fail(MOG_ERR_UNSUPPORTED, "weight packing (tcgen05): filters with more than 16 taps are not supported");
+  if (KH * KW > 25) return fail(MOG_ERR_UNSUPPORTED, "weight packing (tcgen05): filters with more than 25 taps are not supported");
+  if (KH * KW > 16) {
+    pack_tc_kernel<0, 8, 25><<<dim3((unsigned)ceil_div(Cs, PK_C), (unsigned)ceil_div(L.Npad, 8)), 256, 0, st>>>(a);
+    return check_launch("pack_tc_kernel");
+  }
   const dim3 grid((unsigned)ceil_div(Cs, PK_C), (unsigned)ceil_div(L.Npad, PK_N));
   switch (KH * KW) {
     case 1: pack_tc_kernel<1><<<grid, 256, 0, st>>>(a); break;
