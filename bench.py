@@ -7,8 +7,9 @@
 A "step" is one pass of the hot path over one synthetic batch (config 5 of BASELINE.json:
 B=32/GPU, T=18, GF 48, DF 96, R_NUM 3): G_NET forward; D_NET64/128/256 loss + backward + Adam;
 generator adversarial + KL loss, backward through the three discriminators and G, Adam, EMA
-(code/coco/attngan/trainer.py:294-342).  The DAMSM term (Inception-v3 image encoder) is a later
-scope row and is NOT part of the step; `config.workload` says so.
+(code/coco/attngan/trainer.py:294-342), including the DAMSM words/sentence loss through the frozen Inception-v3 image
+encoder (random-init stand-in weights: there is no network for the ImageNet checkpoint).  `--no-damsm` times the G+D-only
+step; `config.workload` says which.
 
 Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same
 through the public trainer API with pinned-host inputs copied in and the losses read back every
@@ -35,8 +36,20 @@ import torch  # noqa: E402
 CFG5 = dict(GF_DIM=48, DF_DIM=96, Z_DIM=100, R_NUM=3, EMBEDDING_DIM=256, T=18)
 # forward GMAC per image from SURVEY.md section 8(a.1)/8(d) (hook-counted on the reference modules),
 # G+D-only step: G fwd 25.09; D step fwd 18.70 + bwd 36.86; G step D fwd 9.18 + D dgrad 9.18 + G bwd 50.18
+# with the DAMSM term (Inception-v3 image encoder fwd + dgrad, words/sentence losses): 161.0 GMAC
 GMAC_PER_IMAGE_GD = 149.2
-WORKLOAD = "attngan256-coco-config5 G+D step (G fwd; 3x D loss+bwd+Adam; G adv+KL loss+bwd+Adam+EMA); no DAMSM/Inception"
+GMAC_PER_IMAGE_FULL = 161.0
+WORKLOAD_GD = "attngan256-coco-config5 G+D step (G fwd; 3x D loss+bwd+Adam; G adv+KL loss+bwd+Adam+EMA); no DAMSM/Inception"
+WORKLOAD_FULL = ("attngan256-coco-config5 full step (G fwd; 3x D loss+bwd+Adam; G adv + DAMSM words/sentence loss through the "
+                 "frozen Inception-v3 image encoder + KL, bwd, Adam, EMA)")
+
+
+def workload(args):
+    return WORKLOAD_GD if args.no_damsm else WORKLOAD_FULL
+
+
+def gmac(args):
+    return GMAC_PER_IMAGE_GD if args.no_damsm else GMAC_PER_IMAGE_FULL
 
 
 def peaks():
@@ -110,7 +123,7 @@ def set_cfg():
 # --------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline: the oracle port of the reference on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, batch):
+def cpu_reference_run(steps, warmup, batch, damsm=True):
     from mog_b200 import synth
     from oracle import attngan_oracle as O
     from mog_b200.attngan import model as M
@@ -124,17 +137,21 @@ def cpu_reference_run(steps, warmup, batch):
     PG, PDs = O.leafify(sdG), [O.leafify(s) for s in sdDs]
     ocfg = O.Cfg(**{k: v for k, v in CFG5.items() if k != "T"})
     b = synth.attngan_batch(batch, T=CFG5["T"], nef=CFG5["EMBEDDING_DIM"], nz=CFG5["Z_DIM"], seed=1234)
+    PE = None
+    if damsm:
+        PE = {k: v for k, v in synth.fill_encoder_state_dict(M.CNN_ENCODER(CFG5["EMBEDDING_DIM"]).state_dict(), 9).items()}
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.gd_step(PG, PDs, ocfg, b)
+        O.gd_step(PG, PDs, ocfg, b, PE=PE)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     tot = sum(times)
     return {"value": batch * len(times) / tot, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "oracle/attngan_oracle.gd_step (torch CPU fp32 port of the reference step, fwd+bwd, no "
-                      "optimiser) at config 5, batch %d, %d warm-up + %d timed steps" % (batch, warmup, len(times)),
+            "sample": "oracle/attngan_oracle.gd_step (torch CPU fp32 port of the reference step, fwd+bwd%s, no "
+                      "optimiser) at config 5, batch %d, %d warm-up + %d timed steps"
+                      % (" incl. DAMSM / Inception-v3" if damsm else "", batch, warmup, len(times)),
             "ms_per_step": 1e3 * tot / len(times)}
 
 
@@ -142,12 +159,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, args.ref_batch)
+    r = cpu_reference_run(args.steps, args.warmup, args.ref_batch, not args.no_damsm)
     line = {"impl": "reference", "metric": "images/sec (G+D fwd+bwd) COCO-AttnGAN 256^2", "value": r["value"],
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_step": args.ref_batch, "device": "cpu"},
+            "config": {"workload": workload(args), "batch_per_step": args.ref_batch, "device": "cpu"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -182,7 +199,16 @@ def run_mog(args):
 
     torch.manual_seed(1234)
     tr = condGANTrainer("", None, 0, None)
-    _, _, netG, netsD, _ = tr.build_models()   # weights_init (orthogonal) on device, broadcast from rank 0
+    enc = None
+    if not args.no_damsm:
+        # frozen DAMSM image encoder in eval mode (trainer.py:56-77); deterministic stand-in for the ImageNet weights
+        from mog_b200.attngan.model import CNN_ENCODER
+        enc = CNN_ENCODER(CFG5["EMBEDDING_DIM"])
+        enc.load_state_dict(synth.fill_encoder_state_dict(enc.state_dict(), 9))
+        for p in enc.parameters():
+            p.requires_grad = False
+        enc.to(dev).eval()
+    _, _, netG, netsD, _ = tr.build_models(image_encoder=enc)   # weights_init (orthogonal) on device, broadcast from rank 0
     optG, optDs = tr.define_optimizers(netG, netsD)
     st = tr.make_step_state(netG, netsD, optG, optDs)
 
@@ -254,7 +280,7 @@ def run_mog(args):
         roof = roofline_probe(dev, args, B)
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         # free the device-side state first? not needed: the CPU leg only touches host memory
-        cpu = cpu_reference_run(1, 1, args.ref_batch)
+        cpu = cpu_reference_run(1, 1, args.ref_batch, not args.no_damsm)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         pk, src = peaks()
@@ -264,12 +290,12 @@ def run_mog(args):
                 "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (3-pass split, fp32-equivalent) + fp32 accumulate",
                           "bf16": "bf16 operands, fp32 accumulate"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": ws * B, "words": CFG5["T"],
+                "config": {"workload": workload(args), "batch_per_gpu": B, "global_batch": ws * B, "words": CFG5["T"],
                            "parallelism": "dp%d (NCCL grad all-reduce per net)" % ws,
                            "precision": args.precision, "l2": "working set per step (>5 GB) exceeds the 126 MB L2; no flush needed",
                            "optimizer": "fused libmog Adam + EMA (mog_adam_multi) inside the timed region",
-                           "algorithmic_gflop_per_image": 2 * GMAC_PER_IMAGE_GD,
-                           "step_tflops_achieved": 2 * GMAC_PER_IMAGE_GD * 1e9 * value / 1e12},
+                           "algorithmic_gflop_per_image": 2 * gmac(args),
+                           "step_tflops_achieved": 2 * gmac(args) * 1e9 * value / 1e12},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K},
@@ -322,6 +348,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
     ap.add_argument("--precision", default=os.environ.get("MOG_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-damsm", action="store_true", help="time the G+D-only step (no DAMSM loss / Inception-v3 encoder)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mog":
         args.warmup = 3

@@ -179,9 +179,13 @@ int mog_word_attention_bwd(const float* h, const float* src, const uint8_t* mask
 int mog_damsm_words_fwd(const float* ctx, const float* words, const int* lens, float* sims, float* wei_out,
                         float* attn_out, int B, int NI, int R, int D, int Tw, int paired, float gamma1, float gamma2,
                         void* stream);
-/* gradient w.r.t. the region features (the word embeddings come from the frozen text encoder). */
+/* gradient w.r.t. the region features (the word embeddings come from the frozen text encoder).  One CTA per
+ * (image, caption) pair writes its contribution into the caller's workspace [NI][B][R][D] (fp32,
+ * mog_damsm_bwd_workspace_bytes); a second kernel sums the NI slices in a fixed order.  D % 4 == 0. */
+size_t mog_damsm_bwd_workspace_bytes(int B, int NI, int R, int D);
 int mog_damsm_words_bwd(const float* ctx, const float* words, const int* lens, const float* dsims, float* dctx,
-                        int B, int NI, int R, int D, int Tw, float gamma1, float gamma2, void* stream);
+                        int B, int NI, int R, int D, int Tw, float gamma1, float gamma2, void* workspace, size_t ws_bytes,
+                        void* stream);
 
 /* ---- loss heads --------------------------------------------------------------------------- */
 /* loss[0] (+)= weight * mean_i BCE(sigmoid(z_i), target_i) with torch's log clamp at -100;
@@ -216,9 +220,10 @@ int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* 
  * Backward is a deterministic gather; for max pooling it recomputes each window's arg-max from the forward input x
  * with torch's tie rule (first maximum in scan order). */
 int mog_pool2d_out_hw(int H, int W, int k, int stride, int pad, int* Ho, int* Wo);
-int mog_pool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad, int mode, void* stream);
-int mog_pool2d_bwd(const float* x /*NULL for average*/, const float* dy, float* dx, int N, int H, int W, int C, int k,
-                   int stride, int pad, int mode, void* stream);
+int mog_pool2d_fwd(const float* x, float* y, unsigned char* argmax /*optional, max pooling: [N,Ho,Wo,C] window positions*/,
+                   int N, int H, int W, int C, int k, int stride, int pad, int mode, void* stream);
+int mog_pool2d_bwd(const float* x /*max pooling without argmax*/, const unsigned char* argmax /*or NULL*/, const float* dy,
+                   float* dx, int N, int H, int W, int C, int k, int stride, int pad, int mode, void* stream);
 /* replaces: nn.Upsample(size=(299, 299), mode='bilinear')(x) (attngan/model.py:256) = torch upsample_bilinear2d
  *   (source index scale*(o + 0.5) - 0.5 clamped at 0 for align_corners = 0) and its autograd (upsampling only). */
 int mog_resize_bilinear_fwd(const float* x, float* y, int N, int Hi, int Wi, int C, int Ho, int Wo, int align_corners,

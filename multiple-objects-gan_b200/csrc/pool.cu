@@ -18,6 +18,7 @@ struct PoolArgs {
   const float* x;
   const float* dy;
   float* out;
+  unsigned char* idx;   // max pooling: window position kh*k + kw of the arg-max per output element (forward writes, backward reads)
   int N, H, W, C, Ho, Wo, k, s, p, mode;   // mode 0: max, 1: average (divisor k*k, count_include_pad)
   long long total;
 };
@@ -33,6 +34,7 @@ __global__ void pool_fwd_kernel(PoolArgs a) {
   const int n = (int)(q / a.Ho);
   const float* xn = a.x + (size_t)n * a.H * a.W * a.C + c;
   float acc = a.mode == 0 ? -FLT_MAX : 0.f;
+  int best = -1;
   for (int kh = 0; kh < a.k; ++kh) {
     const int h = ho * a.s - a.p + kh;
     if (h < 0 || h >= a.H) continue;
@@ -40,11 +42,15 @@ __global__ void pool_fwd_kernel(PoolArgs a) {
       const int w = wo * a.s - a.p + kw;
       if (w < 0 || w >= a.W) continue;
       const float v = __ldg(xn + ((size_t)h * a.W + w) * a.C);
-      if (a.mode == 0) acc = (v > acc || v != v) ? v : acc;
-      else acc += v;
+      if (a.mode == 0) {
+        if (v > acc || v != v || best < 0) { acc = v; best = kh * a.k + kw; }   // first maximum wins (torch)
+      } else {
+        acc += v;
+      }
     }
   }
   a.out[i] = a.mode == 0 ? acc : acc / (float)(a.k * a.k);
+  if (a.idx) a.idx[i] = (unsigned char)best;
 }
 
 __device__ __forceinline__ int fdiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
@@ -71,6 +77,10 @@ __global__ void pool_bwd_kernel(PoolArgs a) {
       const float g = __ldg(dyn + ((size_t)ho * a.Wo + wo) * a.C);
       if (a.mode == 1) {
         acc += g;
+      } else if (a.idx) {
+        // the forward recorded each window's arg-max position
+        const int pos = a.idx[((size_t)n * a.Ho * a.Wo + (size_t)ho * a.Wo + wo) * a.C + c];
+        if (ho * a.s - a.p + pos / a.k == h && wo * a.s - a.p + pos % a.k == w) acc += g;
       } else {
         // arg-max of this window, first maximum wins (torch: `val > maxval || isnan(val)`)
         float best = -FLT_MAX;
@@ -186,25 +196,26 @@ extern "C" int mog_pool2d_out_hw(int H, int W, int k, int stride, int pad, int* 
   return MOG_OK;
 }
 
-extern "C" int mog_pool2d_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad, int mode,
-                              void* stream) {
+extern "C" int mog_pool2d_fwd(const float* x, float* y, unsigned char* argmax, int N, int H, int W, int C, int k, int stride, int pad,
+                              int mode, void* stream) {
   MOG_REQUIRE(x && y && N > 0 && C > 0 && (mode == 0 || mode == 1), "mog_pool2d_fwd: bad argument");
+  MOG_REQUIRE(!argmax || (mode == 0 && k * k <= 255), "mog_pool2d_fwd: arg-max positions exist for max pooling with k*k <= 255 only");
   int Ho, Wo;
   int rc = mog_pool2d_out_hw(H, W, k, stride, pad, &Ho, &Wo);
   if (rc) return rc;
-  PoolArgs a{x, nullptr, y, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * Ho * Wo * C};
+  PoolArgs a{x, nullptr, y, argmax, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * Ho * Wo * C};
   pool_fwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
   return check_launch("pool_fwd_kernel");
 }
 
-extern "C" int mog_pool2d_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C, int k, int stride,
-                              int pad, int mode, void* stream) {
+extern "C" int mog_pool2d_bwd(const float* x, const unsigned char* argmax, const float* dy, float* dx, int N, int H, int W, int C,
+                              int k, int stride, int pad, int mode, void* stream) {
   MOG_REQUIRE(dy && dx && N > 0 && C > 0 && (mode == 0 || mode == 1), "mog_pool2d_bwd: bad argument");
-  MOG_REQUIRE(mode == 1 || x, "mog_pool2d_bwd: max pooling needs the forward input");
+  MOG_REQUIRE(mode == 1 || x || argmax, "mog_pool2d_bwd: max pooling needs the forward input or the recorded arg-max positions");
   int Ho, Wo;
   int rc = mog_pool2d_out_hw(H, W, k, stride, pad, &Ho, &Wo);
   if (rc) return rc;
-  PoolArgs a{x, dy, dx, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * H * W * C};
+  PoolArgs a{x, dy, dx, const_cast<unsigned char*>(argmax), N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * H * W * C};
   pool_bwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
   return check_launch("pool_bwd_kernel");
 }

@@ -58,12 +58,13 @@ SIGNATURES = {
     "mog_word_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mog_word_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mog_damsm_words_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
-    "mog_damsm_words_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "mog_damsm_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mog_damsm_words_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _sz, _p]),
     "mog_sigmoid_bce_fwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _i, _p]),
     "mog_sigmoid_bce_bwd": (_i, [_p, _p, _f, _i, _p, _p, _i, _p]),
     "mog_pool2d_out_hw": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
-    "mog_pool2d_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "mog_pool2d_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_pool2d_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mog_pool2d_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_resize_bilinear_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_resize_bilinear_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_adam_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_longlong, C.c_double, _f, _p]),

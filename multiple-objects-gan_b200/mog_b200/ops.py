@@ -505,8 +505,10 @@ class DamsmSimsFn(torch.autograd.Function):
         B, NI, R, D, Tw, g1, g2 = ctx.cfg
         dsims = dsims.contiguous()
         dfeat = torch.empty_like(feat)
+        nws = _lib.lib().mog_damsm_bwd_workspace_bytes(B, NI, R, D)
+        ws = torch.empty((nws + 3) // 4, device=feat.device, dtype=torch.float32)
         call("mog_damsm_words_bwd", feat.data_ptr(), words.data_ptr(), lens.data_ptr(), dsims.data_ptr(),
-             dfeat.data_ptr(), B, NI, R, D, Tw, g1, g2, _stream())
+             dfeat.data_ptr(), B, NI, R, D, Tw, g1, g2, ws.data_ptr(), nws, _stream())
         return dfeat, None, None, None, None
 
 
@@ -540,18 +542,20 @@ class Pool2dFn(torch.autograd.Function):
         ho, wo = C.c_int(), C.c_int()
         call("mog_pool2d_out_hw", H, W, k, stride, pad, C.byref(ho), C.byref(wo))
         y = torch.empty((N, ho.value, wo.value, Cc), device=x.device, dtype=torch.float32)
-        call("mog_pool2d_fwd", x.data_ptr(), y.data_ptr(), N, H, W, Cc, k, stride, pad, mode, _stream())
+        # max pooling records each window's arg-max position (1 byte per output) instead of keeping x for backward
+        idx = torch.empty(y.shape, device=x.device, dtype=torch.uint8) if (mode == 0 and ctx.needs_input_grad[0]) else None
+        call("mog_pool2d_fwd", x.data_ptr(), y.data_ptr(), _ptr(idx), N, H, W, Cc, k, stride, pad, mode, _stream())
         ctx.cfg = (N, H, W, Cc, k, stride, pad, mode)
-        ctx.save_for_backward(x if mode == 0 else None)
+        ctx.save_for_backward(idx)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
+        (idx,) = ctx.saved_tensors
         N, H, W, Cc, k, stride, pad, mode = ctx.cfg
         dy = dy.contiguous()
         dx = torch.empty((N, H, W, Cc), device=dy.device, dtype=torch.float32)
-        call("mog_pool2d_bwd", _ptr(x), dy.data_ptr(), dx.data_ptr(), N, H, W, Cc, k, stride, pad, mode, _stream())
+        call("mog_pool2d_bwd", None, _ptr(idx), dy.data_ptr(), dx.data_ptr(), N, H, W, Cc, k, stride, pad, mode, _stream())
         return dx, None, None, None, None
 
 

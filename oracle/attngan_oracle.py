@@ -370,8 +370,9 @@ def leafify(sd):
     return P
 
 
-def gd_step(PG, PDs, cfg, batch, eps=None):
-    """G forward, three D losses + backward, G adversarial + KL loss + backward.
+def gd_step(PG, PDs, cfg, batch, eps=None, PE=None):
+    """G forward, three D losses + backward, G adversarial (+ DAMSM when the image-encoder weights ``PE`` are given,
+    losses.py:205-224) + KL loss + backward.
     Returns losses, fake images and leaves gradients in ``.grad`` of PG / PDs[i].
     Order follows trainer.py:294-340.  D weight gradients produced by the G-step backward are
     *not* accumulated (they are discarded by the next zero_grad in the reference, trainer.py:304)."""
@@ -394,6 +395,13 @@ def gd_step(PG, PDs, cfg, batch, eps=None):
     errG = generator_gan_loss(PDs, cfg, fake_imgs, batch["sent_emb"], real_labels,
                               batch["label_one_hot"], batch["transf_matrices"],
                               batch["transf_matrices_inv"])
+    if PE is not None:
+        from .encoder_oracle import cnn_encoder
+        match = torch.arange(B)
+        region, code = cnn_encoder(PE, fake_imgs[-1])
+        w0, w1 = words_loss(region, batch["words_embs"], match, batch["cap_lens"], batch["class_ids"], B, cfg)[:2]
+        s0, s1 = sent_loss(code, batch["sent_emb"], match, batch["class_ids"], B, cfg)
+        errG = errG + (w0 + w1) * cfg.LAMBDA + (s0 + s1) * cfg.LAMBDA
     kl = kl_loss(mu, logvar)
     gparams = [p for p in PG.values() if p.requires_grad]
     grads = torch.autograd.grad(errG + kl, gparams, allow_unused=True)

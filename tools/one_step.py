@@ -12,7 +12,15 @@ warm = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 cfg = bench.set_cfg(); ops.set_precision(prec); cfg.TRAIN.BATCH_SIZE = B
 torch.manual_seed(1234)
 tr = condGANTrainer("", None, 0, None)
-_, _, netG, netsD, _ = tr.build_models()
+enc = None
+if os.environ.get("MOG_NO_DAMSM", "0") != "1":
+    from mog_b200.attngan.model import CNN_ENCODER
+    enc = CNN_ENCODER(256)
+    enc.load_state_dict(synth.fill_encoder_state_dict(enc.state_dict(), 9))
+    for p in enc.parameters():
+        p.requires_grad = False
+    enc.cuda().eval()
+_, _, netG, netsD, _ = tr.build_models(image_encoder=enc)
 optG, optDs = tr.define_optimizers(netG, netsD)
 st = tr.make_step_state(netG, netsD, optG, optDs)
 h = synth.attngan_batch(B, seed=1234)
