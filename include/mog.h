@@ -88,6 +88,10 @@ int mog_pack_weight(const MogConvDesc* d, int which, const float* w_oihw, void* 
  * (channel count must then be a multiple of 8). */
 size_t mog_planes_bytes(long long rows, int C, int precision);
 int mog_split_planes(const float* x, long long rows, int C, int precision, void* planes, void* stream);
+/* Same for the gradient of a conv whose epilogue applied an activation: splits dy * act'(y) (y = the activation OUTPUT;
+ * RELU / LRELU / TANH / SIGMOID), i.e. mog_act_bwd fused into the split -- the fp32 dz is never materialised. */
+int mog_split_planes_act(const float* dy, const float* y, int act, long long rows, int C, int precision, void* planes,
+                         void* stream);
 
 /* replaces: nn.Conv2d forward incl. a preceding nn.Upsample(2,'nearest') (model.py:41-55,
  * 587-609,626,664-677; GlobalAttention.py:25-28) and nn.Linear (H=W=KH=KW=1; model.py:324,

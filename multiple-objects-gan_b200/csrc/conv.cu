@@ -356,6 +356,15 @@ extern "C" int mog_split_planes(const float* x, long long rows, int C, int preci
   return launch_split_planes(x, rows, C, p8(C), planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream));
 }
 
+extern "C" int mog_split_planes_act(const float* dy, const float* y, int act, long long rows, int C, int precision, void* planes,
+                                    void* stream) {
+  MOG_REQUIRE(dy && y && planes && rows > 0 && C > 0, "mog_split_planes_act: bad argument");
+  MOG_REQUIRE(precision == MOG_PREC_BF16X3 || precision == MOG_PREC_BF16, "mog_split_planes_act: precision must be a tcgen05 mode");
+  MOG_REQUIRE(act == MOG_ACT_RELU || act == MOG_ACT_LRELU || act == MOG_ACT_TANH || act == MOG_ACT_SIGMOID,
+              "mog_split_planes_act: activation %d has no output-based derivative", act);
+  return launch_split_planes(dy, rows, C, p8(C), planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream), y, act);
+}
+
 static int build(const MogConvDesc* d, int which, Problem* probs, int* hires) {
   *hires = 0;
   return which == 0 ? build_fwd(d, probs) : build_dgrad(d, probs, hires);

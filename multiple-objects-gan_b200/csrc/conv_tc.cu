@@ -499,8 +499,10 @@ __global__ void patch_dgrad_kernel(const PatchDgradArgs a) {
 
 // fp32 [rows][C] -> bf16 planes [rows][CP] (hi, and lo = bf16(x - hi) when nplanes == 2); CP = C rounded up
 // to 8, pad channels zero.  One thread per 8-channel chunk.
+// With y != nullptr the value split is x * act'(y) (x = upstream gradient, y = activation OUTPUT of a conv epilogue):
+// the backward of the epilogue activation fused into the split, so dz never exists in fp32.
 __global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int C, int CP, __nv_bfloat16* hi,
-                                    __nv_bfloat16* lo) {
+                                    __nv_bfloat16* lo, const float* __restrict__ y, int act) {
   const int cpr = CP >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cpr) return;
@@ -514,6 +516,20 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? __ldg(xp + j) : 0.f;
+  }
+  if (y) {
+    const float* yp = y + (size_t)r * C + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = (c0 + j < C) ? __ldg(yp + j) : 0.f;
+      switch (act) {
+        case MOG_ACT_RELU: f[j] = v > 0.f ? f[j] : 0.f; break;
+        case MOG_ACT_LRELU: f[j] = v > 0.f ? f[j] : 0.2f * f[j]; break;
+        case MOG_ACT_TANH: f[j] *= 1.f - v * v; break;
+        case MOG_ACT_SIGMOID: f[j] *= v * (1.f - v); break;
+        default: break;
+      }
+    }
   }
   uint32_t h[4], l[4];
 #pragma unroll
@@ -536,11 +552,12 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
 // ---------------------------------------------------------------------------------------------
 using namespace tc;
 
-int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st) {
+int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st, const float* y,
+                        int act) {
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(planes);
   __nv_bfloat16* lo = nplanes == 2 ? hi + (size_t)rows * CP : nullptr;
   const long long n = rows * (CP / 8);
-  tc::split_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, rows, C, CP, hi, lo);
+  tc::split_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, rows, C, CP, hi, lo, y, act);
   return check_launch("split_planes_kernel");
 }
 

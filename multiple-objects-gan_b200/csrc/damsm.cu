@@ -47,26 +47,31 @@ struct PairSmem {
   float* cosv; // [TMAXW] cos, [TMAXW] |w|, [TMAXW] |v|, [TMAXW] wv
 };
 
-__device__ __forceinline__ PairSmem carve(float* sm, int R, int D) {
+// tp: word pitch of the layout (= the kernel's NT: Tw rounded up to 8; 18 words -> 24 keeps the forward at 82 KB, two CTAs per SM)
+__device__ __forceinline__ PairSmem carve(float* sm, int R, int D, int tp) {
   PairSmem p;
   p.w = sm;
-  p.S = p.w + (size_t)D * (TMAXW + 1);
-  p.A2 = p.S + (size_t)R * (TMAXW + 1);
-  p.red = p.A2 + (size_t)TMAXW * (R + 1);
-  p.cosv = p.red + 3 * TMAXW * (DT / 32 + 1);
+  p.S = p.w + (size_t)D * (tp + 1);
+  p.A2 = p.S + (size_t)R * (tp + 1);
+  p.red = p.A2 + (size_t)tp * (R + 1);
+  p.cosv = p.red + 3 * tp * (DT / 32 + 1);
   return p;
 }
-static size_t pair_smem_bytes(int R, int D) {
-  return sizeof(float) * ((size_t)D * (TMAXW + 1) + (size_t)R * (TMAXW + 1) + (size_t)TMAXW * (R + 1) +
-                          3 * TMAXW * (DT / 32 + 1) + 4 * TMAXW + (size_t)TMAXW * (R + 1));
+static size_t pair_smem_bytes(int R, int D, int tp, bool bwd) {
+  size_t f = (size_t)D * (tp + 1) + (size_t)R * (tp + 1) + (size_t)tp * (R + 1) + 3 * tp * (DT / 32 + 1) + 4 * tp;
+  if (bwd) f += (size_t)tp * (R + 1) + (size_t)D * (tp + 1);   // dA, dvs
+  return sizeof(float) * f;
 }
 
 // forward of one pair up to v (kept in registers: v[k][t] for channel c = tid + k*DT) and cos/|w|/|v|/wv in smem
-template <int CPT>
+// NT: compile-time bound of the word loops (Tw rounded up to 8): the unrolled loops issue NT, not TMAXW, predicated slots.
+// The loops over regions / channel chunks that start with a global load are unrolled so that several loads are in flight
+// (one CTA of 8 warps per SM: an exposed L2 round trip per iteration made a pair take 240 us).
+template <int CPT, int NT>
 __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float* ctx, const float* wi, int n,
-                             float (&v)[CPT][TMAXW]) {
+                             float (&v)[CPT][NT]) {
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int ldw = TMAXW + 1;
+  const int ldw = NT + 1;
   for (int i = tid; i < a.D * n; i += DT) {
     int c = i / n, t = i - c * n;
     s.w[c * ldw + t] = __ldg(wi + (size_t)c * a.Tw + t);
@@ -74,17 +79,18 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
   __syncthreads();
   // scores: one warp per region, lanes over channels
   for (int r = wrp; r < a.R; r += DT / 32) {
-    float acc[TMAXW];
+    float acc[NT];
 #pragma unroll
-    for (int t = 0; t < TMAXW; ++t) acc[t] = 0.f;
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+#pragma unroll 4
     for (int c = lane; c < a.D; c += 32) {
       const float x = __ldg(ctx + (size_t)r * a.D + c);
 #pragma unroll
-      for (int t = 0; t < TMAXW; ++t)
+      for (int t = 0; t < NT; ++t)
         if (t < n) acc[t] = fmaf(x, s.w[c * ldw + t], acc[t]);
     }
 #pragma unroll
-    for (int t = 0; t < TMAXW; ++t) {
+    for (int t = 0; t < NT; ++t) {
       if (t < n) {
         float z = warp_sum(acc[t]);
         if (lane == 0) s.S[r * ldw + t] = z;
@@ -126,7 +132,8 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
 #pragma unroll
   for (int k = 0; k < CPT; ++k)
 #pragma unroll
-    for (int t = 0; t < TMAXW; ++t) v[k][t] = 0.f;
+    for (int t = 0; t < NT; ++t) v[k][t] = 0.f;
+#pragma unroll 8
   for (int r = 0; r < a.R; ++r) {
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
@@ -134,7 +141,7 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
       if (c < a.D) {
         const float x = __ldg(ctx + (size_t)r * a.D + c);
 #pragma unroll
-        for (int t = 0; t < TMAXW; ++t)
+        for (int t = 0; t < NT; ++t)
           if (t < n) v[k][t] = fmaf(x, s.A2[t * (a.R + 1) + r], v[k][t]);
       }
     }
@@ -142,7 +149,7 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
   // cos(w_t, v_t): block reductions of <w,v>, |w|^2, |v|^2 over channels
   const int ldr = DT / 32 + 1;
 #pragma unroll
-  for (int t = 0; t < TMAXW; ++t) {
+  for (int t = 0; t < NT; ++t) {
     if (t < n) {
       float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
@@ -157,9 +164,9 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
       }
       p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
       if (lane == 0) {
-        s.red[(0 * TMAXW + t) * ldr + wrp] = p0;
-        s.red[(1 * TMAXW + t) * ldr + wrp] = p1;
-        s.red[(2 * TMAXW + t) * ldr + wrp] = p2;
+        s.red[(0 * NT + t) * ldr + wrp] = p0;
+        s.red[(1 * NT + t) * ldr + wrp] = p1;
+        s.red[(2 * NT + t) * ldr + wrp] = p2;
       }
     }
   }
@@ -167,29 +174,29 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
   if (tid < n) {
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
     for (int j = 0; j < DT / 32; ++j) {
-      p0 += s.red[(0 * TMAXW + tid) * ldr + j];
-      p1 += s.red[(1 * TMAXW + tid) * ldr + j];
-      p2 += s.red[(2 * TMAXW + tid) * ldr + j];
+      p0 += s.red[(0 * NT + tid) * ldr + j];
+      p1 += s.red[(1 * NT + tid) * ldr + j];
+      p2 += s.red[(2 * NT + tid) * ldr + j];
     }
     const float nw = sqrtf(p1), nv = sqrtf(p2);
     s.cosv[tid] = p0 / fmaxf(nw * nv, a.eps);   // miscc/losses.py:11-17
-    s.cosv[TMAXW + tid] = nw;
-    s.cosv[2 * TMAXW + tid] = nv;
-    s.cosv[3 * TMAXW + tid] = p0;
+    s.cosv[NT + tid] = nw;
+    s.cosv[2 * NT + tid] = nv;
+    s.cosv[3 * NT + tid] = p0;
   }
   __syncthreads();
 }
 
-template <int CPT>
+template <int CPT, int NT>
 __global__ void __launch_bounds__(DT) damsm_fwd_kernel(DamsmArgs a) {
   extern __shared__ float sm[];
-  const PairSmem s = carve(sm, a.R, a.D);
+  const PairSmem s = carve(sm, a.R, a.D, NT);
   const int b = blockIdx.x, i = a.paired ? blockIdx.x : blockIdx.y;
   const int n = min(a.lens[i], a.Tw);
   const float* ctx = a.ctx + (size_t)b * a.R * a.D;
   const float* wi = a.words + (size_t)i * a.D * a.Tw;
-  float v[CPT][TMAXW];
-  pair_forward<CPT>(a, s, ctx, wi, n, v);
+  float v[CPT][NT];
+  pair_forward<CPT, NT>(a, s, ctx, wi, n, v);
   const int tid = threadIdx.x;
   const size_t pair = a.paired ? (size_t)b : (size_t)b * a.NI + i;
   if (tid == 0 && a.sims) {
@@ -201,8 +208,11 @@ __global__ void __launch_bounds__(DT) damsm_fwd_kernel(DamsmArgs a) {
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int c = tid + k * DT;
-      if (c < a.D)
-        for (int t = 0; t < n; ++t) a.wei_out[(pair * a.D + c) * a.Tw + t] = v[k][t];
+      if (c < a.D) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          if (t < n) a.wei_out[(pair * a.D + c) * a.Tw + t] = v[k][t];
+      }
     }
   }
   if (a.attn_out) {
@@ -215,33 +225,33 @@ __global__ void __launch_bounds__(DT) damsm_fwd_kernel(DamsmArgs a) {
 
 // backward w.r.t. ctx: one CTA per (image b, caption i); its d ctx[b] contribution goes to slice i of the workspace
 // (a.dctx = workspace [NI][B][R][D])
-template <int CPT>
+template <int CPT, int NT>
 __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
   extern __shared__ float sm[];
-  const PairSmem s = carve(sm, a.R, a.D);
-  float* dA = s.cosv + 4 * TMAXW;   // [TMAXW][R+1]: d a2 -> d(gamma1*a1) -> reused
+  const PairSmem s = carve(sm, a.R, a.D, NT);
+  float* dA = s.cosv + 4 * NT;   // [NT][R+1]: d a2 -> d(gamma1*a1) -> reused
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const float* ctx = a.ctx + (size_t)b * a.R * a.D;
-  const int ldw = TMAXW + 1;
+  const int ldw = NT + 1;
   {
     const int i = blockIdx.y;
     float* dctx = a.dctx + ((size_t)i * a.B + b) * a.R * a.D;
     const float gsim = a.dsims[(size_t)b * a.NI + i];
     const int n = min(a.lens[i], a.Tw);
     const float* wi = a.words + (size_t)i * a.D * a.Tw;
-    float v[CPT][TMAXW];
+    float v[CPT][NT];
     __syncthreads();
-    pair_forward<CPT>(a, s, ctx, wi, n, v);
+    pair_forward<CPT, NT>(a, s, ctx, wi, n, v);
     // d cos_t = gsim * gamma2 * softmax_t(gamma2 cos);  dv_t[c] = dcos_t (w_t/(|w||v|) - cos_t v_t/|v|^2)
     float esum = 0.f;
     for (int t = 0; t < n; ++t) esum += expf(a.g2 * s.cosv[t]);
-    float dv[CPT][TMAXW];
+    float dv[CPT][NT];
 #pragma unroll
-    for (int t = 0; t < TMAXW; ++t) {
+    for (int t = 0; t < NT; ++t) {
       float dcos = 0.f, inv_wv = 0.f, c_over_v2 = 0.f;
       if (t < n) {
         dcos = gsim * a.g2 * expf(a.g2 * s.cosv[t]) / esum;
-        const float nw = s.cosv[TMAXW + t], nv = s.cosv[2 * TMAXW + t];
+        const float nw = s.cosv[NT + t], nv = s.cosv[2 * NT + t];
         if (nw * nv > a.eps) {   // clamp inactive (always, in practice)
           inv_wv = 1.f / (nw * nv);
           c_over_v2 = s.cosv[t] / (nv * nv);
@@ -258,26 +268,30 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
     // write dv to global scratch-free path: use dA as [t][r] accumulators via warp-per-region dot products needs dv by
     // channel across lanes, so stage dv through shared memory in slices of 32 words x D channels: reuse s.red? too small.
     // Use the w buffer layout for dv (D x ldw) in a dedicated region appended after dA.
-    float* dvs = dA + (size_t)TMAXW * (a.R + 1);   // [D][TMAXW+1]
+    float* dvs = dA + (size_t)NT * (a.R + 1);   // [D][NT+1]
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int c = tid + k * DT;
-      if (c < a.D)
-        for (int t = 0; t < n; ++t) dvs[c * ldw + t] = dv[k][t];
+      if (c < a.D) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)     // (static indices: dv stays in registers)
+          if (t < n) dvs[c * ldw + t] = dv[k][t];
+      }
     }
     __syncthreads();
     for (int r = wrp; r < a.R; r += DT / 32) {
-      float acc[TMAXW];
+      float acc[NT];
 #pragma unroll
-      for (int t = 0; t < TMAXW; ++t) acc[t] = 0.f;
+      for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+#pragma unroll 4
       for (int c = lane; c < a.D; c += 32) {
         const float x = __ldg(ctx + (size_t)r * a.D + c);
 #pragma unroll
-        for (int t = 0; t < TMAXW; ++t)
+        for (int t = 0; t < NT; ++t)
           if (t < n) acc[t] = fmaf(x, dvs[c * ldw + t], acc[t]);
       }
 #pragma unroll
-      for (int t = 0; t < TMAXW; ++t) {
+      for (int t = 0; t < NT; ++t) {
         if (t < n) {
           float z = warp_sum(acc[t]);
           if (lane == 0) dA[t * (a.R + 1) + r] = z;   // d a2[t][r]
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
         if (c < a.D) {
           float g = 0.f;
 #pragma unroll
-          for (int t = 0; t < TMAXW; ++t)
+          for (int t = 0; t < NT; ++t)
             if (t < n) g = fmaf(dv[k][t], s.A2[t * (a.R + 1) + r], fmaf(dA[t * (a.R + 1) + r], s.w[c * ldw + t], g));
           dctx[(size_t)r * a.D + c] = g;
         }
@@ -349,8 +363,11 @@ extern "C" int mog_damsm_words_fwd(const float* ctx, const float* words, const i
   MOG_REQUIRE(ctx && words && lens && (sims || wei_out || attn_out), "mog_damsm_words_fwd: null tensor");
   MOG_REQUIRE(!paired || B == NI, "mog_damsm_words_fwd: paired mode needs B == NI");
   DamsmArgs a{ctx, words, lens, sims, wei_out, attn_out, nullptr, nullptr, B, NI, R, D, Tw, paired, gamma1, gamma2, 1e-8f};
-  const size_t smem = pair_smem_bytes(R, D);
-  auto kern = D <= DT ? damsm_fwd_kernel<1> : damsm_fwd_kernel<2>;
+  const size_t smem = pair_smem_bytes(R, D, ((Tw - 1) / 8 + 1) * 8, false);
+  typedef void (*Kern)(DamsmArgs);
+  static const Kern table[2][4] = {{damsm_fwd_kernel<1, 8>, damsm_fwd_kernel<1, 16>, damsm_fwd_kernel<1, 24>, damsm_fwd_kernel<1, 32>},
+                                   {damsm_fwd_kernel<2, 8>, damsm_fwd_kernel<2, 16>, damsm_fwd_kernel<2, 24>, damsm_fwd_kernel<2, 32>}};
+  Kern kern = table[D <= DT ? 0 : 1][(Tw - 1) / 8];
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MOG_ERR_UNSUPPORTED, "mog_damsm_words_fwd: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
   dim3 grid(B, paired ? 1 : NI);
@@ -373,8 +390,11 @@ extern "C" int mog_damsm_words_bwd(const float* ctx, const float* words, const i
   const size_t need = mog_damsm_bwd_workspace_bytes(B, NI, R, D);
   if (!workspace || ws_bytes < need) return fail(MOG_ERR_WORKSPACE, "mog_damsm_words_bwd: workspace %zu < %zu", ws_bytes, need);
   DamsmArgs a{ctx, words, lens, nullptr, nullptr, nullptr, dsims, static_cast<float*>(workspace), B, NI, R, D, Tw, 0, gamma1, gamma2, 1e-8f};
-  const size_t smem = pair_smem_bytes(R, D) + sizeof(float) * (size_t)D * (TMAXW + 1);
-  auto kern = D <= DT ? damsm_bwd_kernel<1> : damsm_bwd_kernel<2>;
+  const size_t smem = pair_smem_bytes(R, D, ((Tw - 1) / 8 + 1) * 8, true);
+  typedef void (*Kern)(DamsmArgs);
+  static const Kern table[2][4] = {{damsm_bwd_kernel<1, 8>, damsm_bwd_kernel<1, 16>, damsm_bwd_kernel<1, 24>, damsm_bwd_kernel<1, 32>},
+                                   {damsm_bwd_kernel<2, 8>, damsm_bwd_kernel<2, 16>, damsm_bwd_kernel<2, 24>, damsm_bwd_kernel<2, 32>}};
+  Kern kern = table[D <= DT ? 0 : 1][(Tw - 1) / 8];
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MOG_ERR_UNSUPPORTED, "mog_damsm_words_bwd: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
   cudaStream_t st = as_stream(stream);

@@ -23,43 +23,83 @@ struct PoolArgs {
   long long total;
 };
 
+// V = channels per thread (4: 128-bit accesses when C % 4 == 0; 1: any C)
+template <int V>
+struct Vec { float v[V]; };
+template <int V>
+__device__ __forceinline__ Vec<V> ldv(const float* p) {
+  Vec<V> r;
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1 % V] = t.y; r.v[2 % V] = t.z; r.v[3 % V] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const Vec<V>& r) {
+  if (V == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1 % V], r.v[2 % V], r.v[3 % V]);
+  else *p = r.v[0];
+}
+
+template <int V>
 __global__ void pool_fwd_kernel(PoolArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // element index / V
   if (i >= a.total) return;
-  const int c = (int)(i % a.C);
-  long long q = i / a.C;
+  const int Cv = a.C / V;
+  const int c = (int)(i % Cv) * V;
+  long long q = i / Cv;
   const int wo = (int)(q % a.Wo);
   q /= a.Wo;
   const int ho = (int)(q % a.Ho);
   const int n = (int)(q / a.Ho);
   const float* xn = a.x + (size_t)n * a.H * a.W * a.C + c;
-  float acc = a.mode == 0 ? -FLT_MAX : 0.f;
-  int best = -1;
+  Vec<V> acc;
+  int best[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { acc.v[j] = a.mode == 0 ? -FLT_MAX : 0.f; best[j] = -1; }
   for (int kh = 0; kh < a.k; ++kh) {
     const int h = ho * a.s - a.p + kh;
     if (h < 0 || h >= a.H) continue;
     for (int kw = 0; kw < a.k; ++kw) {
       const int w = wo * a.s - a.p + kw;
       if (w < 0 || w >= a.W) continue;
-      const float v = __ldg(xn + ((size_t)h * a.W + w) * a.C);
-      if (a.mode == 0) {
-        if (v > acc || v != v || best < 0) { acc = v; best = kh * a.k + kw; }   // first maximum wins (torch)
-      } else {
-        acc += v;
+      const Vec<V> v = ldv<V>(xn + ((size_t)h * a.W + w) * a.C);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        if (a.mode == 0) {
+          if (v.v[j] > acc.v[j] || v.v[j] != v.v[j] || best[j] < 0) { acc.v[j] = v.v[j]; best[j] = kh * a.k + kw; }   // first maximum wins (torch)
+        } else {
+          acc.v[j] += v.v[j];
+        }
       }
     }
   }
-  a.out[i] = a.mode == 0 ? acc : acc / (float)(a.k * a.k);
-  if (a.idx) a.idx[i] = (unsigned char)best;
+  if (a.mode == 1) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc.v[j] = acc.v[j] / (float)(a.k * a.k);
+  }
+  stv<V>(a.out + i * V, acc);
+  if (a.idx) {
+    if (V == 4) {
+      *reinterpret_cast<uchar4*>(a.idx + i * V) = make_uchar4((unsigned char)best[0], (unsigned char)best[1 % V], (unsigned char)best[2 % V],
+                                                               (unsigned char)best[3 % V]);
+    } else {
+      a.idx[i] = (unsigned char)best[0];
+    }
+  }
 }
 
 __device__ __forceinline__ int fdiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
+template <int V>
 __global__ void pool_bwd_kernel(PoolArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) return;
-  const int c = (int)(i % a.C);
-  long long q = i / a.C;
+  const int Cv = a.C / V;
+  const int c = (int)(i % Cv) * V;
+  long long q = i / Cv;
   const int w = (int)(q % a.W);
   q /= a.W;
   const int h = (int)(q % a.H);
@@ -71,34 +111,54 @@ __global__ void pool_bwd_kernel(PoolArgs a) {
   ho_hi = min(ho_hi, a.Ho - 1); wo_hi = min(wo_hi, a.Wo - 1);
   const float* xn = a.x ? a.x + (size_t)n * a.H * a.W * a.C + c : nullptr;
   const float* dyn = a.dy + (size_t)n * a.Ho * a.Wo * a.C + c;
-  float acc = 0.f;
+  Vec<V> acc;
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
   for (int ho = ho_lo; ho <= ho_hi; ++ho)
     for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-      const float g = __ldg(dyn + ((size_t)ho * a.Wo + wo) * a.C);
+      const Vec<V> g = ldv<V>(dyn + ((size_t)ho * a.Wo + wo) * a.C);
       if (a.mode == 1) {
-        acc += g;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] += g.v[j];
       } else if (a.idx) {
         // the forward recorded each window's arg-max position
-        const int pos = a.idx[((size_t)n * a.Ho * a.Wo + (size_t)ho * a.Wo + wo) * a.C + c];
-        if (ho * a.s - a.p + pos / a.k == h && wo * a.s - a.p + pos % a.k == w) acc += g;
-      } else {
-        // arg-max of this window, first maximum wins (torch: `val > maxval || isnan(val)`)
-        float best = -FLT_MAX;
-        int bh = -1, bw = -1;
-        for (int kh = 0; kh < a.k; ++kh) {
-          const int hh = ho * a.s - a.p + kh;
-          if (hh < 0 || hh >= a.H) continue;
-          for (int kw = 0; kw < a.k; ++kw) {
-            const int ww = wo * a.s - a.p + kw;
-            if (ww < 0 || ww >= a.W) continue;
-            const float v = __ldg(xn + ((size_t)hh * a.W + ww) * a.C);
-            if (v > best || v != v || bh < 0) { best = v; bh = hh; bw = ww; }
-          }
+        const unsigned char* ip = a.idx + ((size_t)n * a.Ho * a.Wo + (size_t)ho * a.Wo + wo) * a.C + c;
+        unsigned char pos[V];
+        if (V == 4) {
+          const uchar4 t = *reinterpret_cast<const uchar4*>(ip);
+          pos[0] = t.x; pos[1 % V] = t.y; pos[2 % V] = t.z; pos[3 % V] = t.w;
+        } else {
+          pos[0] = *ip;
         }
-        if (bh == h && bw == w) acc += g;
+        const int me = (h - (ho * a.s - a.p)) * a.k + (w - (wo * a.s - a.p));   // this pixel's position inside the window
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if ((int)pos[j] == me) acc.v[j] += g.v[j];
+      } else {
+        // arg-max of this window recomputed from x, first maximum wins (torch: `val > maxval || isnan(val)`)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float best = -FLT_MAX;
+          int bh = -1, bw = -1;
+          for (int kh = 0; kh < a.k; ++kh) {
+            const int hh = ho * a.s - a.p + kh;
+            if (hh < 0 || hh >= a.H) continue;
+            for (int kw = 0; kw < a.k; ++kw) {
+              const int ww = wo * a.s - a.p + kw;
+              if (ww < 0 || ww >= a.W) continue;
+              const float v = __ldg(xn + ((size_t)hh * a.W + ww) * a.C + j);
+              if (v > best || v != v || bh < 0) { best = v; bh = hh; bw = ww; }
+            }
+          }
+          if (bh == h && bw == w) acc.v[j] += g.v[j];
+        }
       }
     }
-  a.out[i] = a.mode == 1 ? acc / (float)(a.k * a.k) : acc;
+  if (a.mode == 1) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc.v[j] = acc.v[j] / (float)(a.k * a.k);
+  }
+  stv<V>(a.out + i * V, acc);
 }
 
 // ---- bilinear resize (torch upsample_bilinear2d) ------------------------------------------------
@@ -203,8 +263,10 @@ extern "C" int mog_pool2d_fwd(const float* x, float* y, unsigned char* argmax, i
   int Ho, Wo;
   int rc = mog_pool2d_out_hw(H, W, k, stride, pad, &Ho, &Wo);
   if (rc) return rc;
-  PoolArgs a{x, nullptr, y, argmax, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * Ho * Wo * C};
-  pool_fwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  const int V = (C & 3) == 0 ? 4 : 1;
+  PoolArgs a{x, nullptr, y, argmax, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * Ho * Wo * C / V};
+  if (V == 4) pool_fwd_kernel<4><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  else pool_fwd_kernel<1><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
   return check_launch("pool_fwd_kernel");
 }
 
@@ -215,8 +277,10 @@ extern "C" int mog_pool2d_bwd(const float* x, const unsigned char* argmax, const
   int Ho, Wo;
   int rc = mog_pool2d_out_hw(H, W, k, stride, pad, &Ho, &Wo);
   if (rc) return rc;
-  PoolArgs a{x, dy, dx, const_cast<unsigned char*>(argmax), N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * H * W * C};
-  pool_bwd_kernel<<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  const int V = (C & 3) == 0 ? 4 : 1;
+  PoolArgs a{x, dy, dx, const_cast<unsigned char*>(argmax), N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * H * W * C / V};
+  if (V == 4) pool_bwd_kernel<4><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  else pool_bwd_kernel<1><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
   return check_launch("pool_bwd_kernel");
 }
 

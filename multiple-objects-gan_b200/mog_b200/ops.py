@@ -206,25 +206,35 @@ class Conv2dFn(torch.autograd.Function):
         d, Ho, Wo = _desc(xshape, w4.shape, stride, pad, up2x, ACT_NONE, precision)
         st = _stream()
         dev = dy.device
-        if act != ACT_NONE:
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dyp = None
+        if act != ACT_NONE and precision != PREC_FP32 and not need_db and (need_dx or need_dw):
+            # backward of the epilogue activation fused into the plane split: dz = dy * act'(y) never exists in fp32
+            Cc = dy.shape[-1]
+            rows = dy.numel() // Cc
+            dyp = torch.empty((_lib.lib().mog_planes_bytes(rows, Cc, precision) + 3) // 4, device=dev, dtype=torch.float32)
+            call("mog_split_planes_act", dy.data_ptr(), y.data_ptr(), act, rows, Cc, precision, dyp.data_ptr(), st)
+            dy = None
+        elif act != ACT_NONE:
             dz = torch.empty_like(dy)
             call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, st)
             dy = dz
-        need_dx = ctx.needs_input_grad[0]
-        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
-        dyp = split_planes(dy, precision) if precision != PREC_FP32 and (need_dx or need_dw) else None
+        if dyp is None and precision != PREC_FP32 and (need_dx or need_dw):
+            dyp = split_planes(dy, precision)
         dx = dw = db = None
         if need_dx:
             dx = torch.empty(xshape, device=dev, dtype=torch.float32)
             ws, nws = _workspace(d, 1, dev)
-            call("mog_conv2d_dgrad", C.byref(d), dy.data_ptr(), _ptr(dyp), _packed(weight, "dgrad", d).data_ptr(),
+            call("mog_conv2d_dgrad", C.byref(d), _ptr(dy), _ptr(dyp), _packed(weight, "dgrad", d).data_ptr(),
                  dx.data_ptr(), _ptr(ws), nws, st)
         if need_dw:
             dw = torch.empty(w4.shape, device=dev, dtype=torch.float32)
             if ctx.has_bias:
                 db = torch.empty(d.Cout, device=dev, dtype=torch.float32)
             ws, nws = _workspace(d, 2, dev)
-            call("mog_conv2d_wgrad", C.byref(d), _ptr(x), _ptr(xp), dy.data_ptr(), _ptr(dyp), dw.data_ptr(), _ptr(db),
+            call("mog_conv2d_wgrad", C.byref(d), _ptr(x), _ptr(xp), _ptr(dy), _ptr(dyp), dw.data_ptr(), _ptr(db),
                  _ptr(ws), nws, st)
             dw = dw.reshape(weight.shape)
         return dx, dw, db, None, None, None, None, None

@@ -83,13 +83,13 @@ def test_libmog_encoder_matches_reference(prec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [(0, 3, 2, 0, 35, 35), (0, 3, 2, 0, 147, 147), (1, 3, 1, 1, 17, 17), (1, 8, 8, 0, 8, 8),
-                                  (0, 3, 2, 1, 9, 12), (1, 2, 2, 0, 7, 9)])
+@pytest.mark.parametrize("case", [(0, 3, 2, 0, 35, 35, 24), (0, 3, 2, 0, 147, 147, 24), (1, 3, 1, 1, 17, 17, 24), (1, 8, 8, 0, 8, 8, 24),
+                                  (0, 3, 2, 1, 9, 12, 24), (1, 2, 2, 0, 7, 9, 24), (0, 3, 2, 0, 13, 11, 6), (1, 3, 1, 1, 5, 7, 3)])
 def test_pool2d_matches_torch(case):
     from mog_b200 import ops
-    mode, k, s, p, H, W = case
+    mode, k, s, p, H, W, Cc = case
     torch.manual_seed(3)
-    x = torch.randn(3, H, W, 24, device="cuda")
+    x = torch.randn(3, H, W, Cc, device="cuda")
     x[0, :4, :4] = 1.25   # ties: the first maximum must get the gradient
     # (contiguous NCHW on the torch side: its avg_pool2d backward mishandles a channels_last-strided gradient on this build)
     xr = x.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
@@ -102,6 +102,13 @@ def test_pool2d_matches_torch(case):
     y.backward(g)
     yr.backward(g.permute(0, 3, 1, 2).contiguous())
     assert torch.allclose(xm.grad.permute(0, 3, 1, 2), xr.grad, rtol=1e-5, atol=2e-6)
+    if mode == 0:   # the C-ABI's other max-pool backward: arg-max recomputed from the forward input (no recorded positions)
+        from mog_b200._lib import call
+        dx = torch.empty_like(x)
+        N, Ho, Wo = y.shape[0], y.shape[1], y.shape[2]
+        call("mog_pool2d_bwd", x.data_ptr(), None, g.contiguous().data_ptr(), dx.data_ptr(), N, H, W, Cc, k, s, p, 0,
+             torch.cuda.current_stream().cuda_stream)
+        assert torch.allclose(dx.permute(0, 3, 1, 2), xr.grad, rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.gpu
