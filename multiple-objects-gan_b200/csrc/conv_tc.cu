@@ -24,6 +24,7 @@
 //   lane quarter and split the columns), add bias / apply the activation, store fp32 NHWC rows.
 //
 // The weight gradient (reduction over pixels, both operands MN-major) is in conv_tc_wgrad.cu.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "conv_common.cuh"
@@ -51,8 +52,27 @@ struct TcParams {
   int kc_per_split;
 };
 
+// B (packed weights [Npad][Kpad], K-major) as TMA tensor maps, hi and lo plane: the PLANES kernel stages every B chunk
+// with ONE bulk tensor copy per plane (box {64 k, BN rows}, SWIZZLE_128B = the layout the MMA descriptors expect) instead
+// of BN*8 16-byte cp.async per plane: with B = 2/3 of a stage's bytes the producers' LDGSTS issue rate (~8 clk per warp
+// instruction) had capped the tensor pipe at ~22 % on the weight-heavy discriminator layers.
+struct TcMaps {
+  CUtensorMap b[2];
+};
+
+__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// raises the barrier's pending transaction count without arriving (the issuing thread still arrives like every producer)
+__device__ __forceinline__ void tc_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
 template <bool PLANES>
-__global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned base (SWIZZLE_128B atoms)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -159,17 +179,11 @@ __global__ void __launch_bounds__(CTHREADS, 1) conv_tc_kernel(const TcParams p) 
             if (++tw == g.ntw) { tw = 0; ++th; }
           }
         }
-        const size_t kbase = (size_t)kc * BK;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = t + u * CPROD;
-          if (i < nB) {
-            const int row = i >> 3, ch = i & 7;
-            const size_t goff = (size_t)(n0 + row) * p.Kpad + kbase + ch * 8;
-            const uint32_t soff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
-            cp_async16(b_hi + soff, p.Bhi + goff, 16u);
-            if (nplanes == 2) cp_async16(b_lo + soff, p.Blo + goff, 16u);
-          }
+        if (t == 0) {
+          // B chunk of this stage: one bulk tensor copy per plane, completing on the stage's full barrier
+          tc_expect_tx(&full[s], (uint32_t)(nplanes * b_plane));
+          tc_tma_2d(b_hi, &maps.b[0], &full[s], kc * BK, n0);
+          if (nplanes == 2) tc_tma_2d(b_lo, &maps.b[1], &full[s], kc * BK, n0);
         }
         cp_async_commit();
         if (it >= LAG) {
@@ -659,6 +673,20 @@ size_t tc_igemm_workspace_bytes(long long M, int ntaps, int Cs, int Cd, int pass
   return splits > 1 ? (size_t)splits * M * Cd * sizeof(float) : 0;
 }
 
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TcEncodeFn>(ptr);
+  }
+  return fn;
+}
+
 int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* workspace, size_t ws_bytes,
                     cudaStream_t st) {
   TcWeightLayout L = tc_weight_layout(g.nth * g.ntw, g.Cs, g.Cd, passes);
@@ -698,13 +726,27 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* 
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div_ll(g.M, BM), (unsigned)L.ntiles, (unsigned)splits);
+  TcMaps maps{};
   if (g.src_planes) {
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    for (int pl = 0; pl < 2; ++pl) {
+      const __nv_bfloat16* base = (pl == 1 && p.Blo) ? p.Blo : p.Bhi;   // (lo map aliases hi in single-pass mode: never used)
+      cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.Npad};
+      cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 2};
+      cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)L.BN};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(&maps.b[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled(conv_tc B) failed: %d", (int)r);
+    }
     p.Xhi = static_cast<const __nv_bfloat16*>(g.src_planes);
     p.Xlo = p.Xhi + g.src_plane_elems;
-    conv_tc_kernel<true><<<grid, CTHREADS, smem, st>>>(p);
+    conv_tc_kernel<true><<<grid, CTHREADS, smem, st>>>(maps, p);
   } else {
     p.Xhi = p.Xlo = nullptr;
-    conv_tc_kernel<false><<<grid, CTHREADS, smem, st>>>(p);
+    conv_tc_kernel<false><<<grid, CTHREADS, smem, st>>>(maps, p);
   }
   int rc = check_launch("conv_tc_kernel");
   if (rc || splits == 1) return rc;
