@@ -332,8 +332,14 @@ def roofline_probe(dev, args, B):
     flops = 2.0 * B * 256 * 256 * 96 * 864
     achieved = flops / (ms / 1e3) / 1e12
     peak = pk["bf16_tflops"]
+    # DRAM bytes of this conv from the committed ncu --set full capture (profiles/r1c_conv_halo_up.raw.csv: four sub-pixel
+    # phase launches, 201.6 MB read + ~158.7 MB written each, at B = 32); algorithmic: 201 MB planes in + 805 MB fp32 out
+    traffic = 4 * (201.56e6 + 158.67e6) * (B / 32.0)
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "conv fwd G.h_net3.upsample (up2x + 3x3, 96->96 @256^2), precision=%s" % args.precision,
+            "traffic": traffic, "executed_tflops": achieved * 3.0 / 2.25,
+            "note": "achieved counts the dense fp32-equivalent FLOPs of the upsampled 3x3 conv; the kernel executes 2.25x fewer "
+                    "MACs (sub-pixel phases) x 3 bf16 passes (hi*hi + lo*hi + hi*lo)",
+            "kernel": "conv fwd G.h_net3.upsample (up2x + 3x3, 96->96 @256^2), precision=%s" % args.precision,
             "ms_per_launch": ms, "peak_source": src + " bf16 burst (kernel timed alone)",
             "algorithmic_flops_per_launch": flops}
 

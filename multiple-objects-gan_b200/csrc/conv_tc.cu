@@ -24,6 +24,8 @@
 //   lane quarter and split the columns), add bias / apply the activation, store fp32 NHWC rows.
 //
 // The weight gradient (reduction over pixels, both operands MN-major) is in conv_tc_wgrad.cu.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -576,8 +578,14 @@ int launch_split_planes(const float* x, long long rows, int C, int CP, void* pla
 }
 
 int tc_bn_for(int Cd) {
+  static int cap = 0;
+  if (!cap) {
+    const char* e = getenv("MOG_TC_BN_CAP");   // tuning knob: largest N tile of the generic kernel (default 256)
+    cap = e ? atoi(e) : 256;
+    if (cap < 16 || cap > 256) cap = 256;
+  }
   int cpad = ceil_div(Cd, 16) * 16;
-  int tiles = ceil_div(cpad, 256);
+  int tiles = ceil_div(cpad, cap);
   int bn = ceil_div(ceil_div(cpad, tiles), 16) * 16;
   return bn;
 }
