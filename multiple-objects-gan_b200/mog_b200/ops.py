@@ -90,7 +90,7 @@ def nhwc(x):
 # ---------------------------------------------------------------------------------------------
 # convolution / linear
 # ---------------------------------------------------------------------------------------------
-def _packed(weight: torch.Tensor, which: str, d: MogConvDesc) -> torch.Tensor:
+def _packed(weight: torch.Tensor, which: str, d: MogConvDesc, dkey=None) -> torch.Tensor:
     """Pack an OIHW parameter into the GEMM B operand of the kernel selected by ``d`` (fp32 matrix or
     bf16 hi/lo planes per stride phase); cached on the tensor per (version, conv geometry)."""
     cache = getattr(weight, "_mog_pack", None)
@@ -103,7 +103,11 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc) -> torch.Tensor:
             pass
     # the dgrad packing depends on stride/pad (phase tap subsets) and, with odd sizes, on H/W parity
     wi = 0 if which == "fwd" else 1
-    tag = _lib.lib().mog_packed_weight_layout(C.byref(d), wi)
+    tag = _layout_cache.get((dkey, wi)) if dkey is not None else None
+    if tag is None:
+        tag = _lib.lib().mog_packed_weight_layout(C.byref(d), wi)
+        if dkey is not None:
+            _layout_cache[(dkey, wi)] = tag
     key = (which, tag, d.precision, d.stride, d.pad, d.pad_w1, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
     if key not in cache:
         w = weight.detach()
@@ -118,7 +122,32 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc) -> torch.Tensor:
     return cache[key]
 
 
+_desc_cache = {}
+_ws_cache = {}
+_layout_cache = {}
+_planes_bytes_cache = {}
+
+
+def _planes_bytes(rows, Cc, precision):
+    k = (rows, Cc, precision)
+    v = _planes_bytes_cache.get(k)
+    if v is None:
+        v = _planes_bytes_cache[k] = _lib.lib().mog_planes_bytes(rows, Cc, precision)
+    return v
+
+
 def _desc(x_shape, w_shape, stride, pad, up2x, act, precision):
+    """Conv descriptor + output size for a call site; cached per geometry (the host side of a step issues ~2000 launches,
+    so every avoidable ctypes round trip matters: the GPU must not wait for Python)."""
+    key = (tuple(x_shape), tuple(w_shape), stride, pad if not isinstance(pad, list) else tuple(pad), bool(up2x), act, precision)
+    hit = _desc_cache.get(key)
+    if hit is not None:
+        return hit
+    hit = _desc_cache[key] = _desc_uncached(x_shape, w_shape, stride, pad, up2x, act, precision) + (key,)
+    return hit
+
+
+def _desc_uncached(x_shape, w_shape, stride, pad, up2x, act, precision):
     N, H, W, Ci = x_shape
     Co, Ci2, KH, KW = w_shape
     if Ci != Ci2:
@@ -132,8 +161,12 @@ def _desc(x_shape, w_shape, stride, pad, up2x, act, precision):
     return d, ho.value, wo.value
 
 
-def _workspace(d, which, device):
-    n = _lib.lib().mog_conv_workspace_bytes(C.byref(d), which)
+def _workspace(d, which, device, key=None):
+    n = _ws_cache.get((key, which)) if key is not None else None
+    if n is None:
+        n = _lib.lib().mog_conv_workspace_bytes(C.byref(d), which)
+        if key is not None:
+            _ws_cache[(key, which)] = n
     if n == 0:
         return None, 0
     ws = torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
@@ -145,7 +178,7 @@ def _alloc_planes(shape, precision, device):
     rows = 1
     for v in shape[:-1]:
         rows *= int(v)
-    n = _lib.lib().mog_planes_bytes(rows, Cc, precision)
+    n = _planes_bytes(rows, Cc, precision)
     return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
 
 
@@ -166,7 +199,7 @@ def split_planes(x: torch.Tensor, precision: int):
     """fp32 [..., C] -> bf16 planes buffer (hi [rows][C8], then lo for bf16x3) for the tcgen05 kernels."""
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    n = _lib.lib().mog_planes_bytes(rows, Cc, precision)
+    n = _planes_bytes(rows, Cc, precision)
     planes = torch.empty((n + 3) // 4, device=x.device, dtype=torch.float32)
     call("mog_split_planes", x.data_ptr(), rows, Cc, precision, planes.data_ptr(), _stream())
     return planes
@@ -182,12 +215,12 @@ class Conv2dFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, stride, pad, up2x, act, precision):
         _chk(x, "conv input")
         w4 = weight if weight.dim() == 4 else weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
-        d, Ho, Wo = _desc(x.shape, w4.shape, stride, pad, up2x, act, precision)
+        d, Ho, Wo, dkey = _desc(x.shape, w4.shape, stride, pad, up2x, act, precision)
         y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
-        ws, nws = _workspace(d, 0, x.device)
+        ws, nws = _workspace(d, 0, x.device, dkey)
         b = None if bias is None else bias.detach().contiguous()
         xp = planes_of(x, precision) if precision != PREC_FP32 else None
-        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _ptr(xp), _packed(weight, "fwd", d).data_ptr(), _ptr(b),
+        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _ptr(xp), _packed(weight, "fwd", d, dkey).data_ptr(), _ptr(b),
              y.data_ptr(), _ptr(ws), nws, _stream())
         ctx.cfg = (stride, pad, up2x, act, precision, tuple(x.shape))
         ctx.has_bias = bias is not None
@@ -203,7 +236,7 @@ class Conv2dFn(torch.autograd.Function):
         stride, pad, up2x, act, precision, xshape = ctx.cfg
         dy = dy.contiguous()
         w4 = weight if weight.dim() == 4 else weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
-        d, Ho, Wo = _desc(xshape, w4.shape, stride, pad, up2x, ACT_NONE, precision)
+        d, Ho, Wo, dkey = _desc(xshape, w4.shape, stride, pad, up2x, ACT_NONE, precision)
         st = _stream()
         dev = dy.device
         need_dx = ctx.needs_input_grad[0]
@@ -214,7 +247,7 @@ class Conv2dFn(torch.autograd.Function):
             # backward of the epilogue activation fused into the plane split: dz = dy * act'(y) never exists in fp32
             Cc = dy.shape[-1]
             rows = dy.numel() // Cc
-            dyp = torch.empty((_lib.lib().mog_planes_bytes(rows, Cc, precision) + 3) // 4, device=dev, dtype=torch.float32)
+            dyp = torch.empty((_planes_bytes(rows, Cc, precision) + 3) // 4, device=dev, dtype=torch.float32)
             call("mog_split_planes_act", dy.data_ptr(), y.data_ptr(), act, rows, Cc, precision, dyp.data_ptr(), st)
             dy = None
         elif act != ACT_NONE:
@@ -226,14 +259,14 @@ class Conv2dFn(torch.autograd.Function):
         dx = dw = db = None
         if need_dx:
             dx = torch.empty(xshape, device=dev, dtype=torch.float32)
-            ws, nws = _workspace(d, 1, dev)
-            call("mog_conv2d_dgrad", C.byref(d), _ptr(dy), _ptr(dyp), _packed(weight, "dgrad", d).data_ptr(),
+            ws, nws = _workspace(d, 1, dev, dkey)
+            call("mog_conv2d_dgrad", C.byref(d), _ptr(dy), _ptr(dyp), _packed(weight, "dgrad", d, dkey).data_ptr(),
                  dx.data_ptr(), _ptr(ws), nws, st)
         if need_dw:
             dw = torch.empty(w4.shape, device=dev, dtype=torch.float32)
             if ctx.has_bias:
                 db = torch.empty(d.Cout, device=dev, dtype=torch.float32)
-            ws, nws = _workspace(d, 2, dev)
+            ws, nws = _workspace(d, 2, dev, dkey)
             call("mog_conv2d_wgrad", C.byref(d), _ptr(x), _ptr(xp), _ptr(dy), _ptr(dyp), dw.data_ptr(), _ptr(db),
                  _ptr(ws), nws, st)
             dw = dw.reshape(weight.shape)
