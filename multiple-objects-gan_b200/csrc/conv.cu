@@ -256,7 +256,11 @@ static size_t tc_bytes(const Problem& q, int passes) {
   return tc_packed_bytes(q.g.nth * q.g.ntw, tap_pitch(q), q.g.Cd, passes);
 }
 static size_t split_bytes(const Problem& q, int passes) {
-  if (halo_shape_eligible(q.g)) return 0;
+  if (halo_shape_eligible(q.g)) {
+    IGemmParams g = q.g;
+    g.Cs = p8(q.CsReal);
+    return halo_workspace_bytes(&g, 1, passes);     // (small-grid form: split-K partials)
+  }
   return tc_igemm_workspace_bytes(q.g.M, q.g.nth * q.g.ntw, p8(q.CsReal), q.g.Cd, passes);
 }
 
@@ -317,7 +321,7 @@ static int run_tc_problems(Problem* probs, int n, const float* src_f32, const vo
       gs[i] = probs[i].g;
     }
     gs[0].dst = dst; gs[0].bias = bias; gs[0].act = probs[n - 1].g.act; gs[0].accum_dst = 0;
-    return launch_igemm_halo(gs, n, blocks, passes, st);
+    return launch_igemm_halo(gs, n, blocks, passes, ws, ws_bytes, st);
   }
   for (int i = 0; i < n; ++i) {
     Problem& q = probs[i];
@@ -328,7 +332,7 @@ static int run_tc_problems(Problem* probs, int n, const float* src_f32, const vo
     if (halo && !planes) return fail(MOG_ERR_BAD_ARG, "%s: this shape runs on the halo kernel and needs pre-split planes", who);
     int rc = attach_source(&q, src_f32, planes, N, who);
     if (rc) return rc;
-    rc = halo ? launch_igemm_halo(&q.g, 1, &blocks[i], passes, st) : launch_igemm_tc(q.g, blocks[i], passes, ws, ws_bytes, st);
+    rc = halo ? launch_igemm_halo(&q.g, 1, &blocks[i], passes, ws, ws_bytes, st) : launch_igemm_tc(q.g, blocks[i], passes, ws, ws_bytes, st);
     if (rc) return rc;
   }
   return MOG_OK;
@@ -439,6 +443,13 @@ extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   size_t mx = 0;
   for (int i = 0; i < n; ++i) {
     size_t b = split_bytes(probs[i], passes_of(d));
+    if (b > mx) mx = b;
+  }
+  if (mergeable(probs, n)) {      // parity views merged into one launch: its own split-K plan
+    IGemmParams gs[4];
+    for (int i = 0; i < n; ++i) { gs[i] = probs[i].g; gs[i].Cs = p8(probs[i].CsReal); }
+    gs[0].accum_dst = 0;
+    size_t b = halo_workspace_bytes(gs, n, passes_of(d));
     if (b > mx) mx = b;
   }
   return dgrad_up_bytes(d, hires) + mx;

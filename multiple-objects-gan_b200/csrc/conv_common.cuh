@@ -53,7 +53,10 @@ int launch_patch_dgrad(const MogConvDesc& d, const float* dy, const void* packed
 // halo-tile TMA persistent kernel (conv_halo.cu)
 bool halo_shape_eligible(const IGemmParams& g);
 int halo_tap_pitch(int Cs);
-int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, int passes, cudaStream_t st);
+int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, int passes, void* workspace, size_t ws_bytes,
+                      cudaStream_t st);
+size_t halo_workspace_bytes(const IGemmParams* gs, int n, int passes);
+int launch_splitk_reduce(const float* partial, const IGemmParams& g, int splits, cudaStream_t st);
 int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
                   const int (*taps)[4], int pitch, int passes, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);

@@ -60,7 +60,10 @@ struct HaloParams {
   int ngroups, nchunk, pitch;
   int HH;                          // rows of an A box
   int subA;                        // bytes of one A sub-tile box (1024-aligned)
-  int tiles_w, tiles_h;
+  int tw, th, tn;                  // sub-tile geometry: tw x th pixels of tn images = 128 GEMM rows
+  int tiles_w, tiles_h, tiles_n;
+  int ksplit, kper, niter;         // split-K: niter = ngroups * nchunk (group, chunk) iterations, kper per split
+  int split_store;                 // epilogue stores raw fp32 partials [ksplit][N][Hr][Wr][Cd] (5-D map), reduced by splitk_reduce
   long long nsub, npairs, total_tiles;
   int n_ntiles, BN, nbuf;
   int passes, stagesA, stagesB, tmem_cols;
@@ -74,7 +77,8 @@ struct HaloParams {
 struct HaloMaps {
   CUtensorMap a[HALO_MAXPROBS][2];   // [problem / view][hi, lo]
   CUtensorMap b[HALO_MAXPROBS][2];
-  CUtensorMap d;                     // fp32 destination pixel grid of this problem (a strided view for sub-pixel phases)
+  CUtensorMap d;                     // fp32 destination pixel grid of this problem (a strided view for sub-pixel phases), or the
+                                     // 5-D split-K partial buffer
 };
 
 __device__ __forceinline__ void halo_tma_4d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -95,6 +99,11 @@ __device__ __forceinline__ void halo_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void halo_tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1),
                "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void halo_tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(tm), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -135,13 +144,21 @@ __device__ __forceinline__ void halo_epi_slab16(const uint32_t (&acc)[16], const
 // hi word of a K-major SWIZZLE_64B descriptor: SBO = 512 bytes (8 rows of 64 bytes), version 1, layout 4
 __device__ __forceinline__ uint32_t desc_hi_sw64() { return (512u >> 4) | (1u << 14) | (4u << 29); }
 
+// sub-tile index -> first image / pixel of the sub-tile (tn images x th x tw pixels)
 __device__ __forceinline__ void halo_decode(const HaloParams& p, long long sub, int* n, int* h0, int* w0) {
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int tw_ = (int)(sub % p.tiles_w);
   const int th_ = (int)((sub / p.tiles_w) % p.tiles_h);
-  *n = (int)(sub / tiles_per_img);     // >= N for the padding sub-tile of an odd count: TMA zero-fills, nothing is stored
-  *h0 = th_ * HT_H;
-  *w0 = tw_ * HT_W;
+  *n = (int)(sub / tiles_per_img) * p.tn;   // >= N for the padding sub-tile of an odd count: TMA zero-fills, nothing is stored
+  *h0 = th_ * p.th;
+  *w0 = tw_ * p.tw;
+}
+// work item -> (sub-tile pair, N tile, K split)
+__device__ __forceinline__ void halo_item(const HaloParams& p, long long tile, long long* pair, int* ntile, int* ks) {
+  *ks = (int)(tile % p.ksplit);
+  const long long q = tile / p.ksplit;
+  *ntile = (int)(q % p.n_ntiles);
+  *pair = q / p.n_ntiles;
 }
 
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
@@ -182,15 +199,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     if (lane == 0) {
       int sa = 0;
       uint32_t pha = 0;
-      const uint32_t bytesA = (uint32_t)(nplanes * 2 * (HCH * 2 * HT_W * p.HH));
+      const uint32_t bytesA = (uint32_t)(nplanes * 2 * (HCH * 2 * p.tw * p.HH * p.tn));
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const long long pair = tile / p.n_ntiles;
+        long long pair;
+        int ntile_, ks;
+        halo_item(p, tile, &pair, &ntile_, &ks);
         int n[2], h0[2], w0[2];
         halo_decode(p, pair * 2, &n[0], &h0[0], &w0[0]);
         halo_decode(p, pair * 2 + 1, &n[1], &h0[1], &w0[1]);
-        for (int gi = 0; gi < p.ngroups; ++gi) {
+        const int it_end = min((ks + 1) * p.kper, p.niter);
+        for (int it = ks * p.kper; it < it_end; ++it) {
+          const int gi = it / p.nchunk, c = it - gi * p.nchunk;
           const HaloGroup& g = p.grp[gi];
-          for (int c = 0; c < p.nchunk; ++c) {
+          {
             mbar_wait(&emptyA[sa], pha ^ 1u);
             const uint32_t stA = smem_u32(ringA + (size_t)sa * slotA);
             halo_expect_tx(&fullA[sa], bytesA);
@@ -210,10 +231,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       uint32_t phb = 0;
       const uint32_t bytesB = (uint32_t)slotB;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ntile = (int)(tile % p.n_ntiles);
-        for (int gi = 0; gi < p.ngroups; ++gi) {
+        long long pair;
+        int ntile, ks;
+        halo_item(p, tile, &pair, &ntile, &ks);
+        const int it_end = min((ks + 1) * p.kper, p.niter);
+        for (int it = ks * p.kper; it < it_end; ++it) {
+          const int gi = it / p.nchunk, c = it - gi * p.nchunk;
           const HaloGroup& g = p.grp[gi];
-          for (int c = 0; c < p.nchunk; ++c) {
+          {
             for (int a = 0; a < g.nth; ++a) {
               mbar_wait(&emptyB[sb], phb ^ 1u);
               const uint32_t stB = smem_u32(ringB + (size_t)sb * slotB);
@@ -239,16 +264,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)((as * 2 + sub) * p.BN);
       uint32_t first = 0u;                     // becomes 1 after the first k-step of the tile
-      for (int gi = 0; gi < p.ngroups; ++gi) {
-        const HaloGroup& g = p.grp[gi];
-        for (int c = 0; c < p.nchunk; ++c) {
+      const int ks = (int)(tile % p.ksplit);
+      const int it_end = min((ks + 1) * p.kper, p.niter);
+      for (int it = ks * p.kper; it < it_end; ++it) {
+        const HaloGroup& g = p.grp[it / p.nchunk];
+        {
           mbar_wait(&fullA[sa], pha);
           const uint32_t stA = smem_u32(ringA + (size_t)sa * slotA) + (uint32_t)(sub * p.subA);
           for (int a = 0; a < g.nth; ++a) {
             mbar_wait(&fullB[sb], phb);
             tcgen05_fence_after();
             const uint32_t stB = smem_u32(ringB + (size_t)sb * slotB);
-            const uint32_t sh = (uint32_t)g.shift[a] * (HT_W * HCH * 2);
+            const uint32_t sh = (uint32_t)g.shift[a] * (uint32_t)(p.tw * HCH * 2);
             const uint32_t ah = desc_lo(stA + sh, 16), al = desc_lo(stA + planeA + sh, 16);
             const uint32_t bh = desc_lo(stB, 16), bl = desc_lo(stB + planeB, 16);
 #pragma unroll
@@ -275,8 +302,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     // ===================== epilogue: warps 3-6 drain sub-tile 0, warps 7-10 sub-tile 1 ==============
     const int s = (warp - 3) >> 2;      // sub-tile of this warp
     const int q4 = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp id % 4)
-    const int r = q4 * 32 + lane;       // sub-tile row = pixel (r / 8, r % 8)
-    const int hl = r >> 3, wl = r & 7;
+    const int r = q4 * 32 + lane;       // sub-tile row = (image nl, pixel hl, wl) of the sub-tile, wl fastest
+    const int wl = r % p.tw, hl = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
     const bool vec = (p.Cd & 3) == 0;
     int as = 0;
     uint32_t aph = 0;
@@ -284,8 +311,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     const bool leader = ((warp - 3) & 3) == 0 && lane == 0;   // issues this group's TMA stores
     unsigned char* slabs = outbuf + (size_t)s * 2 * HALO_OUT_SLAB;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int ntile = (int)(tile % p.n_ntiles);
-      const long long pair = tile / p.n_ntiles;
+      long long pair;
+      int ntile, ks;
+      halo_item(p, tile, &pair, &ntile, &ks);
       const int n0c = ntile * p.BN;
       mbar_wait(&tfull[as], aph);
       tcgen05_fence_after();
@@ -312,7 +340,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA unit
                 named_bar_sync(1 + s, 128);
                 if (leader) {
-                  halo_tma_store_4d(&maps.d, smem_u32(slab), n0c + gg * 16, w0, h0, n);
+                  if (p.split_store) halo_tma_store_5d(&maps.d, smem_u32(slab), n0c + gg * 16, w0, h0, n, ks);
+                  else halo_tma_store_4d(&maps.d, smem_u32(slab), n0c + gg * 16, w0, h0, n);
                   bulk_commit();
                 }
                 ob ^= 1;
@@ -323,11 +352,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       } else {
         int n, h0, w0;
         halo_decode(p, pair * 2 + s, &n, &h0, &w0);
-        const int rh = h0 + hl, rw = w0 + wl;
-        const bool ok = n < p.N && rh < p.Hr && rw < p.Wr;
+        const int rh = h0 + hl, rw = w0 + wl, rn = n + nl;
+        const bool ok = rn < p.N && rh < p.Hr && rw < p.Wr;
         float* dptr = nullptr;
         if (ok) {
-          const size_t pix = ((size_t)n * p.Hd + (rh * p.dsh + p.doh)) * p.Wd + (rw * p.dsw + p.dow);
+          const size_t pix = ((size_t)rn * p.Hd + (rh * p.dsh + p.doh)) * p.Wd + (rw * p.dsw + p.dow);
           dptr = p.dst + pix * p.Cd + n0c;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((as * 2 + s) * p.BN);
@@ -388,83 +417,164 @@ static HaloEncodeFn halo_encode_fn() {
 // K pitch of one tap slot in the weights packed for this kernel
 int halo_tap_pitch(int Cs) { return ceil_div(Cs, HCH) * HCH; }
 
+// ---- sub-tile geometry -------------------------------------------------------------------------------------
+// Large pixel grids use 8 x 16 pixel sub-tiles of one image with halo boxes (row taps = shifted windows of one box per
+// filter column).  Small grids (the deep discriminator layers at 8 x 8 / 4 x 4, the 8 x 8 stage of the image encoder)
+// pack several images into one 128-row sub-tile and load one box per filter tap (no halo: the rows of different images
+// are not a uniform stride apart); their few output tiles are spread over the SMs by split-K.
+struct HaloGeom { int tw, th, tn, halo; };
+static HaloGeom halo_geom(const IGemmParams& g) {
+  if (g.Hr >= 12 && g.Wr >= HT_W) return {HT_W, HT_H, 1, 1};
+  if (g.Hr > 4 || g.Wr > 4) return {8, 8, 2, 0};
+  return {4, 4, 8, 0};
+}
+
 // shape-only test (the weight packing depends on it)
 bool halo_shape_eligible(const IGemmParams& g) {
   if (g.rs != 1 || g.up2x) return false;
   if (g.vstep > 1 && ((g.Hp % g.vstep) || (g.Wp % g.vstep))) return false;
-  if (g.nth < 1 || g.ntw < 1 || g.nth > 4 || g.ntw > HALO_MAXGROUPS) return false;
+  if (g.nth < 1 || g.ntw < 1) return false;
   if (g.Cd < 1) return false;
-  if (g.Hr < 12 || g.Wr < HT_W) return false;     // tiny grids: the 8 x 16 sub-tiles would be mostly padding
-  if (g.M < 32LL * 128) return false;             // small problems: the split-K kernel fills the machine better
-  int lo = g.off_h[0], hi = g.off_h[0];
-  for (int i = 1; i < g.nth; ++i) { lo = g.off_h[i] < lo ? g.off_h[i] : lo; hi = g.off_h[i] > hi ? g.off_h[i] : hi; }
-  if (hi - lo > 8) return false;
-  return halo_encode_fn() != nullptr;
+  if (halo_encode_fn() == nullptr) return false;
+  const HaloGeom ge = halo_geom(g);
+  if (ge.halo) {
+    if (g.nth > 4 || g.ntw > HALO_MAXGROUPS) return false;
+    if (g.M < 32LL * 128) return false;             // small problems on big grids: the split-K gather kernel fills the machine better
+    int lo = g.off_h[0], hi = g.off_h[0];
+    for (int i = 1; i < g.nth; ++i) { lo = g.off_h[i] < lo ? g.off_h[i] : lo; hi = g.off_h[i] > hi ? g.off_h[i] : hi; }
+    return hi - lo <= 8;
+  }
+  // small grids: one group per tap; split-K partials go through TMA stores (channel count multiple of 4, no accumulate chain)
+  if (g.nth * g.ntw > HALO_MAXGROUPS) return false;
+  if ((g.Cd & 3) || g.Cd < 64) return false;        // (narrow outputs: the gather kernel's N tile wastes less)
+  if (g.Hr > 8 || g.Wr > 8) return false;           // 9..11-row grids stay on the gather kernel
+  if (g.M < 256 || g.Cs < 64) return false;
+  return true;
 }
 
-// gs[0..n): problems that write the same destination pixels (n > 1: parity views accumulated in TMEM);
-// packed[i]: weight block of problem i (layout of tc_pack_pitch with pitch = halo_tap_pitch(Cs))
-int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, int passes, cudaStream_t st) {
-  HaloEncodeFn enc = halo_encode_fn();
-  if (!enc) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+// plan of one (possibly merged) launch: everything but the pointers
+static int halo_plan(const IGemmParams* gs, int n, int passes, HaloParams* out) {
   if (n < 1 || n > HALO_MAXPROBS) return fail(MOG_ERR_BAD_ARG, "conv (halo): %d problems", n);
   const IGemmParams& g0 = gs[0];
   const int nplanes = passes == 3 ? 2 : 1;
+  const HaloGeom ge = halo_geom(g0);
   HaloParams p{};
   int maxshift = 0, ng = 0;
   for (int i = 0; i < n; ++i) {
     const IGemmParams& g = gs[i];
-    if (!g.src_planes || (g.Cs % 8)) return fail(MOG_ERR_BAD_ARG, "conv (halo): needs pre-split planes with a channel pitch multiple of 8");
+    if (g.Cs % 8) return fail(MOG_ERR_BAD_ARG, "conv (halo): needs pre-split planes with a channel pitch multiple of 8");
     if (g.Cs != g0.Cs || g.Hr != g0.Hr || g.Wr != g0.Wr || g.N != g0.N || g.Cd != g0.Cd)
       return fail(MOG_ERR_BAD_ARG, "conv (halo): merged problems must share the output grid");
-    int hmin = g.off_h[0];
-    for (int a = 1; a < g.nth; ++a) hmin = g.off_h[a] < hmin ? g.off_h[a] : hmin;
-    for (int b = 0; b < g.ntw; ++b) {
-      if (ng == HALO_MAXGROUPS) return fail(MOG_ERR_UNSUPPORTED, "conv (halo): too many filter columns");
-      HaloGroup& q = p.grp[ng++];
-      q.prob = i; q.w_off = g.off_w[b]; q.h_org = hmin; q.nth = g.nth;
-      for (int a = 0; a < g.nth; ++a) {
-        q.shift[a] = g.off_h[a] - hmin;
-        q.slot[a] = a * g.ntw + b;
-        if (q.shift[a] > maxshift) maxshift = q.shift[a];
+    if (ge.halo) {
+      int hmin = g.off_h[0];
+      for (int a = 1; a < g.nth; ++a) hmin = g.off_h[a] < hmin ? g.off_h[a] : hmin;
+      for (int b = 0; b < g.ntw; ++b) {
+        if (ng == HALO_MAXGROUPS) return fail(MOG_ERR_UNSUPPORTED, "conv (halo): too many filter columns");
+        HaloGroup& q = p.grp[ng++];
+        q.prob = i; q.w_off = g.off_w[b]; q.h_org = hmin; q.nth = g.nth;
+        for (int a = 0; a < g.nth; ++a) {
+          q.shift[a] = g.off_h[a] - hmin;
+          q.slot[a] = a * g.ntw + b;
+          if (q.shift[a] > maxshift) maxshift = q.shift[a];
+        }
       }
+    } else {
+      for (int a = 0; a < g.nth; ++a)
+        for (int b = 0; b < g.ntw; ++b) {
+          if (ng == HALO_MAXGROUPS) return fail(MOG_ERR_UNSUPPORTED, "conv (halo): too many filter taps for the small-grid form");
+          HaloGroup& q = p.grp[ng++];
+          q.prob = i; q.w_off = g.off_w[b]; q.h_org = g.off_h[a]; q.nth = 1;
+          q.shift[0] = 0; q.slot[0] = a * g.ntw + b;
+        }
     }
   }
   p.ngroups = ng;
   p.nchunk = ceil_div(g0.Cs, HCH);
   p.pitch = p.nchunk * HCH;
-  p.HH = HT_H + maxshift;
-  p.subA = ceil_div(HT_W * p.HH * HCH * 2, 1024) * 1024;
-  p.tiles_w = ceil_div(g0.Wr, HT_W);
-  p.tiles_h = ceil_div(g0.Hr, HT_H);
-  p.nsub = (long long)g0.N * p.tiles_w * p.tiles_h;
+  p.niter = p.ngroups * p.nchunk;
+  p.tw = ge.tw; p.th = ge.th; p.tn = ge.tn;
+  p.HH = ge.th + maxshift;
+  p.subA = ceil_div(ge.tw * p.HH * ge.tn * HCH * 2, 1024) * 1024;
+  p.tiles_w = ceil_div(g0.Wr, ge.tw);
+  p.tiles_h = ceil_div(g0.Hr, ge.th);
+  p.tiles_n = ceil_div(g0.N, ge.tn);
+  p.nsub = (long long)p.tiles_n * p.tiles_w * p.tiles_h;
   p.npairs = (p.nsub + 1) / 2;
-  // N tile <= 128 columns so that two sub-tiles x two accumulator buffers fit the 512 TMEM columns: the epilogue
-  // (fp32 stores at ~16 B/clk/SM) must overlap the MMAs of the next tile; N = 192 is issued as 2 x 96
+  p.passes = passes;
+  p.tma_store = ((g0.Cd & 3) == 0 && !g0.accum_dst) ? 1 : 0;
+  // N tile: <= 128 columns on the big grids so that two sub-tiles x two accumulator buffers fit the 512 TMEM columns
+  // (the epilogue overlaps the MMAs of the next tile; N = 192 is issued as 2 x 96); the small-grid form takes up to 256
+  // columns (single-buffered: few tiles per CTA, and the weight chunk is then shared by 2 x 128 rows x 256 columns)
   {
     const int cpad = ceil_div(g0.Cd, 16) * 16;
-    const int tiles = ceil_div(cpad, 128);
+    const int tiles = ceil_div(cpad, ge.halo ? 128 : 256);
     p.BN = ceil_div(ceil_div(cpad, tiles), 16) * 16;
   }
   p.n_ntiles = ceil_div(g0.Cd, p.BN);
-  p.total_tiles = p.npairs * p.n_ntiles;
   p.nbuf = 4 * p.BN <= 512 ? 2 : 1;
-  p.passes = passes;
+  // split-K (small-grid form only): aim at two work items per SM, at least 4 (group, chunk) iterations per split
+  p.ksplit = 1;
+  if (!ge.halo && p.tma_store) {
+    const long long items = p.npairs * p.n_ntiles;
+    if (items < kNumSMs) {
+      long long want = (2 * kNumSMs) / items, maxs = p.niter / 4;
+      long long ks = want < maxs ? want : maxs;
+      if (ks > 32) ks = 32;
+      if (ks > 1) p.ksplit = (int)ks;
+    }
+  }
+  p.kper = ceil_div(p.niter, p.ksplit);
+  p.ksplit = ceil_div(p.niter, p.kper);
+  p.split_store = p.ksplit > 1 ? 1 : 0;
+  p.total_tiles = p.npairs * p.n_ntiles * p.ksplit;
   int cols = 32;
   while (cols < 2 * p.nbuf * p.BN) cols *= 2;
   p.tmem_cols = cols;
-  p.tma_store = ((g0.Cd & 3) == 0 && !g0.accum_dst) ? 1 : 0;
   const int slotA = nplanes * 2 * p.subA, slotB = nplanes * p.BN * HCH * 2;
   const int budget = 224 * 1024 - 1024 - (p.tma_store ? 4 * HALO_OUT_SLAB : 0);
-  int stagesA = 3;
+  int stagesA = ge.halo ? 3 : 2;     // (small-grid form: the weight ring is the one that must run deep)
   int stagesB = (budget - stagesA * slotA) / slotB;
   if (stagesB < 2) { stagesA = 2; stagesB = (budget - stagesA * slotA) / slotB; }
   if (stagesB < 2) return fail(MOG_ERR_UNSUPPORTED, "conv (halo): BN=%d does not fit the shared-memory rings", p.BN);
   if (stagesB > HALO_MAXRING) stagesB = HALO_MAXRING;
   p.stagesA = stagesA; p.stagesB = stagesB;
-  p.dst = g0.dst; p.bias = g0.bias; p.act = g0.act; p.accum_dst = g0.accum_dst;
   p.N = g0.N; p.Hr = g0.Hr; p.Wr = g0.Wr; p.Cd = g0.Cd; p.Hd = g0.Hd; p.Wd = g0.Wd;
   p.dsh = g0.dsh; p.doh = g0.doh; p.dsw = g0.dsw; p.dow = g0.dow;
+  *out = p;
+  return MOG_OK;
+}
+
+// split-K workspace of a launch (0 when it does not split); gs[i].Cs must be the channel pitch of the planes
+size_t halo_workspace_bytes(const IGemmParams* gs, int n, int passes) {
+  HaloParams p;
+  if (halo_plan(gs, n, passes, &p) != MOG_OK || p.ksplit <= 1) return 0;
+  return (size_t)p.ksplit * gs[0].M * gs[0].Cd * sizeof(float);
+}
+
+// gs[0..n): problems that write the same destination pixels (n > 1: parity views accumulated in TMEM);
+// packed[i]: weight block of problem i (layout of tc_pack_pitch with pitch = halo_tap_pitch(Cs))
+int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, int passes, void* workspace, size_t ws_bytes,
+                      cudaStream_t st) {
+  HaloEncodeFn enc = halo_encode_fn();
+  if (!enc) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  HaloParams p;
+  int rc = halo_plan(gs, n, passes, &p);
+  if (rc) return rc;
+  const IGemmParams& g0 = gs[0];
+  for (int i = 0; i < n; ++i)
+    if (!gs[i].src_planes) return fail(MOG_ERR_BAD_ARG, "conv (halo): needs pre-split planes");
+  const int nplanes = passes == 3 ? 2 : 1;
+  const int stagesA = p.stagesA, stagesB = p.stagesB;
+  const int slotA = nplanes * 2 * p.subA, slotB = nplanes * p.BN * HCH * 2;
+  float* partial = nullptr;
+  if (p.split_store) {
+    const size_t need = (size_t)p.ksplit * g0.M * g0.Cd * sizeof(float);
+    if (!workspace || ws_bytes < need) return fail(MOG_ERR_WORKSPACE, "conv (halo split-K): workspace %zu < %zu", ws_bytes, need);
+    partial = static_cast<float*>(workspace);
+    p.dst = partial; p.bias = nullptr; p.act = MOG_ACT_NONE; p.accum_dst = 0;   // raw partials; bias / activation in the reduce
+  } else {
+    p.dst = g0.dst; p.bias = g0.bias; p.act = g0.act; p.accum_dst = g0.accum_dst;
+  }
 
   HaloMaps maps;
   const int Npad = ceil_div(g0.Cd, tc_bn_for(g0.Cd)) * tc_bn_for(g0.Cd);   // rows of the packed weight planes (tc_pack_pitch)
@@ -480,7 +590,7 @@ int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, i
         const int vs = g.vstep > 0 ? g.vstep : 1, Hp = g.vstep > 0 ? g.Hp : g.Hs, Wp = g.vstep > 0 ? g.Wp : g.Ws;
         cuuint64_t dims[4] = {(cuuint64_t)g.Cs, (cuuint64_t)g.Ws, (cuuint64_t)g.Hs, (cuuint64_t)g.N};
         cuuint64_t strides[3] = {(cuuint64_t)vs * g.Cs * 2, (cuuint64_t)vs * Wp * g.Cs * 2, (cuuint64_t)Hp * Wp * g.Cs * 2};
-        cuuint32_t box[4] = {(cuuint32_t)HCH, (cuuint32_t)HT_W, (cuuint32_t)p.HH, 1u};
+        cuuint32_t box[4] = {(cuuint32_t)HCH, (cuuint32_t)p.tw, (cuuint32_t)p.HH, (cuuint32_t)p.tn};
         cuuint32_t es[4] = {1, 1, 1, 1};
         void* base = const_cast<__nv_bfloat16*>(xa + (size_t)src * g.src_plane_elems + ((size_t)g.voh * Wp + g.vow) * g.Cs);
         CUresult r = enc(&maps.a[i][pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -499,11 +609,21 @@ int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, i
       }
     }
   }
-  if (p.tma_store) {
+  if (p.split_store) {
+    // split-K partials [ksplit][N][Hr][Wr][Cd] fp32 (= [ksplit][M][Cd], the layout splitk_reduce reads); images beyond N clip
+    cuuint64_t dims[5] = {(cuuint64_t)g0.Cd, (cuuint64_t)g0.Wr, (cuuint64_t)g0.Hr, (cuuint64_t)g0.N, (cuuint64_t)p.ksplit};
+    cuuint64_t strides[4] = {(cuuint64_t)g0.Cd * 4, (cuuint64_t)g0.Wr * g0.Cd * 4, (cuuint64_t)g0.Hr * g0.Wr * g0.Cd * 4,
+                             (cuuint64_t)g0.M * g0.Cd * 4};
+    cuuint32_t box[5] = {16u, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, 1u};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&maps.d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, partial, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled(halo split-K partials) failed: %d", (int)r);
+  } else if (p.tma_store) {
     // destination pixel grid of this problem: pixel (rh, rw) -> physical (rh*dsh + doh, rw*dsw + dow) of [N][Hd][Wd][Cd] fp32
     cuuint64_t dims[4] = {(cuuint64_t)g0.Cd, (cuuint64_t)g0.Wr, (cuuint64_t)g0.Hr, (cuuint64_t)g0.N};
     cuuint64_t strides[3] = {(cuuint64_t)g0.dsw * g0.Cd * 4, (cuuint64_t)g0.dsh * g0.Wd * g0.Cd * 4, (cuuint64_t)g0.Hd * g0.Wd * g0.Cd * 4};
-    cuuint32_t box[4] = {16u, (cuuint32_t)HT_W, (cuuint32_t)HT_H, 1u};
+    cuuint32_t box[4] = {16u, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = g0.dst + ((size_t)g0.doh * g0.Wd + g0.dow) * g0.Cd;
     CUresult r = enc(&maps.d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -522,7 +642,10 @@ int launch_igemm_halo(const IGemmParams* gs, int n, const void* const* packed, i
   }
   const long long grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   conv_halo_kernel<<<(unsigned)grid, HALO_THREADS, smem, st>>>(maps, p);
-  return check_launch("conv_halo_kernel");
+  rc = check_launch("conv_halo_kernel");
+  if (rc || !p.split_store) return rc;
+  IGemmParams gr = g0;          // destination / bias / activation of the (merged) problem
+  return launch_splitk_reduce(partial, gr, p.ksplit, st);
 }
 
 }  // namespace mog

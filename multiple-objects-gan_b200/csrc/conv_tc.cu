@@ -758,8 +758,13 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* 
   }
   int rc = check_launch("conv_tc_kernel");
   if (rc || splits == 1) return rc;
+  return launch_splitk_reduce(p.partial, g, splits, st);
+}
+
+// dst[pix(m), n] = act(sum_z partial[z][m][n] + bias[n]) (fixed summation order)
+int launch_splitk_reduce(const float* partial, const IGemmParams& g, int splits, cudaStream_t st) {
   const size_t total = (size_t)g.M * g.Cd;
-  splitk_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(p.partial, g, splits);
+  splitk_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(partial, g, splits);
   return check_launch("splitk_reduce_kernel");
 }
 

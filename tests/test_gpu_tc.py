@@ -54,6 +54,14 @@ TC_CASES = [
     (1, 32, 32, 64, 64, 4, 2, 1, False, False, 0),    # stride 2: x through its 4 parity views, 2 x 2 taps each
     (2, 12, 20, 48, 3, 3, 1, 1, False, False, 0),     # Cout=3: operand roles swapped (x on M, dy on N)
     (3, 20, 12, 24, 16, 1, 1, 0, False, False, 0),    # 1x1 conv: single tap, single group
+    # small pixel grids on the halo kernel (several images per 128-row sub-tile, one box per tap, split-K partials by TMA)
+    (32, 8, 8, 128, 192, 4, 2, 1, False, False, 0),   # 8 -> 4: 4 parity views merged, (4,4,8) sub-tiles, M = 512
+    (31, 8, 8, 96, 128, 4, 2, 1, False, False, 2),    # N = 31 (wrong-pair batch): ragged last sub-tile, LeakyReLU in the reduce
+    (32, 4, 4, 160, 96, 3, 1, 1, False, True, 0),     # 3x3 on 4x4 (jointConv-like), bias applied by the reduce
+    (8, 16, 16, 64, 128, 4, 2, 1, False, False, 0),   # 16 -> 8: (8,8,2) sub-tiles
+    (6, 8, 8, 192, 320, 1, 1, 0, False, False, 1),    # 1x1 on 8x8 (Inception 8x8 stage), ReLU, two N tiles of 160
+    (5, 7, 7, 64, 64, 3, 1, 1, False, False, 0),      # 7x7 grid: sub-tile rows / columns beyond the image clip
+    (40, 4, 4, 64, 64, 4, 2, 1, False, False, 0),     # 4 -> 2 grid
 ]
 
 
@@ -61,7 +69,9 @@ def _torch_conv(x, w, b, stride, pad, up2x, act):
     if up2x:
         x = F.interpolate(x, scale_factor=2, mode="nearest")
     y = F.conv2d(x, w, b, stride, pad)
-    if act == 2:
+    if act == 1:
+        y = F.relu(y)
+    elif act == 2:
         y = F.leaky_relu(y, 0.2)
     elif act == 4:
         y = torch.tanh(y)
