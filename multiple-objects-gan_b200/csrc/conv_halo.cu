@@ -31,6 +31,8 @@
 //     {16 ch, 8 w, 16 h} into the (strided, for sub-pixel phases) NHWC destination; ragged edges, channel
 //     tails and padding sub-tiles are clipped by the TMA unit.
 //   * MOG_PREC_BF16X3: three MMAs per k-step (hi*hi, lo*hi, hi*lo) on the hi/lo planes.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -512,12 +514,20 @@ static int halo_plan(const IGemmParams* gs, int n, int passes, HaloParams* out) 
   }
   p.n_ntiles = ceil_div(g0.Cd, p.BN);
   p.nbuf = 4 * p.BN <= 512 ? 2 : 1;
-  // split-K (small-grid form only): aim at two work items per SM, at least 4 (group, chunk) iterations per split
+  // split-K (small-grid form only): aim at one work item per SM, at least 4 (group, chunk) iterations per split
   p.ksplit = 1;
   if (!ge.halo && p.tma_store) {
     const long long items = p.npairs * p.n_ntiles;
     if (items < kNumSMs) {
-      long long want = (2 * kNumSMs) / items, maxs = p.niter / 4;
+      static int per_sm = 0;
+      if (!per_sm) {
+        // tuning knob: work items per SM the split aims at.  Measured on the full step: 1 -> 72.8 ms, 2 -> 77.8 ms (the
+        // fp32 partials of a second wave cost more than the idle SMs of a single one)
+        const char* e = getenv("MOG_HALO_SPLIT_WAVES");
+        per_sm = e ? atoi(e) : 1;
+        if (per_sm < 1 || per_sm > 4) per_sm = 1;
+      }
+      long long want = ((long long)per_sm * kNumSMs) / items, maxs = p.niter / 4;
       long long ks = want < maxs ? want : maxs;
       if (ks > 32) ks = 32;
       if (ks > 1) p.ksplit = (int)ks;

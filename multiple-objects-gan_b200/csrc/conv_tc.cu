@@ -369,22 +369,48 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 }
 
 // split-K reduce: dst[pix(m), n] = act(sum_z partial[z][m][n] + bias[n])
+// V = 4: four consecutive channels per thread with 128-bit accesses (Cd % 4 == 0); the split loop is unrolled by 4 so
+// that four partial loads are in flight (fixed summation order: z ascending)
+template <int V>
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, const IGemmParams g, int splits) {
   const size_t total = (size_t)g.M * g.Cd;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (idx >= total) return;
   const int n = (int)(idx % g.Cd);
   const long long m = (long long)(idx / g.Cd);
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + idx];
-  if (g.bias) s += __ldg(g.bias + n);
+  float s[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s[j] = 0.f;
+  if (V == 4) {
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(partial + (size_t)(z + u) * total + idx));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s[0] += v[u].x; s[1 % V] += v[u].y; s[2 % V] += v[u].z; s[3 % V] += v[u].w; }
+    }
+    for (; z < splits; ++z) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)z * total + idx));
+      s[0] += v.x; s[1 % V] += v.y; s[2 % V] += v.z; s[3 % V] += v.w;
+    }
+  } else {
+    for (int z = 0; z < splits; ++z) s[0] += partial[(size_t)z * total + idx];
+  }
   int rw = (int)(m % g.Wr);
   long long q = m / g.Wr;
   int rh = (int)(q % g.Hr);
   int rn = (int)(q / g.Hr);
   size_t pix = ((size_t)rn * g.Hd + (rh * g.dsh + g.doh)) * g.Wd + (rw * g.dsw + g.dow);
-  if (g.accum_dst) s += g.dst[pix * g.Cd + n];
-  g.dst[pix * g.Cd + n] = epi_act(s, g.act);
+  float* dp = g.dst + pix * g.Cd + n;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    if (g.bias) s[j] += __ldg(g.bias + n + j);
+    if (g.accum_dst) s[j] += dp[j];
+    s[j] = epi_act(s[j], g.act);
+  }
+  if (V == 4) *reinterpret_cast<float4*>(dp) = make_float4(s[0], s[1 % V], s[2 % V], s[3 % V]);
+  else dp[0] = s[0];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -764,7 +790,10 @@ int launch_igemm_tc(const IGemmParams& g, const void* packed, int passes, void* 
 // dst[pix(m), n] = act(sum_z partial[z][m][n] + bias[n]) (fixed summation order)
 int launch_splitk_reduce(const float* partial, const IGemmParams& g, int splits, cudaStream_t st) {
   const size_t total = (size_t)g.M * g.Cd;
-  splitk_reduce_kernel<<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(partial, g, splits);
+  if ((g.Cd & 3) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.dst) & 15) == 0)
+    splitk_reduce_kernel<4><<<(unsigned)ceil_div_ll((long long)(total / 4), 256), 256, 0, st>>>(partial, g, splits);
+  else
+    splitk_reduce_kernel<1><<<(unsigned)ceil_div_ll((long long)total, 256), 256, 0, st>>>(partial, g, splits);
   return check_launch("splitk_reduce_kernel");
 }
 
