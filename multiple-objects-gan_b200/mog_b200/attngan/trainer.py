@@ -177,7 +177,11 @@ class condGANTrainer(object):
 
         # (3) update the discriminators
         errD_total = 0
-        for i, netD in enumerate(netsD):
+        # multi-GPU: the discriminators are independent, so the one with the largest gradient bucket (D_NET256, 643 MB)
+        # goes first and its all-reduce travels while the smaller ones compute; single GPU keeps the reference's order
+        order = sorted(range(len(netsD)), key=lambda j: -st["bucketDs"][j].flat.numel()) if multi else range(len(netsD))
+        for i in order:
+            netD = netsD[i]
             netD.zero_grad(set_to_none=True)
             if i == 0:
                 errD = discriminator_loss(netD, imgs[i], fake_imgs[i], sent_emb, st["real_labels"],
