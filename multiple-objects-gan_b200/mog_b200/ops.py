@@ -94,7 +94,9 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc, dkey=None) -> torc
     """Pack an OIHW parameter into the GEMM B operand of the kernel selected by ``d`` (fp32 matrix or
     bf16 hi/lo planes per stride phase); cached on the tensor per (version, conv geometry)."""
     cache = getattr(weight, "_mog_pack", None)
-    ver = weight._version
+    # torch's version counter catches torch-side in-place updates; `_mog_ver` is bumped by mog_b200.optim.Adam, whose fused
+    # kernel writes the parameter through its raw pointer (invisible to the version counter)
+    ver = (weight._version, getattr(weight, "_mog_ver", 0))
     if cache is None or cache.get("ver") != ver or cache.get("ptr") != weight.data_ptr():
         cache = {"ver": ver, "ptr": weight.data_ptr()}
         try:

@@ -68,6 +68,8 @@ class Adam(torch.optim.Optimizer):
                 vs.append(state["exp_avg_sq"].data_ptr()); es.append(e.data_ptr() if e is not None else None)
                 ns.append(p.numel())
                 state["_keep"] = g   # the gradient must outlive the asynchronous launch
+                # the kernel writes p through its raw pointer: tell the packed-weight cache (ops._packed) that p changed
+                p._mog_ver = getattr(p, "_mog_ver", 0) + 1
             if ps:
                 self._launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale)
         for group in self.param_groups:

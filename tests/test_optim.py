@@ -70,3 +70,29 @@ def test_adam_refuses_cpu_params():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
         Adam([p], lr=1e-3).step()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_adam_update_reaches_the_next_forward(prec):
+    """The fused kernel writes parameters through raw pointers (torch's version counter does not move): the packed-weight
+    cache of the convolutions must still notice, i.e. the forward after step() uses the NEW weights."""
+    import torch.nn.functional as F
+    from mog_b200 import ops
+    from mog_b200.optim import Adam
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(11)
+    w = (torch.randn(32, 16, 3, 3, device="cuda") * 0.1).requires_grad_(True)
+    x = torch.randn(2, 12, 12, 16, device="cuda")
+    opt = Adam([w], lr=0.05, betas=(0.5, 0.999))
+    P = ops.PREC_NAMES[prec]
+    for it in range(3):
+        y = ops.conv2d(x, w, None, 1, 1, False, ops.ACT_NONE, P)
+        ref = F.conv2d(x.permute(0, 3, 1, 2), w.detach(), None, 1, 1).permute(0, 2, 3, 1)
+        err = float((y.detach() - ref).norm() / ref.norm())
+        assert err < 1e-4, (it, err)          # a stale pack would be off by O(lr) = percent
+        opt.zero_grad(set_to_none=True)
+        y.square().mean().backward()
+        w_before = w.detach().clone()
+        opt.step()
+        assert float((w.detach() - w_before).abs().max()) > 1e-3
