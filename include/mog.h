@@ -79,6 +79,24 @@ size_t mog_packed_weight_bytes(const MogConvDesc* d, int which);
 int mog_packed_weight_layout(const MogConvDesc* d, int which);
 int mog_pack_weight(const MogConvDesc* d, int which, const float* w_oihw, void* w_packed, void* stream);
 
+/* Multi-tensor repacking: after an optimiser step every trainable weight needs its packed operands again
+ * (~350 small launches per step when done one problem at a time).  mog_pack_plan describes the launches
+ * mog_pack_weight(d, which, w, out) would make as table entries; the caller concatenates the entries of all weights of a
+ * network, fills `block_start` (exclusive prefix sum of nxb * nyb), keeps the table in device memory and refreshes all
+ * packs with ONE mog_pack_multi launch per step.  tcgen05 precisions, filters of at most 16 taps. */
+typedef struct MogPackEntry {
+  const float* w;          /* OIHW fp32 source                                                   */
+  void* hi;                /* destination planes of this problem                                  */
+  void* lo;                /* NULL in single-pass mode                                            */
+  int32_t Cout, Cin, KHW, transpose, ntaps, Nreal, Npad, Cs, CsReal, K, Kpad;
+  int32_t nxb, nyb;        /* tile grid of the entry: ceil(Cs / 32) x ceil(Npad / 16) blocks      */
+  int32_t block_start;     /* first block of the entry within the launch (filled by the caller)   */
+  int32_t taps[16][4];     /* filter taps summed into each local tap, -1 = unused                 */
+} MogPackEntry;
+/* returns the number of entries written (<= capacity), or a negative MOG_ERR_* (MOG_ERR_UNSUPPORTED: use mog_pack_weight) */
+int mog_pack_plan(const MogConvDesc* d, int which, const float* w, void* out, MogPackEntry* entries, int capacity);
+int mog_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, void* stream);
+
 /* ---- convolution ----------------------------------------------------------------------- */
 /* Operand formats.  MOG_PREC_FP32: fp32 NHWC tensors.  tcgen05 precisions: the gathered operands
  * (x for forward/wgrad, dy for dgrad/wgrad) are preferably passed as pre-split bf16 *planes*

@@ -426,6 +426,30 @@ extern "C" int mog_pack_weight(const MogConvDesc* d, int which, const float* w, 
   return MOG_OK;
 }
 
+extern "C" int mog_pack_plan(const MogConvDesc* d, int which, const float* w, void* out, MogPackEntry* entries, int capacity) {
+  int rc = validate(d, "mog_pack_plan");
+  if (rc) return rc;
+  MOG_REQUIRE(w && out && entries && capacity > 0 && (which == 0 || which == 1), "mog_pack_plan: bad argument");
+  if (!use_tc(d)) return fail(MOG_ERR_UNSUPPORTED, "mog_pack_plan: tcgen05 precisions only");
+  Problem probs[16];
+  int hires;
+  const int n = build(d, which, probs, &hires);
+  if (n > capacity) return fail(MOG_ERR_BAD_ARG, "mog_pack_plan: %d entries > capacity %d", n, capacity);
+  unsigned char* o = static_cast<unsigned char*>(out);
+  for (int i = 0; i < n; ++i) {
+    const Problem& q = probs[i];
+    rc = tc_pack_entry(w, o, d->Cout, d->Cin, d->KH, d->KW, q.transpose, q.g.nth * q.g.ntw, q.taps, tap_pitch(q), passes_of(d), &entries[i]);
+    if (rc) return fail(rc, "mog_pack_plan: filter %dx%d / %d taps not supported by the multi-tensor form", d->KH, d->KW, q.g.nth * q.g.ntw);
+    o += tc_bytes(q, passes_of(d));
+  }
+  return n;
+}
+
+extern "C" int mog_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, void* stream) {
+  MOG_REQUIRE(entries_dev && n > 0 && total_blocks > 0, "mog_pack_multi: bad argument");
+  return launch_pack_multi(entries_dev, n, total_blocks, as_stream(stream));
+}
+
 extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {
   if (validate(d, "mog_conv_workspace_bytes")) return 0;
   int Ho, Wo;

@@ -503,6 +503,93 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
   }
 }
 
+// Multi-tensor form: one launch repacks every (weight, problem) entry of a device-resident table (mog_pack_multi).
+// Same tiling as pack_tc_kernel<0, 16, 17>; block -> entry by binary search over the entries' first blocks.
+template <int KHW_T>
+__device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, int by, float* tile) {
+  const int n0 = by * PK_N, c0 = bx * PK_C;
+  const int KHW = KHW_T ? KHW_T : a.KHW;      // compile-time tap count: no integer division in the copy loops
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (!a.transpose) {
+    for (int nl = ty; nl < PK_N; nl += 8) {
+      const int nn = n0 + nl;
+      const float* src = a.w + ((size_t)nn * a.Cin + c0) * KHW;
+      for (int j = tx; j < PK_C * KHW; j += 32) {
+        const int cl = j / KHW, t = j - cl * KHW;
+        float v = 0.f;
+        if (nn < a.Nreal && c0 + cl < a.CsReal) v = __ldg(src + j);
+        tile[(nl * PK_C + cl) * 17 + t] = v;
+      }
+    }
+  } else {
+    for (int cl = ty; cl < PK_C; cl += 8) {
+      const int c = c0 + cl;
+      const float* src = a.w + ((size_t)c * a.Cin + n0) * KHW;
+      for (int j = tx; j < PK_N * KHW; j += 32) {
+        const int nl = j / KHW, t = j - nl * KHW;
+        float v = 0.f;
+        if (n0 + nl < a.Nreal && c < a.CsReal) v = __ldg(src + j);
+        tile[(nl * PK_C + cl) * 17 + t] = v;
+      }
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* phi = static_cast<__nv_bfloat16*>(a.hi);
+  __nv_bfloat16* plo = static_cast<__nv_bfloat16*>(a.lo);
+  const int c = c0 + tx;
+  if (c < a.Cs) {
+    for (int nl = ty; nl < PK_N; nl += 8) {
+      const int nn = n0 + nl;
+      if (nn >= a.Npad) break;
+      for (int tl = 0; tl < a.ntaps; ++tl) {
+        float v = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int tp = a.taps[tl][u];
+          if (tp >= 0) v += tile[(nl * PK_C + tx) * 17 + tp];
+        }
+        const size_t o = (size_t)nn * a.Kpad + (size_t)tl * a.Cs + c;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        phi[o] = h;
+        if (plo) plo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+  if (bx == 0) {
+    for (int nl = ty; nl < PK_N; nl += 8) {
+      const int nn = n0 + nl;
+      if (nn >= a.Npad) break;
+      for (int k = a.K + tx; k < a.Kpad; k += 32) {
+        phi[(size_t)nn * a.Kpad + k] = __float2bfloat16_rn(0.f);
+        if (plo) plo[(size_t)nn * a.Kpad + k] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const MogPackEntry* __restrict__ T, int n) {
+  __shared__ float tile[PK_N * PK_C * 17];
+  __shared__ MogPackEntry ent;
+  int lo = 0, hi = n - 1;
+  const int b = (int)blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&T[mid].block_start) <= b) lo = mid; else hi = mid - 1;
+  }
+  // the entry (336 bytes) once into shared memory: the taps table and the geometry are read many times below
+  for (int i = threadIdx.x; i < (int)(sizeof(MogPackEntry) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(&ent)[i] = __ldg(reinterpret_cast<const int*>(&T[lo]) + i);
+  __syncthreads();
+  const int local = b - ent.block_start;
+  const int bx = local % ent.nxb, by = local / ent.nxb;
+  switch (ent.KHW) {
+    case 1: pack_multi_body<1>(ent, bx, by, tile); break;
+    case 9: pack_multi_body<9>(ent, bx, by, tile); break;
+    case 16: pack_multi_body<16>(ent, bx, by, tile); break;
+    default: pack_multi_body<0>(ent, bx, by, tile); break;
+  }
+}
+
 // Data gradient of a non-overlapping strided conv (stride == KH == KW, pad == 0, e.g. the 4x4/s4 logit heads,
 // model.py:627,640) with a handful of output channels: every dx pixel sees exactly one tap,
 //   dx[n, ho*s + kh, wo*s + kw, ci] = sum_co dy[n, ho, wo, co] * w[co, ci, kh, kw]
@@ -683,6 +770,29 @@ int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int
     default: pack_tc_kernel<0><<<grid, 256, 0, st>>>(a); break;
   }
   return check_launch("pack_tc_kernel");
+}
+
+// table entry of the launch tc_pack_pitch would make (multi-tensor repacking)
+int tc_pack_entry(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
+                  const int (*taps)[4], int pitch, int passes, MogPackEntry* e) {
+  if (KH * KW > 16 || ntaps > 16) return MOG_ERR_UNSUPPORTED;
+  const int CsReal = transpose ? Cout : Cin, Cd = transpose ? Cin : Cout;
+  TcWeightLayout L = tc_weight_layout(ntaps, pitch, Cd, passes);
+  e->w = w_oihw;
+  e->hi = out;
+  e->lo = L.planes == 2 ? static_cast<void*>(static_cast<__nv_bfloat16*>(out) + L.plane_elems) : nullptr;
+  e->Cout = Cout; e->Cin = Cin; e->KHW = KH * KW; e->transpose = transpose; e->ntaps = ntaps;
+  e->Nreal = Cd; e->Npad = L.Npad; e->Cs = pitch; e->CsReal = CsReal; e->K = L.K; e->Kpad = L.Kpad;
+  e->nxb = ceil_div(pitch, PK_C); e->nyb = ceil_div(L.Npad, PK_N);
+  e->block_start = 0;
+  for (int i = 0; i < 16; ++i)
+    for (int u = 0; u < 4; ++u) e->taps[i][u] = i < ntaps ? taps[i][u] : -1;
+  return MOG_OK;
+}
+
+int launch_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, cudaStream_t st) {
+  tc::pack_multi_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(entries_dev, n);
+  return check_launch("pack_multi_kernel");
 }
 
 // split-K factor for one gather-GEMM problem

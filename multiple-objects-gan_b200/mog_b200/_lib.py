@@ -22,6 +22,12 @@ class MogConvDesc(C.Structure):
                 ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "up2x", "act", "precision", "pad_w1")]
 
 
+class MogPackEntry(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p)] + \
+               [(n, C.c_int32) for n in ("Cout", "Cin", "KHW", "transpose", "ntaps", "Nreal", "Npad", "Cs", "CsReal", "K", "Kpad",
+                                         "nxb", "nyb", "block_start")] + [("taps", (C.c_int32 * 4) * 16)]
+
+
 _p = C.c_void_p
 _i = C.c_int
 _f = C.c_float
@@ -38,6 +44,8 @@ SIGNATURES = {
     "mog_packed_weight_bytes": (_sz, [_dp, _i]),
     "mog_packed_weight_layout": (_i, [_dp, _i]),
     "mog_pack_weight": (_i, [_dp, _i, _p, _p, _p]),
+    "mog_pack_plan": (_i, [_dp, _i, _p, _p, C.POINTER(MogPackEntry), _i]),
+    "mog_pack_multi": (_i, [_p, _i, _i, _p]),
     "mog_conv_out_hw": (_i, [_dp, C.POINTER(_i), C.POINTER(_i)]),
     "mog_conv_workspace_bytes": (_sz, [_dp, _i]),
     "mog_planes_bytes": (_sz, [C.c_longlong, _i, _i]),

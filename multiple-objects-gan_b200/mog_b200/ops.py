@@ -90,19 +90,31 @@ def nhwc(x):
 # ---------------------------------------------------------------------------------------------
 # convolution / linear
 # ---------------------------------------------------------------------------------------------
-def _packed(weight: torch.Tensor, which: str, d: MogConvDesc, dkey=None) -> torch.Tensor:
-    """Pack an OIHW parameter into the GEMM B operand of the kernel selected by ``d`` (fp32 matrix or
-    bf16 hi/lo planes per stride phase); cached on the tensor per (version, conv geometry)."""
-    cache = getattr(weight, "_mog_pack", None)
+def _weight_version(weight):
     # torch's version counter catches torch-side in-place updates; `_mog_ver` is bumped by mog_b200.optim.Adam, whose fused
     # kernel writes the parameter through its raw pointer (invisible to the version counter)
-    ver = (weight._version, getattr(weight, "_mog_ver", 0))
-    if cache is None or cache.get("ver") != ver or cache.get("ptr") != weight.data_ptr():
-        cache = {"ver": ver, "ptr": weight.data_ptr()}
+    return (weight._version, getattr(weight, "_mog_ver", 0), weight.data_ptr())
+
+
+def _weight4(weight):
+    w = weight.detach()
+    if w.dim() == 2:
+        w = w.reshape(w.shape[0], w.shape[1], 1, 1)
+    return w.contiguous()
+
+
+def _packed(weight: torch.Tensor, which: str, d: MogConvDesc, dkey=None) -> torch.Tensor:
+    """Pack an OIHW parameter into the GEMM B operand of the kernel selected by ``d`` (fp32 matrix or
+    bf16 hi/lo planes per stride phase).  One persistent buffer per (weight, conv geometry), refreshed when the weight's
+    version moves -- lazily here, or for all weights of a network at once by :func:`repack` after an optimiser step."""
+    cache = getattr(weight, "_mog_pack", None)
+    if cache is None:
+        cache = {}
         try:
             weight._mog_pack = cache
         except Exception:
             pass
+    ver = _weight_version(weight)
     # the dgrad packing depends on stride/pad (phase tap subsets) and, with odd sizes, on H/W parity
     wi = 0 if which == "fwd" else 1
     tag = _layout_cache.get((dkey, wi)) if dkey is not None else None
@@ -111,17 +123,63 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc, dkey=None) -> torc
         if dkey is not None:
             _layout_cache[(dkey, wi)] = tag
     key = (which, tag, d.precision, d.stride, d.pad, d.pad_w1, d.up2x, (d.H << d.up2x) >= d.stride, (d.W << d.up2x) >= d.stride)
-    if key not in cache:
-        w = weight.detach()
-        if w.dim() == 2:
-            w = w.reshape(w.shape[0], w.shape[1], 1, 1)
-        w = w.contiguous()
+    ent = cache.get(key)
+    if ent is None:
+        w = _weight4(weight)
         _chk(w, "weight")
         n = _lib.lib().mog_packed_weight_bytes(C.byref(d), wi)
-        out = torch.empty((n + 3) // 4, device=w.device, dtype=torch.float32)
-        call("mog_pack_weight", C.byref(d), wi, w.data_ptr(), out.data_ptr(), _stream())
-        cache[key] = out
-    return cache[key]
+        ent = cache[key] = {"out": torch.empty((n + 3) // 4, device=w.device, dtype=torch.float32), "ver": None,
+                            "d": MogConvDesc.from_buffer_copy(d), "wi": wi}
+    if ent["ver"] != ver:
+        w = _weight4(weight)
+        _chk(w, "weight")
+        call("mog_pack_weight", C.byref(d), wi, w.data_ptr(), ent["out"].data_ptr(), _stream())
+        ent["ver"] = ver
+    return ent["out"]
+
+
+_repack_tables = {}
+
+
+def repack(params):
+    """Refresh every packed operand of the given parameters with ONE multi-tensor launch (``mog_pack_multi``): called by
+    ``mog_b200.optim.Adam.step`` right after the update, instead of ~350 per-problem pack launches spread over the next
+    step.  Entries the multi-tensor form does not cover (filters with more than 16 taps, fp32 mode) stay on the lazy path."""
+    params = [p for p in params if getattr(p, "_mog_pack", None)]
+    if not params:
+        return
+    sig = tuple((id(p), p.data_ptr(), len(p._mog_pack)) for p in params)
+    tkey = tuple(id(p) for p in params)
+    tab = _repack_tables.get(tkey)
+    if tab is None or tab["sig"] != sig:
+        L = _lib.lib()
+        buf = (_lib.MogPackEntry * 16)()
+        entries, ents = [], []
+        for p in params:
+            w = _weight4(p)
+            for ent in p._mog_pack.values():
+                if ent["d"].precision == PREC_FP32:
+                    continue
+                n = L.mog_pack_plan(C.byref(ent["d"]), ent["wi"], w.data_ptr(), ent["out"].data_ptr(), buf, 16)
+                if n <= 0:
+                    continue            # not covered: refreshed lazily by _packed
+                for i in range(n):
+                    entries.append(_lib.MogPackEntry.from_buffer_copy(buf[i]))
+                ents.append((p, ent))
+        blocks = 0
+        for e in entries:
+            e.block_start = blocks
+            blocks += e.nxb * e.nyb
+        dev = None
+        if entries:
+            arr = (_lib.MogPackEntry * len(entries))(*entries)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            dev = host.to(params[0].device)
+        tab = _repack_tables[tkey] = {"sig": sig, "dev": dev, "n": len(entries), "blocks": blocks, "ents": ents}
+    if tab["n"]:
+        call("mog_pack_multi", tab["dev"].data_ptr(), tab["n"], tab["blocks"], _stream())
+        for p, ent in tab["ents"]:
+            ent["ver"] = _weight_version(p)
 
 
 _desc_cache = {}

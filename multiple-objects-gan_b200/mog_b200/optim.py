@@ -72,9 +72,14 @@ class Adam(torch.optim.Optimizer):
                 p._mog_ver = getattr(p, "_mog_ver", 0) + 1
             if ps:
                 self._launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale)
+        updated = []
         for group in self.param_groups:
             for p in group["params"]:
-                self.state[p].pop("_keep", None) if p in self.state else None
+                if p in self.state and self.state[p].pop("_keep", None) is not None:
+                    updated.append(p)
+        # the convolutions' packed operands of every updated weight, refreshed in one multi-tensor launch
+        from . import ops
+        ops.repack(updated)
         return loss
 
     @staticmethod
