@@ -505,6 +505,8 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
 
 // Multi-tensor form: one launch repacks every (weight, problem) entry of a device-resident table (mog_pack_multi).
 // Same tiling as pack_tc_kernel<0, 16, 17>; block -> entry by binary search over the entries' first blocks.
+constexpr int PM_ROW = PK_C * 17 + 1;
+
 template <int KHW_T>
 __device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, int by, float* tile) {
   const int n0 = by * PK_N, c0 = bx * PK_C;
@@ -514,46 +516,61 @@ __device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, i
     for (int nl = ty; nl < PK_N; nl += 8) {
       const int nn = n0 + nl;
       const float* src = a.w + ((size_t)nn * a.Cin + c0) * KHW;
+#pragma unroll 8
       for (int j = tx; j < PK_C * KHW; j += 32) {
         const int cl = j / KHW, t = j - cl * KHW;
         float v = 0.f;
         if (nn < a.Nreal && c0 + cl < a.CsReal) v = __ldg(src + j);
-        tile[(nl * PK_C + cl) * 17 + t] = v;
+        tile[nl * PM_ROW + cl * 17 + t] = v;
       }
     }
   } else {
     for (int cl = ty; cl < PK_C; cl += 8) {
       const int c = c0 + cl;
       const float* src = a.w + ((size_t)c * a.Cin + n0) * KHW;
+#pragma unroll 8
       for (int j = tx; j < PK_N * KHW; j += 32) {
         const int nl = j / KHW, t = j - nl * KHW;
         float v = 0.f;
         if (n0 + nl < a.Nreal && c < a.CsReal) v = __ldg(src + j);
-        tile[(nl * PK_C + cl) * 17 + t] = v;
+        tile[nl * PM_ROW + cl * 17 + t] = v;
       }
     }
   }
   __syncthreads();
   __nv_bfloat16* phi = static_cast<__nv_bfloat16*>(a.hi);
   __nv_bfloat16* plo = static_cast<__nv_bfloat16*>(a.lo);
-  const int c = c0 + tx;
-  if (c < a.Cs) {
-    for (int nl = ty; nl < PK_N; nl += 8) {
-      const int nn = n0 + nl;
-      if (nn >= a.Npad) break;
-      for (int tl = 0; tl < a.ntaps; ++tl) {
-        float v = 0.f;
+  // store: an item = (local tap tl, row nl, group of 8 consecutive channels) -> one 16-byte store per plane; the n rows of
+  // the tile are PM_ROW = 32 * 17 + 1 floats apart so that the 32 (nl, group) items of a warp read 32 different banks
+  const int ngr = PK_C / 8, per_tap = PK_N * ngr;
+  for (int it = threadIdx.x; it < a.ntaps * per_tap; it += 256) {
+    const int tl = it / per_tap, rem = it - tl * per_tap;
+    const int nl = rem / ngr, gq = rem - nl * ngr;
+    const int nn = n0 + nl, cg = c0 + gq * 8;
+    if (nn >= a.Npad || cg >= a.Cs) continue;
+    const int t0 = a.taps[tl][0], t1 = a.taps[tl][1], t2 = a.taps[tl][2], t3 = a.taps[tl][3];
+    uint32_t h[4], l[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int tp = a.taps[tl][u];
-          if (tp >= 0) v += tile[(nl * PK_C + tx) * 17 + tp];
-        }
-        const size_t o = (size_t)nn * a.Kpad + (size_t)tl * a.Cs + c;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        phi[o] = h;
-        if (plo) plo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float* tp = tile + nl * PM_ROW + (gq * 8 + 2 * e + q) * 17;
+        float x = tp[t0];
+        if (t1 >= 0) x += tp[t1];
+        if (t2 >= 0) x += tp[t2];
+        if (t3 >= 0) x += tp[t3];
+        v[q] = x;
       }
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+      h[e] = *reinterpret_cast<uint32_t*>(&h2);
+      const float2 hf = __bfloat1622float2(h2);
+      __nv_bfloat162 l2 = __floats2bfloat162_rn(v[0] - hf.x, v[1] - hf.y);
+      l[e] = *reinterpret_cast<uint32_t*>(&l2);
     }
+    const size_t o = (size_t)nn * a.Kpad + (size_t)tl * a.Cs + cg;
+    *reinterpret_cast<uint4*>(phi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (plo) *reinterpret_cast<uint4*>(plo + o) = make_uint4(l[0], l[1], l[2], l[3]);
   }
   if (bx == 0) {
     for (int nl = ty; nl < PK_N; nl += 8) {
@@ -568,7 +585,7 @@ __device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, i
 }
 
 __global__ void __launch_bounds__(256) pack_multi_kernel(const MogPackEntry* __restrict__ T, int n) {
-  __shared__ float tile[PK_N * PK_C * 17];
+  __shared__ float tile[PK_N * PM_ROW];
   __shared__ MogPackEntry ent;
   int lo = 0, hi = n - 1;
   const int b = (int)blockIdx.x;
