@@ -93,9 +93,17 @@ typedef struct MogPackEntry {
   int32_t block_start;     /* first block of the entry within the launch (filled by the caller)   */
   int32_t taps[16][4];     /* filter taps summed into each local tap, -1 = unused                 */
 } MogPackEntry;
+/* Entries that read the same source tiles (the problems of one weight: sub-pixel phases, parity views, stride phases --
+ * same w, orientation, channel pitch and row padding) form a group: a block loads its 16 x 32 x taps tile ONCE and writes it
+ * into every entry of the group.  block_start (exclusive prefix sum of nxb * nyb over the groups) is filled by the caller. */
+typedef struct MogPackGroup {
+  int32_t first, count;    /* entries [first, first + count) of the entry table                   */
+  int32_t block_start;     /* first block of the group within the launch                          */
+  int32_t nxb;             /* blocks along the channel axis (= the entries' nxb)                   */
+} MogPackGroup;
 /* returns the number of entries written (<= capacity), or a negative MOG_ERR_* (MOG_ERR_UNSUPPORTED: use mog_pack_weight) */
 int mog_pack_plan(const MogConvDesc* d, int which, const float* w, void* out, MogPackEntry* entries, int capacity);
-int mog_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, void* stream);
+int mog_pack_multi(const MogPackEntry* entries_dev, const MogPackGroup* groups_dev, int ngroups, int total_blocks, void* stream);
 
 /* ---- convolution ----------------------------------------------------------------------- */
 /* Operand formats.  MOG_PREC_FP32: fp32 NHWC tensors.  tcgen05 precisions: the gathered operands

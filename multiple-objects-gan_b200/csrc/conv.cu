@@ -445,9 +445,10 @@ extern "C" int mog_pack_plan(const MogConvDesc* d, int which, const float* w, vo
   return n;
 }
 
-extern "C" int mog_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, void* stream) {
-  MOG_REQUIRE(entries_dev && n > 0 && total_blocks > 0, "mog_pack_multi: bad argument");
-  return launch_pack_multi(entries_dev, n, total_blocks, as_stream(stream));
+extern "C" int mog_pack_multi(const MogPackEntry* entries_dev, const MogPackGroup* groups_dev, int ngroups, int total_blocks,
+                              void* stream) {
+  MOG_REQUIRE(entries_dev && groups_dev && ngroups > 0 && total_blocks > 0, "mog_pack_multi: bad argument");
+  return launch_pack_multi(entries_dev, groups_dev, ngroups, total_blocks, as_stream(stream));
 }
 
 extern "C" size_t mog_conv_workspace_bytes(const MogConvDesc* d, int which) {

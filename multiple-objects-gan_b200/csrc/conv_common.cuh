@@ -61,7 +61,7 @@ int tc_pack_pitch(const float* w_oihw, void* out, int Cout, int Cin, int KH, int
                   const int (*taps)[4], int pitch, int passes, cudaStream_t st);
 int tc_pack_entry(const float* w_oihw, void* out, int Cout, int Cin, int KH, int KW, int transpose, int ntaps,
                   const int (*taps)[4], int pitch, int passes, MogPackEntry* e);
-int launch_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, cudaStream_t st);
+int launch_pack_multi(const MogPackEntry* entries_dev, const MogPackGroup* groups_dev, int ngroups, int total_blocks, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(const MogConvDesc& d, int Ho, int Wo);
 int launch_wgrad_tc(const MogConvDesc& d, int Ho, int Wo, const float* x, const float* dy, const void* x_planes,
                     size_t x_plane_elems, const void* dy_planes, size_t dy_plane_elems, float* ws, int passes,

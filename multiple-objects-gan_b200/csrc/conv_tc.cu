@@ -507,10 +507,11 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
 // Same tiling as pack_tc_kernel<0, 16, 17>; block -> entry by binary search over the entries' first blocks.
 constexpr int PM_ROW = PK_C * 17 + 1;
 
+// load the block's source tile [16 n][32 c][taps] of entry a (all filter taps); KHW_T: compile-time tap count
 template <int KHW_T>
-__device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, int by, float* tile) {
+__device__ __forceinline__ void pack_multi_load(const MogPackEntry& a, int bx, int by, float* tile) {
   const int n0 = by * PK_N, c0 = bx * PK_C;
-  const int KHW = KHW_T ? KHW_T : a.KHW;      // compile-time tap count: no integer division in the copy loops
+  const int KHW = KHW_T ? KHW_T : a.KHW;      // no integer division by a runtime value in the copy loops
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (!a.transpose) {
     for (int nl = ty; nl < PK_N; nl += 8) {
@@ -537,11 +538,15 @@ __device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, i
       }
     }
   }
-  __syncthreads();
+}
+
+// write the tile into entry a: an item = (local tap tl, row nl, group of 8 consecutive channels) -> one 16-byte store per
+// plane; the n rows of the tile are PM_ROW = 32 * 17 + 1 floats apart so that the 32 items of a warp read 32 different banks
+__device__ __forceinline__ void pack_multi_store(const MogPackEntry& a, int bx, int by, const float* tile) {
+  const int n0 = by * PK_N, c0 = bx * PK_C;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   __nv_bfloat16* phi = static_cast<__nv_bfloat16*>(a.hi);
   __nv_bfloat16* plo = static_cast<__nv_bfloat16*>(a.lo);
-  // store: an item = (local tap tl, row nl, group of 8 consecutive channels) -> one 16-byte store per plane; the n rows of
-  // the tile are PM_ROW = 32 * 17 + 1 floats apart so that the 32 (nl, group) items of a warp read 32 different banks
   const int ngr = PK_C / 8, per_tap = PK_N * ngr;
   for (int it = threadIdx.x; it < a.ntaps * per_tap; it += 256) {
     const int tl = it / per_tap, rem = it - tl * per_tap;
@@ -572,7 +577,7 @@ __device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, i
     *reinterpret_cast<uint4*>(phi + o) = make_uint4(h[0], h[1], h[2], h[3]);
     if (plo) *reinterpret_cast<uint4*>(plo + o) = make_uint4(l[0], l[1], l[2], l[3]);
   }
-  if (bx == 0) {
+  if (bx == 0) {     // zero the K tail [K, Kpad) of this block's rows
     for (int nl = ty; nl < PK_N; nl += 8) {
       const int nn = n0 + nl;
       if (nn >= a.Npad) break;
@@ -584,26 +589,34 @@ __device__ __forceinline__ void pack_multi_body(const MogPackEntry& a, int bx, i
   }
 }
 
-__global__ void __launch_bounds__(256) pack_multi_kernel(const MogPackEntry* __restrict__ T, int n) {
+__global__ void __launch_bounds__(256) pack_multi_kernel(const MogPackEntry* __restrict__ T, const MogPackGroup* __restrict__ G, int ng) {
   __shared__ float tile[PK_N * PM_ROW];
   __shared__ MogPackEntry ent;
-  int lo = 0, hi = n - 1;
+  int lo = 0, hi = ng - 1;
   const int b = (int)blockIdx.x;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(&T[mid].block_start) <= b) lo = mid; else hi = mid - 1;
+    if (__ldg(&G[mid].block_start) <= b) lo = mid; else hi = mid - 1;
   }
-  // the entry (336 bytes) once into shared memory: the taps table and the geometry are read many times below
-  for (int i = threadIdx.x; i < (int)(sizeof(MogPackEntry) / 4); i += blockDim.x)
-    reinterpret_cast<int*>(&ent)[i] = __ldg(reinterpret_cast<const int*>(&T[lo]) + i);
-  __syncthreads();
-  const int local = b - ent.block_start;
-  const int bx = local % ent.nxb, by = local / ent.nxb;
-  switch (ent.KHW) {
-    case 1: pack_multi_body<1>(ent, bx, by, tile); break;
-    case 9: pack_multi_body<9>(ent, bx, by, tile); break;
-    case 16: pack_multi_body<16>(ent, bx, by, tile); break;
-    default: pack_multi_body<0>(ent, bx, by, tile); break;
+  const int first = __ldg(&G[lo].first), count = __ldg(&G[lo].count), nxb = __ldg(&G[lo].nxb);
+  const int local = b - __ldg(&G[lo].block_start);
+  const int bx = local % nxb, by = local / nxb;
+  for (int gi = 0; gi < count; ++gi) {
+    // the entry (336 bytes) into shared memory: its taps table and geometry are read many times
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(sizeof(MogPackEntry) / 4); i += blockDim.x)
+      reinterpret_cast<int*>(&ent)[i] = __ldg(reinterpret_cast<const int*>(&T[first + gi]) + i);
+    __syncthreads();
+    if (gi == 0) {   // the source tile is the same for every entry of the group
+      switch (ent.KHW) {
+        case 1: pack_multi_load<1>(ent, bx, by, tile); break;
+        case 9: pack_multi_load<9>(ent, bx, by, tile); break;
+        case 16: pack_multi_load<16>(ent, bx, by, tile); break;
+        default: pack_multi_load<0>(ent, bx, by, tile); break;
+      }
+      __syncthreads();
+    }
+    pack_multi_store(ent, bx, by, tile);
   }
 }
 
@@ -807,8 +820,8 @@ int tc_pack_entry(const float* w_oihw, void* out, int Cout, int Cin, int KH, int
   return MOG_OK;
 }
 
-int launch_pack_multi(const MogPackEntry* entries_dev, int n, int total_blocks, cudaStream_t st) {
-  tc::pack_multi_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(entries_dev, n);
+int launch_pack_multi(const MogPackEntry* entries_dev, const MogPackGroup* groups_dev, int ngroups, int total_blocks, cudaStream_t st) {
+  tc::pack_multi_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(entries_dev, groups_dev, ngroups);
   return check_launch("pack_multi_kernel");
 }
 

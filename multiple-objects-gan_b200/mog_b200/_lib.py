@@ -28,6 +28,10 @@ class MogPackEntry(C.Structure):
                                          "nxb", "nyb", "block_start")] + [("taps", (C.c_int32 * 4) * 16)]
 
 
+class MogPackGroup(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("first", "count", "block_start", "nxb")]
+
+
 _p = C.c_void_p
 _i = C.c_int
 _f = C.c_float
@@ -45,7 +49,7 @@ SIGNATURES = {
     "mog_packed_weight_layout": (_i, [_dp, _i]),
     "mog_pack_weight": (_i, [_dp, _i, _p, _p, _p]),
     "mog_pack_plan": (_i, [_dp, _i, _p, _p, C.POINTER(MogPackEntry), _i]),
-    "mog_pack_multi": (_i, [_p, _i, _i, _p]),
+    "mog_pack_multi": (_i, [_p, _p, _i, _i, _p]),
     "mog_conv_out_hw": (_i, [_dp, C.POINTER(_i), C.POINTER(_i)]),
     "mog_conv_workspace_bytes": (_sz, [_dp, _i]),
     "mog_planes_bytes": (_sz, [C.c_longlong, _i, _i]),

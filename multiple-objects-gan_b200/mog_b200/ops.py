@@ -154,7 +154,7 @@ def repack(params):
     if tab is None or tab["sig"] != sig:
         L = _lib.lib()
         buf = (_lib.MogPackEntry * 16)()
-        entries, ents = [], []
+        entries, groups, ents = [], [], []
         for p in params:
             w = _weight4(p)
             for ent in p._mog_pack.values():
@@ -164,20 +164,30 @@ def repack(params):
                 if n <= 0:
                     continue            # not covered: refreshed lazily by _packed
                 for i in range(n):
-                    entries.append(_lib.MogPackEntry.from_buffer_copy(buf[i]))
+                    e = _lib.MogPackEntry.from_buffer_copy(buf[i])
+                    g = groups[-1] if groups else None
+                    # problems of the same weight that read the same source tiles (sub-pixel phases, parity views, stride
+                    # phases) share one group: the tile is loaded once and written into each of them
+                    if i > 0 and g is not None and (e.Cs, e.Npad, e.transpose, e.nxb, e.nyb) == g["sig"]:
+                        g["count"] += 1
+                    else:
+                        groups.append({"first": len(entries), "count": 1, "sig": (e.Cs, e.Npad, e.transpose, e.nxb, e.nyb),
+                                       "blocks": e.nxb * e.nyb, "nxb": e.nxb})
+                    entries.append(e)
                 ents.append((p, ent))
         blocks = 0
-        for e in entries:
-            e.block_start = blocks
-            blocks += e.nxb * e.nyb
-        dev = None
+        garr = (_lib.MogPackGroup * max(len(groups), 1))()
+        for i, g in enumerate(groups):
+            garr[i].first, garr[i].count, garr[i].block_start, garr[i].nxb = g["first"], g["count"], blocks, g["nxb"]
+            blocks += g["blocks"]
+        dev = gdev = None
         if entries:
             arr = (_lib.MogPackEntry * len(entries))(*entries)
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            dev = host.to(params[0].device)
-        tab = _repack_tables[tkey] = {"sig": sig, "dev": dev, "n": len(entries), "blocks": blocks, "ents": ents}
+            dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(params[0].device)
+            gdev = torch.frombuffer(bytearray(bytes(garr)), dtype=torch.uint8).to(params[0].device)
+        tab = _repack_tables[tkey] = {"sig": sig, "dev": dev, "gdev": gdev, "n": len(groups), "blocks": blocks, "ents": ents}
     if tab["n"]:
-        call("mog_pack_multi", tab["dev"].data_ptr(), tab["n"], tab["blocks"], _stream())
+        call("mog_pack_multi", tab["dev"].data_ptr(), tab["gdev"].data_ptr(), tab["n"], tab["blocks"], _stream())
         for p, ent in tab["ents"]:
             ent["ver"] = _weight_version(p)
 
