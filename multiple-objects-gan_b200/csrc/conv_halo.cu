@@ -31,6 +31,12 @@
 //     {16 ch, 8 w, 16 h} into the (strided, for sub-pixel phases) NHWC destination; ragged edges, channel
 //     tails and padding sub-tiles are clipped by the TMA unit.
 //   * MOG_PREC_BF16X3: three MMAs per k-step (hi*hi, lo*hi, hi*lo) on the hi/lo planes.
+//   * small-grid form (pixel grids up to 8 x 8: the deep discriminator layers, the 8 x 8 stage of the image encoder): a
+//     sub-tile packs several images (8 x 8 px of 2 images, or 4 x 4 px of 8 images), every filter tap is its own box (no
+//     halo: rows of different images are not a uniform stride apart), the N tile grows to 256 columns (single-buffered
+//     TMEM: two 128-row sub-tiles share each 256-column weight chunk), and the few output tiles are spread over the SMs
+//     by split-K: a work item is (sub-tile pair, N tile, K range); raw fp32 partials leave through a 5-D TMA store into
+//     [split][N][H][W][C] and splitk_reduce sums them in a fixed order (bias / activation applied there).
 #include <cstdlib>
 
 #include <cuda.h>
