@@ -167,6 +167,12 @@ int mog_bn_act_bwd_apply(const float* x, const float* dy, const float* mean, con
                          const float* gamma, const float* beta, const double* dgamma_seg,
                          const double* dbeta_seg, int S, int M, int C, int act, float* dx,
                          float* dgamma /*[C], summed over segments*/, float* dbeta, void* stream);
+/* Same, and additionally emits dx as the pre-split bf16 planes (hi [rows][C], then lo for MOG_PREC_BF16X3) that the data /
+ * weight gradient kernels of the producing convolution read, saving the separate split pass over dx.  C % 8 == 0. */
+int mog_bn_act_bwd_apply_planes(const float* x, const float* dy, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, const double* dgamma_seg,
+                                const double* dbeta_seg, int S, int M, int C, int act, float* dx, void* dx_planes,
+                                int precision, float* dgamma, float* dbeta, void* stream);
 /* dz = dy * act'(.) given the activation OUTPUT y (LRELU / RELU / TANH / SIGMOID). */
 int mog_act_bwd(const float* dy, const float* y, float* dz, size_t n, int act, void* stream);
 

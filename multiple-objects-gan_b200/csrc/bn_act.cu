@@ -527,9 +527,19 @@ __global__ void bn_bwd_reduce_v4_kernel(BnBwdArgs a, V4Geom g, double* __restric
   }
 }
 
+__device__ __forceinline__ void emit_planes4(const float (&o)[4], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]), h23 = __floats2bfloat162_rn(o[2], o[3]);
+  *reinterpret_cast<uint2*>(hi) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+  if (lo) {
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    __nv_bfloat162 l01 = __floats2bfloat162_rn(o[0] - f01.x, o[1] - f01.y), l23 = __floats2bfloat162_rn(o[2] - f23.x, o[3] - f23.y);
+    *reinterpret_cast<uint2*>(lo) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+  }
+}
+
 template <int ACT>
 __global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __restrict__ dgamma, const double* __restrict__ dbeta,
-                                       float* __restrict__ dx) {
+                                       float* __restrict__ dx, __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo) {
   constexpr bool GLU = ACT == MOG_ACT_GLU;
   const int Co = GLU ? a.C / 2 : a.C;
   const int cgl = threadIdx.x % g.GB, rl = threadIdx.x / g.GB;
@@ -562,10 +572,14 @@ __global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = kv.sc[j] * (dzv[j] - k1v[j] - (xv[j] - kv.mu[j]) * kv.is[j] * k2v[j]);
     *reinterpret_cast<float4*>(dp + (size_t)r * a.C) = make_float4(o[0], o[1], o[2], o[3]);
+    // dx also as the bf16 hi (+ lo) planes the data / weight gradient kernels of the producing convolution read (C % 8 == 0)
+    const size_t prow = ((size_t)s * a.M + (size_t)r) * a.C + c;
+    if (phi) emit_planes4(o, phi + prow, plo ? plo + prow : nullptr);
     if (GLU) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = kg.sc[j] * (dzg[j] - k1g[j] - (xg[j] - kg.mu[j]) * kg.is[j] * k2g[j]);
       *reinterpret_cast<float4*>(dp + (size_t)r * a.C + Co) = make_float4(o[0], o[1], o[2], o[3]);
+      if (phi) emit_planes4(o, phi + prow + Co, plo ? plo + prow + Co : nullptr);
     }
   };
   long long r = r_begin + rl;
@@ -589,24 +603,26 @@ __global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __re
 }
 
 template <int ACT>
-static void launch_bwd_v4(bool reduce, const BnBwdArgs& a, const V4Geom& g, double* dgamma, double* dbeta, float* dx, cudaStream_t st) {
+static void launch_bwd_v4(bool reduce, const BnBwdArgs& a, const V4Geom& g, double* dgamma, double* dbeta, float* dx, cudaStream_t st,
+                          __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr) {
   dim3 grid(g.nxb, g.nyb, a.S);
   if (reduce)
     bn_bwd_reduce_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta);
   else
-    bn_bwd_apply_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta, dx);
+    bn_bwd_apply_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta, dx, phi, plo);
 }
-static bool bwd_v4(bool reduce, const BnBwdArgs& a, double* dgamma, double* dbeta, float* dx, cudaStream_t st) {
+static bool bwd_v4(bool reduce, const BnBwdArgs& a, double* dgamma, double* dbeta, float* dx, cudaStream_t st,
+                   __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr) {
   const int width = a.act == MOG_ACT_GLU ? a.C / 2 : a.C;
   if ((width & 3) || (a.C & 3) || a.S > 65535) return false;
   const V4Geom g = v4_geom(width, a.M, a.S, reduce);
   switch (a.act) {
-    case MOG_ACT_NONE: launch_bwd_v4<MOG_ACT_NONE>(reduce, a, g, dgamma, dbeta, dx, st); break;
-    case MOG_ACT_RELU: launch_bwd_v4<MOG_ACT_RELU>(reduce, a, g, dgamma, dbeta, dx, st); break;
-    case MOG_ACT_LRELU: launch_bwd_v4<MOG_ACT_LRELU>(reduce, a, g, dgamma, dbeta, dx, st); break;
-    case MOG_ACT_GLU: launch_bwd_v4<MOG_ACT_GLU>(reduce, a, g, dgamma, dbeta, dx, st); break;
-    case MOG_ACT_TANH: launch_bwd_v4<MOG_ACT_TANH>(reduce, a, g, dgamma, dbeta, dx, st); break;
-    case MOG_ACT_SIGMOID: launch_bwd_v4<MOG_ACT_SIGMOID>(reduce, a, g, dgamma, dbeta, dx, st); break;
+    case MOG_ACT_NONE: launch_bwd_v4<MOG_ACT_NONE>(reduce, a, g, dgamma, dbeta, dx, st, phi, plo); break;
+    case MOG_ACT_RELU: launch_bwd_v4<MOG_ACT_RELU>(reduce, a, g, dgamma, dbeta, dx, st, phi, plo); break;
+    case MOG_ACT_LRELU: launch_bwd_v4<MOG_ACT_LRELU>(reduce, a, g, dgamma, dbeta, dx, st, phi, plo); break;
+    case MOG_ACT_GLU: launch_bwd_v4<MOG_ACT_GLU>(reduce, a, g, dgamma, dbeta, dx, st, phi, plo); break;
+    case MOG_ACT_TANH: launch_bwd_v4<MOG_ACT_TANH>(reduce, a, g, dgamma, dbeta, dx, st, phi, plo); break;
+    case MOG_ACT_SIGMOID: launch_bwd_v4<MOG_ACT_SIGMOID>(reduce, a, g, dgamma, dbeta, dx, st, phi, plo); break;
     default: return false;
   }
   return true;
@@ -693,7 +709,24 @@ extern "C" int mog_bn_act_bwd_apply(const float* x, const float* dy, const float
                                     const float* gamma, const float* beta, const double* dgamma_seg,
                                     const double* dbeta_seg, int S, int M, int C, int act, float* dx, float* dgamma,
                                     float* dbeta, void* stream) {
+  return mog_bn_act_bwd_apply_planes(x, dy, mean, invstd, gamma, beta, dgamma_seg, dbeta_seg, S, M, C, act, dx, nullptr, MOG_PREC_FP32,
+                                     dgamma, dbeta, stream);
+}
+
+extern "C" int mog_bn_act_bwd_apply_planes(const float* x, const float* dy, const float* mean, const float* invstd,
+                                           const float* gamma, const float* beta, const double* dgamma_seg,
+                                           const double* dbeta_seg, int S, int M, int C, int act, float* dx, void* dx_planes,
+                                           int precision, float* dgamma, float* dbeta, void* stream) {
   MOG_REQUIRE(x && dy && dx && S > 0 && M > 0 && C > 0, "mog_bn_act_bwd_apply: bad argument");
+  __nv_bfloat16* phi = nullptr;
+  __nv_bfloat16* plo = nullptr;
+  if (dx_planes) {
+    const int width = act == MOG_ACT_GLU ? C / 2 : C;
+    MOG_REQUIRE(precision == MOG_PREC_BF16X3 || precision == MOG_PREC_BF16, "mog_bn_act_bwd_apply_planes: precision must be a tcgen05 mode");
+    MOG_REQUIRE((C & 7) == 0 && (width & 3) == 0, "mog_bn_act_bwd_apply_planes: plane emission needs C %% 8 == 0 (got %d)", C);
+    phi = static_cast<__nv_bfloat16*>(dx_planes);
+    plo = precision == MOG_PREC_BF16X3 ? phi + (size_t)S * M * C : nullptr;
+  }
   const bool has_bn = mean != nullptr;
   MOG_REQUIRE(has_bn == (invstd != nullptr) && has_bn == (dgamma_seg != nullptr) && has_bn == (dbeta_seg != nullptr),
               "mog_bn_act_bwd_apply: mean/invstd/dgamma_seg/dbeta_seg must all be given or all be NULL");
@@ -701,9 +734,10 @@ extern "C" int mog_bn_act_bwd_apply(const float* x, const float* dy, const float
   const int rpb = rows_per_block(M);
   BnBwdArgs a{x, dy, mean, invstd, gamma, beta, S, M, C, act, rpb};
   int rc;
-  if (bwd_v4(false, a, const_cast<double*>(dgamma_seg), const_cast<double*>(dbeta_seg), dx, st)) {
+  if (bwd_v4(false, a, const_cast<double*>(dgamma_seg), const_cast<double*>(dbeta_seg), dx, st, phi, plo)) {
     rc = check_launch("bn_bwd_apply_v4_kernel");
   } else {
+    MOG_REQUIRE(!dx_planes, "mog_bn_act_bwd_apply_planes: this shape runs on the scalar kernel, which does not emit planes");
     dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
     MOG_REQUIRE(grid.z <= 65535, "mog_bn_act_bwd_apply: too many segments");
     bn_bwd_apply_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, dgamma_seg, dbeta_seg, dx);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "mog_affine_act_fwd_planes": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mog_bn_act_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "mog_bn_act_bwd_apply": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mog_bn_act_bwd_apply_planes": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
     "mog_act_bwd": (_i, [_p, _p, _p, _sz, _i, _p]),
     "mog_sumpool2x2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mog_stn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -254,13 +254,13 @@ def _alloc_planes(shape, precision, device):
 
 def _attach_planes(y: torch.Tensor, planes: torch.Tensor, precision: int):
     """Remember the pre-split planes of ``y`` (written by the producing kernel) for a consuming convolution."""
-    y._mog_planes = (planes, precision, y._version)
+    y._mog_planes = (planes, precision, y._version, y.data_ptr())
 
 
 def planes_of(x: torch.Tensor, precision: int):
     """Planes of x: those its producer emitted (bn_act / activation epilogue) if still valid, else a split pass."""
     cached = getattr(x, "_mog_planes", None)
-    if cached is not None and cached[1] == precision and cached[2] == x._version:
+    if cached is not None and cached[1] == precision and cached[2] == x._version and cached[3] == x.data_ptr():
         return cached[0]
     return split_planes(x, precision)
 
@@ -325,7 +325,7 @@ class Conv2dFn(torch.autograd.Function):
             call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, st)
             dy = dz
         if dyp is None and precision != PREC_FP32 and (need_dx or need_dw):
-            dyp = split_planes(dy, precision)
+            dyp = planes_of(dy, precision)     # emitted by the BatchNorm backward that produced dy, else a split pass
         dx = dw = db = None
         if need_dx:
             dx = torch.empty(xshape, device=dev, dtype=torch.float32)
@@ -387,6 +387,7 @@ class BnActFn(torch.autograd.Function):
         call("mog_affine_act_fwd_planes", x.data_ptr(), mis[2].data_ptr(), mis[3].data_ptr(), _ptr(residual),
              y.data_ptr(), _ptr(planes), precision, S, M, Cc, act, st)
         ctx.cfg = (S, M, Cc, act)
+        ctx.precision = precision
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, g, b, mis)
         return y
@@ -403,9 +404,16 @@ class BnActFn(torch.autograd.Function):
              g.data_ptr(), b.data_ptr(), S, M, Cc, act, red[0].data_ptr(), red[1].data_ptr(), st)
         dx = torch.empty_like(x)
         dgb = torch.empty((2, Cc), device=dev, dtype=torch.float32)
-        call("mog_bn_act_bwd_apply", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
-             g.data_ptr(), b.data_ptr(), red[0].data_ptr(), red[1].data_ptr(), S, M, Cc, act, dx.data_ptr(),
+        # dx usually is the output gradient of a convolution: emit it as bf16 planes too (saves that conv's split pass)
+        prec = ctx.precision
+        planes = None
+        if prec != PREC_FP32 and x.dim() == 4 and Cc % 8 == 0:
+            planes = torch.empty((_planes_bytes(S * M, Cc, prec) + 3) // 4, device=dev, dtype=torch.float32)
+        call("mog_bn_act_bwd_apply_planes", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
+             g.data_ptr(), b.data_ptr(), red[0].data_ptr(), red[1].data_ptr(), S, M, Cc, act, dx.data_ptr(), _ptr(planes), prec,
              dgb[0].data_ptr(), dgb[1].data_ptr(), st)
+        if planes is not None:
+            _attach_planes(dx, planes, prec)
         dres = dy if ctx.has_res else None
         return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None, None, None
 
