@@ -47,19 +47,22 @@ struct PairSmem {
   float* cosv; // [TMAXW] cos, [TMAXW] |w|, [TMAXW] |v|, [TMAXW] wv
 };
 
-// tp: word pitch of the layout (= the kernel's NT: Tw rounded up to 8; 18 words -> 24 keeps the forward at 82 KB, two CTAs per SM)
+// tp: word pitch of the layout (= the kernel's NT: Tw rounded up to 8; 18 words -> 24 keeps the forward at ~84 KB, two CTAs per SM)
+// Region pitch of the [word][region] arrays: R rounded up to 4 so that four regions are one 128-bit shared-memory load.
+__host__ __device__ __forceinline__ int lda_of(int R) { return (R + 3) & ~3; }
+__host__ __device__ __forceinline__ size_t al4(size_t n) { return (n + 3) & ~size_t(3); }
 __device__ __forceinline__ PairSmem carve(float* sm, int R, int D, int tp) {
   PairSmem p;
   p.w = sm;
-  p.S = p.w + (size_t)D * (tp + 1);
-  p.A2 = p.S + (size_t)R * (tp + 1);
-  p.red = p.A2 + (size_t)tp * (R + 1);
-  p.cosv = p.red + 3 * tp * (DT / 32 + 1);
+  p.S = p.w + al4((size_t)D * (tp + 1));
+  p.A2 = p.S + al4((size_t)R * (tp + 1));
+  p.red = p.A2 + (size_t)tp * lda_of(R);
+  p.cosv = p.red + al4(3 * tp * (DT / 32 + 1));
   return p;
 }
 static size_t pair_smem_bytes(int R, int D, int tp, bool bwd) {
-  size_t f = (size_t)D * (tp + 1) + (size_t)R * (tp + 1) + (size_t)tp * (R + 1) + 3 * tp * (DT / 32 + 1) + 4 * tp;
-  if (bwd) f += (size_t)tp * (R + 1) + (size_t)D * (tp + 1);   // dA, dvs
+  size_t f = al4((size_t)D * (tp + 1)) + al4((size_t)R * (tp + 1)) + (size_t)tp * lda_of(R) + al4(3 * tp * (DT / 32 + 1)) + 4 * tp;
+  if (bwd) f += (size_t)tp * lda_of(R) + (size_t)D * (tp + 1);   // dA, dvs
   return sizeof(float) * f;
 }
 
@@ -71,29 +74,40 @@ template <int CPT, int NT>
 __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float* ctx, const float* wi, int n,
                              float (&v)[CPT][NT]) {
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int ldw = NT + 1;
+  const int ldw = NT + 1, ldA = lda_of(a.R);
   for (int i = tid; i < a.D * n; i += DT) {
     int c = i / n, t = i - c * n;
     s.w[c * ldw + t] = __ldg(wi + (size_t)c * a.Tw + t);
   }
   __syncthreads();
-  // scores: one warp per region, lanes over channels
-  for (int r = wrp; r < a.R; r += DT / 32) {
-    float acc[NT];
+  // scores: one warp per PAIR of regions, lanes over channels: every word vector element read from shared memory feeds
+  // two FMAs (the loop is bound by shared-memory loads, one per FMA before)
+  for (int r = wrp; r < a.R; r += 2 * (DT / 32)) {
+    const int r1 = r + DT / 32;
+    const bool has1 = r1 < a.R;
+    float acc0[NT], acc1[NT];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    for (int t = 0; t < NT; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
 #pragma unroll 4
     for (int c = lane; c < a.D; c += 32) {
-      const float x = __ldg(ctx + (size_t)r * a.D + c);
+      const float x0 = __ldg(ctx + (size_t)r * a.D + c);
+      const float x1 = has1 ? __ldg(ctx + (size_t)r1 * a.D + c) : 0.f;
 #pragma unroll
       for (int t = 0; t < NT; ++t)
-        if (t < n) acc[t] = fmaf(x, s.w[c * ldw + t], acc[t]);
+        if (t < n) {
+          const float wv = s.w[c * ldw + t];
+          acc0[t] = fmaf(x0, wv, acc0[t]);
+          acc1[t] = fmaf(x1, wv, acc1[t]);
+        }
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       if (t < n) {
-        float z = warp_sum(acc[t]);
-        if (lane == 0) s.S[r * ldw + t] = z;
+        const float z0 = warp_sum(acc0[t]), z1 = warp_sum(acc1[t]);
+        if (lane == 0) {
+          s.S[r * ldw + t] = z0;
+          if (has1) s.S[r1 * ldw + t] = z1;
+        }
       }
     }
   }
@@ -120,12 +134,13 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
     float sum = 0.f;
     for (int r = lane; r < a.R; r += 32) {
       float e = expf(a.g1 * s.S[r * ldw + t] - mx);
-      s.A2[t * (a.R + 1) + r] = e;
+      s.A2[t * ldA + r] = e;
       sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int r = lane; r < a.R; r += 32) s.A2[t * (a.R + 1) + r] *= inv;
+    for (int r = lane; r < a.R; r += 32) s.A2[t * ldA + r] *= inv;
+    if (lane < ldA - a.R) s.A2[t * ldA + a.R + lane] = 0.f;     // pad regions: read by the 128-bit loads below
   }
   __syncthreads();
   // v[c][t] = sum_r a2[t][r] ctx[r][c]: thread per channel (coalesced over c)
@@ -133,16 +148,21 @@ __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float*
   for (int k = 0; k < CPT; ++k)
 #pragma unroll
     for (int t = 0; t < NT; ++t) v[k][t] = 0.f;
-#pragma unroll 8
-  for (int r = 0; r < a.R; ++r) {
+#pragma unroll 2
+  for (int r = 0; r < a.R; r += 4) {     // four regions per step: one 128-bit load of a2[t][r..r+3] feeds four FMAs
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int c = tid + k * DT;
       if (c < a.D) {
-        const float x = __ldg(ctx + (size_t)r * a.D + c);
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = (r + u < a.R) ? __ldg(ctx + (size_t)(r + u) * a.D + c) : 0.f;
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-          if (t < n) v[k][t] = fmaf(x, s.A2[t * (a.R + 1) + r], v[k][t]);
+          if (t < n) {
+            const float4 q = *reinterpret_cast<const float4*>(s.A2 + t * ldA + r);
+            v[k][t] = fmaf(x[0], q.x, fmaf(x[1], q.y, fmaf(x[2], q.z, fmaf(x[3], q.w, v[k][t]))));
+          }
       }
     }
   }
@@ -216,9 +236,10 @@ __global__ void __launch_bounds__(DT) damsm_fwd_kernel(DamsmArgs a) {
     }
   }
   if (a.attn_out) {
+    const int ldA = lda_of(a.R);
     for (int j = tid; j < n * a.R; j += DT) {
       int t = j / a.R, r = j - t * a.R;
-      a.attn_out[(pair * a.Tw + t) * a.R + r] = s.A2[t * (a.R + 1) + r];
+      a.attn_out[(pair * a.Tw + t) * a.R + r] = s.A2[t * ldA + r];
     }
   }
 }
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
   float* dA = s.cosv + 4 * NT;   // [NT][R+1]: d a2 -> d(gamma1*a1) -> reused
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const float* ctx = a.ctx + (size_t)b * a.R * a.D;
-  const int ldw = NT + 1;
+  const int ldw = NT + 1, ldA = lda_of(a.R);
   {
     const int i = blockIdx.y;
     float* dctx = a.dctx + ((size_t)i * a.B + b) * a.R * a.D;
@@ -268,7 +289,7 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
     // write dv to global scratch-free path: use dA as [t][r] accumulators via warp-per-region dot products needs dv by
     // channel across lanes, so stage dv through shared memory in slices of 32 words x D channels: reuse s.red? too small.
     // Use the w buffer layout for dv (D x ldw) in a dedicated region appended after dA.
-    float* dvs = dA + (size_t)NT * (a.R + 1);   // [D][NT+1]
+    float* dvs = dA + (size_t)NT * ldA;   // [D][NT+1]
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int c = tid + k * DT;
@@ -279,22 +300,32 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
       }
     }
     __syncthreads();
-    for (int r = wrp; r < a.R; r += DT / 32) {
-      float acc[NT];
+    for (int r = wrp; r < a.R; r += 2 * (DT / 32)) {
+      const int r1 = r + DT / 32;
+      const bool has1 = r1 < a.R;
+      float acc0[NT], acc1[NT];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+      for (int t = 0; t < NT; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
 #pragma unroll 4
       for (int c = lane; c < a.D; c += 32) {
-        const float x = __ldg(ctx + (size_t)r * a.D + c);
+        const float x0 = __ldg(ctx + (size_t)r * a.D + c);
+        const float x1 = has1 ? __ldg(ctx + (size_t)r1 * a.D + c) : 0.f;
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-          if (t < n) acc[t] = fmaf(x, dvs[c * ldw + t], acc[t]);
+          if (t < n) {
+            const float dvv = dvs[c * ldw + t];
+            acc0[t] = fmaf(x0, dvv, acc0[t]);
+            acc1[t] = fmaf(x1, dvv, acc1[t]);
+          }
       }
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         if (t < n) {
-          float z = warp_sum(acc[t]);
-          if (lane == 0) dA[t * (a.R + 1) + r] = z;   // d a2[t][r]
+          const float z0 = warp_sum(acc0[t]), z1 = warp_sum(acc1[t]);
+          if (lane == 0) {
+            dA[t * ldA + r] = z0;   // d a2[t][r]
+            if (has1) dA[t * ldA + r1] = z1;
+          }
         }
       }
     }
@@ -302,30 +333,44 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
     // softmax-over-regions backward: d(gamma1 a1[r][t]) = a2 (da2 - <a2, da2>)  -> da1 = gamma1 * that
     for (int t = wrp; t < n; t += DT / 32) {
       float dot = 0.f;
-      for (int r = lane; r < a.R; r += 32) dot = fmaf(s.A2[t * (a.R + 1) + r], dA[t * (a.R + 1) + r], dot);
+      for (int r = lane; r < a.R; r += 32) dot = fmaf(s.A2[t * ldA + r], dA[t * ldA + r], dot);
       dot = warp_sum(dot);
       for (int r = lane; r < a.R; r += 32)
-        dA[t * (a.R + 1) + r] = a.g1 * s.A2[t * (a.R + 1) + r] * (dA[t * (a.R + 1) + r] - dot);   // = d a1[r][t]
+        dA[t * ldA + r] = a.g1 * s.A2[t * ldA + r] * (dA[t * ldA + r] - dot);   // = d a1[r][t]
     }
     __syncthreads();
     // softmax-over-words backward (per region): dS[r][t] = a1 (da1 - <a1, da1>), stored back into dA[t][r]
     for (int r = tid; r < a.R; r += DT) {
       float dot = 0.f;
-      for (int t = 0; t < n; ++t) dot = fmaf(s.S[r * ldw + t], dA[t * (a.R + 1) + r], dot);
-      for (int t = 0; t < n; ++t) dA[t * (a.R + 1) + r] = s.S[r * ldw + t] * (dA[t * (a.R + 1) + r] - dot);
+      for (int t = 0; t < n; ++t) dot = fmaf(s.S[r * ldw + t], dA[t * ldA + r], dot);
+      for (int t = 0; t < n; ++t) dA[t * ldA + r] = s.S[r * ldw + t] * (dA[t * ldA + r] - dot);
     }
     __syncthreads();
-    // d ctx[r][c] += sum_t dv_t[c] a2[t][r] + dS[r][t] w[c][t]
-    for (int r = 0; r < a.R; ++r) {
+    // d ctx[r][c] = sum_t dv_t[c] a2[t][r] + dS[r][t] w[c][t]: four regions per step (128-bit loads of a2 / dS), the
+    // thread's word-vector row w[c][:] in registers
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) {
-        const int c = tid + k * DT;
-        if (c < a.D) {
-          float g = 0.f;
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * DT;
+      if (c < a.D) {
+        float wr[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) wr[t] = t < n ? s.w[c * ldw + t] : 0.f;
+        for (int r = 0; r < a.R; r += 4) {
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
           for (int t = 0; t < NT; ++t)
-            if (t < n) g = fmaf(dv[k][t], s.A2[t * (a.R + 1) + r], fmaf(dA[t * (a.R + 1) + r], s.w[c * ldw + t], g));
-          dctx[(size_t)r * a.D + c] = g;
+            if (t < n) {
+              const float4 q = *reinterpret_cast<const float4*>(s.A2 + t * ldA + r);
+              const float4 e = *reinterpret_cast<const float4*>(dA + t * ldA + r);
+              g0 = fmaf(dv[k][t], q.x, fmaf(e.x, wr[t], g0));
+              g1 = fmaf(dv[k][t], q.y, fmaf(e.y, wr[t], g1));
+              g2 = fmaf(dv[k][t], q.z, fmaf(e.z, wr[t], g2));
+              g3 = fmaf(dv[k][t], q.w, fmaf(e.w, wr[t], g3));
+            }
+          dctx[(size_t)r * a.D + c] = g0;
+          if (r + 1 < a.R) dctx[(size_t)(r + 1) * a.D + c] = g1;
+          if (r + 2 < a.R) dctx[(size_t)(r + 2) * a.D + c] = g2;
+          if (r + 3 < a.R) dctx[(size_t)(r + 3) * a.D + c] = g3;
         }
       }
     }
