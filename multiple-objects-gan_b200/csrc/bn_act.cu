@@ -635,8 +635,12 @@ using namespace mog;
 extern "C" int mog_bn_stats(const float* x, int S, int M, int C, double* sum, double* sqsum, void* stream) {
   MOG_REQUIRE(x && sum && sqsum && S > 0 && M > 0 && C > 0, "mog_bn_stats: bad argument");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(sum, 0, sizeof(double) * S * C, st);
-  cudaMemsetAsync(sqsum, 0, sizeof(double) * S * C, st);
+  if (sqsum == sum + (size_t)S * C) {     // the two accumulators back to back (how ops.py allocates them): one memset
+    cudaMemsetAsync(sum, 0, 2 * sizeof(double) * S * C, st);
+  } else {
+    cudaMemsetAsync(sum, 0, sizeof(double) * S * C, st);
+    cudaMemsetAsync(sqsum, 0, sizeof(double) * S * C, st);
+  }
   MOG_REQUIRE(S <= 65535, "mog_bn_stats: too many segments");
   if ((C & 3) == 0) {
     const V4Geom g = v4_geom(C, M, S, true);
@@ -694,8 +698,12 @@ extern "C" int mog_bn_act_bwd_reduce(const float* x, const float* dy, const floa
                                      double* dgamma_seg, double* dbeta_seg, void* stream) {
   MOG_REQUIRE(x && dy && mean && invstd && dgamma_seg && dbeta_seg && S > 0 && M > 0 && C > 0, "mog_bn_act_bwd_reduce: bad argument");
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(dgamma_seg, 0, sizeof(double) * S * C, st);
-  cudaMemsetAsync(dbeta_seg, 0, sizeof(double) * S * C, st);
+  if (dbeta_seg == dgamma_seg + (size_t)S * C) {
+    cudaMemsetAsync(dgamma_seg, 0, 2 * sizeof(double) * S * C, st);
+  } else {
+    cudaMemsetAsync(dgamma_seg, 0, sizeof(double) * S * C, st);
+    cudaMemsetAsync(dbeta_seg, 0, sizeof(double) * S * C, st);
+  }
   const int rpb = rows_per_block(M);
   BnBwdArgs a{x, dy, mean, invstd, gamma, beta, S, M, C, act, rpb};
   if (bwd_v4(true, a, dgamma_seg, dbeta_seg, nullptr, st)) return check_launch("bn_bwd_reduce_v4_kernel");

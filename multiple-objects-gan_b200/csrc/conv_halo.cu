@@ -549,6 +549,14 @@ static int halo_plan(const IGemmParams* gs, int n, int passes, HaloParams* out) 
   const int slotA = nplanes * 2 * p.subA, slotB = nplanes * p.BN * HCH * 2;
   const int budget = 224 * 1024 - 1024 - (p.tma_store ? 4 * HALO_OUT_SLAB : 0);
   int stagesA = ge.halo ? 3 : 2;     // (small-grid form: the weight ring is the one that must run deep)
+  {
+    static int knob = -1;
+    if (knob < 0) {
+      const char* e = getenv("MOG_HALO_STAGES_A");   // tuning knob: depth of the activation ring of the halo form
+      knob = e ? atoi(e) : 0;
+    }
+    if (ge.halo && knob >= 2 && knob <= 6) stagesA = knob;
+  }
   int stagesB = (budget - stagesA * slotA) / slotB;
   if (stagesB < 2) { stagesA = 2; stagesB = (budget - stagesA * slotA) / slotB; }
   if (stagesB < 2) return fail(MOG_ERR_UNSUPPORTED, "conv (halo): BN=%d does not fit the shared-memory rings", p.BN);
