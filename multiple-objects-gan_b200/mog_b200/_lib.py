@@ -111,10 +111,15 @@ def launch_count() -> int:
     return int(lib().mog_launch_count())
 
 
+_fn_cache = {}
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise RuntimeError(mog_last_error()) on failure."""
-    L = lib()
-    rc = getattr(L, name)(*args)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)     # (bound once: a step makes ~2000 of these calls)
+    rc = fn(*args)
     if rc != 0:
-        raise RuntimeError("%s failed (%d): %s" % (name, rc, L.mog_last_error().decode()))
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib().mog_last_error().decode()))
     return rc
