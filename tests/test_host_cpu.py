@@ -120,3 +120,41 @@ def test_bbox_to_theta():
     assert np.allclose(t.numpy(), synth.transformation_matrix(bbox))
     assert np.allclose(ti.numpy(), synth.transformation_matrix_inverse(bbox))
     assert ti[1].tolist() == [[-1.0, 0.0, -4.0], [0.0, -1.0, -4.0]]  # empty slot => fully out of range
+
+
+def test_pack_plan_is_consistent_with_packed_bytes(built):
+    """mog_pack_plan is host-only planning: the entries it emits for (descriptor, direction) must tile exactly the buffer
+    mog_packed_weight_bytes sizes -- hi plane then lo plane per problem, each problem 256-byte aligned -- and carry sane
+    tile grids (the multi-tensor repack kernel trusts them)."""
+    import ctypes as C
+    L = built.lib()
+    cases = [  # N, H, W, Cin, Cout, KH, KW, stride, pad, up2x
+        (4, 16, 16, 96, 96, 3, 3, 1, 1, 1),      # upBlock: four sub-pixel phases
+        (4, 16, 16, 96, 192, 4, 4, 2, 1, 0),     # downBlock: stride phases / parity views
+        (4, 8, 8, 384, 768, 4, 4, 2, 1, 0),
+        (2, 4, 4, 1024, 768, 3, 3, 1, 1, 0),     # jointConv
+        (6, 1, 1, 248, 512, 1, 1, 1, 0, 0),      # Linear
+    ]
+    buf = (built.MogPackEntry * 16)()
+    base = 0x10000
+    for prec in (built.PREC_BF16X3, built.PREC_BF16):
+        planes = 2 if prec == built.PREC_BF16X3 else 1
+        for c in cases:
+            d = built.MogConvDesc(*c, 0, prec, 0)
+            for which in (0, 1):
+                n = L.mog_pack_plan(C.byref(d), which, C.c_void_p(0x1000), C.c_void_p(base), buf, 16)
+                assert n >= 1, (c, which, L.mog_last_error())
+                end = base
+                for i in range(n):
+                    e = buf[i]
+                    assert e.hi == end, (c, which, i)
+                    plane = e.Npad * e.Kpad * 2
+                    assert (e.lo == e.hi + plane) if planes == 2 else (e.lo is None or e.lo == 0)
+                    assert e.K == e.ntaps * e.Cs and e.Kpad >= e.K and e.Kpad % 64 == 0 and e.Cs % 8 == 0
+                    assert e.nxb == (e.Cs + 31) // 32 and e.nyb == (e.Npad + 15) // 16 and 1 <= e.ntaps <= 16
+                    assert all(0 <= e.taps[t][0] < e.KHW for t in range(e.ntaps))
+                    end += (plane * planes + 255) // 256 * 256
+                assert end - base == L.mog_packed_weight_bytes(C.byref(d), which), (c, which)
+    # filters beyond 16 taps are left to mog_pack_weight
+    d = built.MogConvDesc(2, 35, 35, 48, 64, 5, 5, 1, 2, 0, 0, built.PREC_BF16X3, 0)
+    assert L.mog_pack_plan(C.byref(d), 0, C.c_void_p(0x1000), C.c_void_p(base), buf, 16) < 0
