@@ -43,6 +43,19 @@ def _worker(rank, world, port, q):
     for p, lst in zip(net.parameters(), gathered):
         ok &= torch.allclose(p.grad, sum(lst) / world, atol=1e-6)
         ok &= p.grad.data_ptr() >= bucket.flat.data_ptr()
+    # every view starts on a 16-byte boundary of the flat bucket (the fused optimiser's 128-bit path relies on it)
+    for v in bucket.views:
+        ok &= (v.data_ptr() - bucket.flat.data_ptr()) % 16 == 0
+    # finish(scale=False): the bucket stays the SUM over ranks (1/world is folded into the fused Adam pass)
+    net.zero_grad(set_to_none=True)
+    net(x).sum().backward()
+    local2 = [p.grad.clone() for p in net.parameters()]
+    bucket.launch()
+    bucket.finish(scale=False)
+    for p, g in zip(net.parameters(), local2):
+        lst = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(lst, g)
+        ok &= torch.allclose(p.grad, sum(lst), atol=1e-6)
     w0 = [p.detach().clone() for p in net.parameters()]
     ws = [[torch.zeros_like(w) for _ in range(world)] for w in w0]
     for w, lst in zip(w0, ws):
