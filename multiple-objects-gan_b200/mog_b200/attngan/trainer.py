@@ -164,7 +164,7 @@ class condGANTrainer(object):
         return st
 
     def train_step(self, st, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv,
-                   label_one_hot, cap_lens=None, class_ids=None, noise=None, optimize=True):
+                   label_one_hot, cap_lens=None, class_ids=None, noise=None, optimize=True, eps=None):
         """One iteration of trainer.py:294-342: G forward; per D: zero_grad, loss, backward, Adam;
         then G: zero_grad, adversarial (+DAMSM if an image encoder is attached) + KL loss, backward,
         Adam, EMA.  Returns (errD_total, errG_total, kl_loss) as device scalars (no host sync)."""
@@ -173,7 +173,7 @@ class condGANTrainer(object):
         B = sent_emb.shape[0]
         if noise is None:
             noise = torch.empty(B, cfg.GAN.Z_DIM, device=sent_emb.device).normal_(0, 1)
-        fake_imgs, _, mu, logvar = netG(noise, sent_emb, words_embs, mask, transf_matrices_inv, label_one_hot)
+        fake_imgs, _, mu, logvar = netG(noise, sent_emb, words_embs, mask, transf_matrices_inv, label_one_hot, eps=eps)
 
         # (3) update the discriminators
         errD_total = 0

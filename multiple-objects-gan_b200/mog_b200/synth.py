@@ -129,6 +129,16 @@ def fill_state_dict(sd: dict, seed: int) -> dict:
     return out
 
 
+def soften_logits(sd: dict, factor: float = 0.02) -> dict:
+    """Scale the ``outlogits`` weights of a filled discriminator ``state_dict`` in place.  With N(0, 1/fan_in) weights
+    the 4x4 logit convs of the tiny test nets saturate the sigmoid (BCE at its -100 clamp, vanishing and noise-dominated
+    gradients); multi-step fixtures use this to keep the losses in the regime training runs in."""
+    for k, v in sd.items():
+        if "outlogits" in k and k.endswith("weight"):
+            v.mul_(factor)
+    return sd
+
+
 class StandInEncoder:
     """A tiny fixed, differentiable stand-in for the frozen DAMSM image encoder (Inception-v3,
     ``attngan/model.py:207-313``), used so the DAMSM branch of ``generator_loss``

@@ -370,15 +370,18 @@ def leafify(sd):
     return P
 
 
-def gd_step(PG, PDs, cfg, batch, eps=None, PE=None):
+def gd_step(PG, PDs, cfg, batch, eps=None, PE=None, image_encoder=None, after_d=None, noise=None):
     """G forward, three D losses + backward, G adversarial (+ DAMSM when the image-encoder weights ``PE`` are given,
     losses.py:205-224) + KL loss + backward.
     Returns losses, fake images and leaves gradients in ``.grad`` of PG / PDs[i].
     Order follows trainer.py:294-340.  D weight gradients produced by the G-step backward are
-    *not* accumulated (they are discarded by the next zero_grad in the reference, trainer.py:304)."""
+    *not* accumulated (they are discarded by the next zero_grad in the reference, trainer.py:304).
+    ``image_encoder``: a callable img -> (region features, cnn_code) used instead of the Inception-v3 restatement;
+    ``after_d(i)``: called once discriminator i's gradients are in place (trainer.py:317 ``optimizersD[i].step()``)."""
     B = batch["noise"].shape[0]
+    noise = batch["noise"] if noise is None else noise
     real_labels, fake_labels = torch.ones(B), torch.zeros(B)
-    fake_imgs, _, mu, logvar = g_net(PG, cfg, batch["noise"], batch["sent_emb"], batch["words_embs"],
+    fake_imgs, _, mu, logvar = g_net(PG, cfg, noise, batch["sent_emb"], batch["words_embs"],
                                      batch["mask"], batch["transf_matrices_inv"],
                                      batch["label_one_hot"], eps=eps if eps is not None else batch.get("eps"))
     errDs = []
@@ -392,13 +395,18 @@ def gd_step(PG, PDs, cfg, batch, eps=None, PE=None):
         for p, g in zip(params, grads):
             p.grad = g
         errDs.append(errD.detach())
+        if after_d is not None:
+            after_d(i)
     errG = generator_gan_loss(PDs, cfg, fake_imgs, batch["sent_emb"], real_labels,
                               batch["label_one_hot"], batch["transf_matrices"],
                               batch["transf_matrices_inv"])
-    if PE is not None:
-        from .encoder_oracle import cnn_encoder
+    if PE is not None or image_encoder is not None:
         match = torch.arange(B)
-        region, code = cnn_encoder(PE, fake_imgs[-1])
+        if image_encoder is not None:
+            region, code = image_encoder(fake_imgs[-1])
+        else:
+            from .encoder_oracle import cnn_encoder
+            region, code = cnn_encoder(PE, fake_imgs[-1])
         w0, w1 = words_loss(region, batch["words_embs"], match, batch["cap_lens"], batch["class_ids"], B, cfg)[:2]
         s0, s1 = sent_loss(code, batch["sent_emb"], match, batch["class_ids"], B, cfg)
         errG = errG + (w0 + w1) * cfg.LAMBDA + (s0 + s1) * cfg.LAMBDA
@@ -409,3 +417,24 @@ def gd_step(PG, PDs, cfg, batch, eps=None, PE=None):
         p.grad = g
     return {"errD": errDs, "errG": errG.detach(), "kl": kl.detach(),
             "fake_imgs": [f.detach() for f in fake_imgs], "mu": mu.detach(), "logvar": logvar.detach()}
+
+
+def make_train_state(PG, PDs, lr=2e-4):
+    """trainer.py:139-160,251 -- Adam(lr, betas=(0.5, 0.999)) per network and the EMA copy of the G parameters."""
+    gp = [p for p in PG.values() if p.requires_grad]
+    return {"optG": torch.optim.Adam(gp, lr=lr, betas=(0.5, 0.999)),
+            "optDs": [torch.optim.Adam([p for p in PD.values() if p.requires_grad], lr=lr, betas=(0.5, 0.999)) for PD in PDs],
+            "ema": [p.detach().clone() for p in gp], "gparams": gp}
+
+
+def train_step(PG, PDs, state, cfg, batch, eps=None, noise=None, PE=None, image_encoder=None):
+    """One iteration of trainer.py:294-342 including the optimiser steps (each D right after its backward, so the G
+    step sees the UPDATED discriminators) and the EMA of the generator (trainer.py:341-342)."""
+    def after_d(i):
+        state["optDs"][i].step()
+    out = gd_step(PG, PDs, cfg, batch, eps=eps, PE=PE, image_encoder=image_encoder, after_d=after_d, noise=noise)
+    state["optG"].step()
+    with torch.no_grad():
+        for p, a in zip(state["gparams"], state["ema"]):
+            a.mul_(0.999).add_(p.detach(), alpha=0.001)
+    return out

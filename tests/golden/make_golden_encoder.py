@@ -18,7 +18,7 @@ import torch.nn as nn
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference/code/coco/attngan"
-sys.path[:0] = [os.path.join(HERE, "_shims"), REF, os.path.join(ROOT, "multiple-objects-gan_b200"), os.path.join(ROOT, "tests")]
+sys.path[:0] = [os.path.join(ROOT, "baseline", "shims"), REF, os.path.join(ROOT, "multiple-objects-gan_b200"), os.path.join(ROOT, "tests")]
 torch.cuda.FloatTensor = torch.FloatTensor
 
 from mog_b200 import synth  # noqa: E402

@@ -24,7 +24,7 @@ stage = int(sys.argv[1])
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference/code/coco/stackgan"
-sys.path[:0] = [os.path.join(HERE, "_shims"), REF, os.path.join(ROOT, "multiple-objects-gan_b200"), os.path.join(ROOT, "tests")]
+sys.path[:0] = [os.path.join(ROOT, "baseline", "shims"), REF, os.path.join(ROOT, "multiple-objects-gan_b200"), os.path.join(ROOT, "tests")]
 torch.cuda.FloatTensor = torch.FloatTensor
 torch.cuda.DoubleTensor = torch.DoubleTensor
 

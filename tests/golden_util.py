@@ -78,3 +78,27 @@ def save(name, entries, meta):
     with open(os.path.join(here, name + ".json"), "w") as f:
         json.dump({"meta": meta, "index": index}, f, indent=1, sort_keys=True)
     print("wrote", name, "entries", len(entries), "bytes", os.path.getsize(os.path.join(here, name + ".npz")))
+
+
+class Aggregate:
+    """Norm-weighted rel-L2 over a group of tensors (e.g. all Adam moments of one network): tensors whose reference is
+    tiny (cancelling gradients) cannot dominate the way they do in a per-tensor maximum."""
+
+    def __init__(self):
+        self.num = self.den = 0.0
+        self.worst = (0.0, "")
+
+    def add(self, t, summ, name=""):
+        a = t.detach().cpu().double().numpy().reshape(-1)
+        ref = np.asarray(summ["full"] if "full" in summ else summ["sample"], np.float64)
+        got = a if "full" in summ else a[_idx(a.size)]
+        scale = a.size / ref.size          # a sample stands for the whole tensor
+        self.num += scale * float(((got - ref) ** 2).sum())
+        self.den += scale * float((ref ** 2).sum())
+        e = rel_l2(got, ref)
+        if e > self.worst[0]:
+            self.worst = (e, name)
+        return e
+
+    def rel(self):
+        return float(np.sqrt(self.num / max(self.den, 1e-60)))

@@ -153,3 +153,54 @@ def test_public_api_shapes_and_reference_signatures():
     p = netsD[0].COND_DNET(f, b["sent_emb"])
     q = netsD[0].UNCOND_DNET(f)
     assert p.shape == (2,) and q.shape == (2,) and float(p.min()) > 0 and float(p.max()) < 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_train_step_matches_reference(precision):
+    """a20 -- the function bench.py times: three consecutive ``condGANTrainer.train_step`` calls (G forward, per D:
+    pair pass + backward + fused Adam + repack, G loss incl. the DAMSM branch, backward, fused Adam + EMA) against the
+    reference's trainer.py:294-342 executed with ``optim.Adam`` (tests/golden/make_golden_trainstep.py): parameters,
+    EMA copy, Adam moments and BatchNorm buffers after the third step, the losses of every step."""
+    from mog_b200 import ops
+    from mog_b200.attngan import model as M
+    from mog_b200.attngan.trainer import condGANTrainer
+    from test_oracle_golden import check_train_state
+    G, meta = gu.load("attngan_tiny_trainstep")
+    c, seed, K = meta["cfg"], meta["seed"], meta["steps"]
+    cfg = _set_cfg(c)
+    cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2, cfg.TRAIN.SMOOTH.GAMMA3, cfg.TRAIN.SMOOTH.LAMBDA = 4.0, 5.0, 10.0, 50.0
+    old = ops.get_precision()
+    ops.set_precision(precision)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False      # the stand-in encoder is a torch conv (test infrastructure)
+    try:
+        netG = M.G_NET()
+        netsD = [M.D_NET64(), M.D_NET128(), M.D_NET256()]
+        netG.load_state_dict(synth.fill_state_dict(netG.state_dict(), seed + 1))
+        for i, d in enumerate(netsD):
+            d.load_state_dict(synth.soften_logits(synth.fill_state_dict(d.state_dict(), seed + 2 + i), meta["logit_scale"]))
+        netG.cuda().train()
+        for d in netsD:
+            d.cuda().train()
+        tr = condGANTrainer("", None, 0, None)
+        tr.image_encoder = synth.StandInEncoder(c["EMBEDDING_DIM"], device="cuda")
+        optG, optDs = tr.define_optimizers(netG, netsD)
+        st = tr.make_step_state(netG, netsD, optG, optDs)
+        b = _dev(synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed))
+        tol = 2e-4 if precision == "fp32" else 5e-4
+        for k in range(K):
+            noise = torch.from_numpy(np.random.RandomState(seed + 10 + k).standard_normal((c["B"], c["Z_DIM"])).astype(np.float32)).cuda()
+            errD, errG, kl = tr.train_step(st, b["imgs"], b["sent_emb"], b["words_embs"], b["mask"], b["transf_matrices"],
+                                           b["transf_matrices_inv"], b["label_one_hot"], b["cap_lens"], b["class_ids"],
+                                           noise=noise, eps=gu.full(G, "step%d/eps" % k).cuda())
+            gu.check(errD, G["step%d/errD_total" % k], tol, "errD step %d" % k)
+            gu.check(errG, G["step%d/errG_total" % k], tol, "errG step %d" % k)
+            gu.check(kl, G["step%d/kl" % k], tol, "kl step %d" % k)
+        nets = {"G": (dict(netG.state_dict(keep_vars=True)), optG.state)}
+        for i, d in enumerate(netsD):
+            nets["D%d" % i] = (dict(d.state_dict(keep_vars=True)), optDs[i].state)
+        ema = dict(zip([n for n, _ in netG.named_parameters()], st["avg_param_G"]))
+        check_train_state(G, nets, ema, scale=1.0 if precision == "fp32" else 2.0)
+    finally:
+        ops.set_precision(old)
+        torch.backends.cudnn.allow_tf32 = tf32

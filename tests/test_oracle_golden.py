@@ -146,3 +146,61 @@ def test_attngan_gd_only_step(keys):
     for k, p in PG.items():
         if p.requires_grad:
             gu.check(p.grad, G["G/grad/%s" % k], 2e-4, "G grad %s" % k)
+
+
+def test_train_steps_with_adam_and_ema(keys):
+    """a20: three consecutive iterations of trainer.py:294-342 INCLUDING the optimiser steps (each discriminator is
+    updated before the generator step sees it), the DAMSM branch and the EMA: the oracle's ``train_step`` against the
+    executed reference (tests/golden/make_golden_trainstep.py)."""
+    G, meta = gu.load("attngan_tiny_trainstep")
+    c, seed, K = meta["cfg"], meta["seed"], meta["steps"]
+    cfg = _tiny_cfg(c)
+    PG = _build(keys["tiny"]["G_NET"], seed + 1)
+    PDs = []
+    for i in range(3):
+        shapes = {k: torch.empty(s) for k, s in keys["tiny"]["D_NET%d" % (64 << i)].items()}
+        PDs.append(O.leafify(synth.soften_logits(synth.fill_state_dict(shapes, seed + 2 + i), meta["logit_scale"])))
+    batch = synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed)
+    enc = synth.StandInEncoder(c["EMBEDDING_DIM"])
+    state = O.make_train_state(PG, PDs)
+    for k in range(K):
+        noise = torch.from_numpy(np.random.RandomState(seed + 10 + k).standard_normal((c["B"], c["Z_DIM"])).astype(np.float32))
+        out = O.train_step(PG, PDs, state, cfg, batch, eps=gu.full(G, "step%d/eps" % k), noise=noise, image_encoder=enc)
+        gu.check(sum(out["errD"]), G["step%d/errD_total" % k], 1e-4, "errD step %d" % k)
+        gu.check(out["errG"] + out["kl"], G["step%d/errG_total" % k], 1e-4, "errG step %d" % k)
+        gu.check(out["kl"], G["step%d/kl" % k], 1e-4, "kl step %d" % k)
+    check_train_state(G, {"G": (PG, state["optG"].state), "D0": (PDs[0], state["optDs"][0].state),
+                          "D1": (PDs[1], state["optDs"][1].state), "D2": (PDs[2], state["optDs"][2].state)},
+                      dict(zip([n for n, p in PG.items() if p.requires_grad], state["ema"])))
+
+
+# Gates of the after-K-steps comparison.  One Adam step moves every weight by ~lr = 2e-4 whatever the size of its
+# gradient (m / sqrt(v) = +-1 at t = 1), so summation-order noise on near-zero gradient entries shows up at full size in
+# those elements: fp32-vs-fp32 restatements of the same step differ by up to 1.2e-4 per parameter tensor (5e-5 per network)
+# and up to 2e-2 in the moments of single tensors whose gradient nearly cancels (6e-4 per network; measured: oracle vs
+# reference, both CPU fp32).  A missing or doubled update would be >= 6e-3 on the parameters and O(1) on the moments.
+TS_PARAM, TS_PARAM_NET, TS_MOM_NET, TS_MOM, TS_EMA, TS_BUF = 5e-4, 2e-4, 2e-3, 0.05, 1e-5, 2e-4
+
+
+def check_train_state(G, nets, ema, scale=1.0):
+    """nets: tag -> (name -> tensor incl. buffers, param tensor -> Adam state); ema: G param name -> EMA tensor."""
+    for tag, (P, ostate) in nets.items():
+        ap, am, av = gu.Aggregate(), gu.Aggregate(), gu.Aggregate()
+        for name, p in P.items():
+            if ("%s/param/%s" % (tag, name)) in G:
+                e = ap.add(p, G["%s/param/%s" % (tag, name)], name)
+                assert e <= scale * TS_PARAM, "%s param %s: %.3e" % (tag, name, e)
+                s = ostate[p]
+                e = am.add(s["exp_avg"], G["%s/exp_avg/%s" % (tag, name)], name)
+                assert e <= scale * TS_MOM, "%s exp_avg %s: %.3e" % (tag, name, e)
+                e = av.add(s["exp_avg_sq"], G["%s/exp_avg_sq/%s" % (tag, name)], name)
+                assert e <= scale * TS_MOM, "%s exp_avg_sq %s: %.3e" % (tag, name, e)
+            elif ("%s/buf/%s" % (tag, name)) in G:
+                gu.check(p.float(), G["%s/buf/%s" % (tag, name)], scale * TS_BUF, "%s buffer %s" % (tag, name))
+        assert ap.rel() <= scale * TS_PARAM_NET, "%s params: %.3e (worst %s)" % (tag, ap.rel(), ap.worst)
+        assert am.rel() <= scale * TS_MOM_NET, "%s exp_avg: %.3e (worst %s)" % (tag, am.rel(), am.worst)
+        assert av.rel() <= scale * TS_MOM_NET, "%s exp_avg_sq: %.3e (worst %s)" % (tag, av.rel(), av.worst)
+        print(tag, "params %.2e (worst %.2e)  exp_avg %.2e (worst %.2e)  exp_avg_sq %.2e (worst %.2e)"
+              % (ap.rel(), ap.worst[0], am.rel(), am.worst[0], av.rel(), av.worst[0]))
+    for name, a in ema.items():
+        gu.check(a, G["G/ema/%s" % name], TS_EMA, "ema %s" % name)

@@ -19,7 +19,7 @@ import torch.nn as nn
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = "/root/reference/code/coco/attngan"
-sys.path[:0] = [os.path.join(ROOT, "tests", "golden", "_shims"), REF, os.path.join(ROOT, "multiple-objects-gan_b200")]
+sys.path[:0] = [os.path.join(ROOT, "baseline", "shims"), REF, os.path.join(ROOT, "multiple-objects-gan_b200")]
 torch.cuda.FloatTensor = torch.FloatTensor
 nn.parallel.data_parallel = lambda m, i, d=None, **k: m(*i) if isinstance(i, tuple) else m(i)
 import torch.utils.model_zoo as model_zoo  # noqa: E402
