@@ -208,7 +208,7 @@ def run_mog(args):
         for p in enc.parameters():
             p.requires_grad = False
         enc.to(dev).eval()
-    _, _, netG, netsD, _ = tr.build_models(image_encoder=enc)   # weights_init (orthogonal) on device, broadcast from rank 0
+    _, _, netG, netsD, _ = tr.build_models(image_encoder=enc, load_encoders=False)   # weights_init (orthogonal) on device, broadcast from rank 0
     optG, optDs = tr.define_optimizers(netG, netsD)
     st = tr.make_step_state(netG, netsD, optG, optDs)
 

@@ -32,6 +32,8 @@ def compute_transformation_matrix(bbox):
 
 
 def weights_init(m):
+    from ... import ops
+    ops.invalidate_packed(m.parameters(recurse=False))     # .data writes below are invisible to torch's version counter
     classname = m.__class__.__name__
     if classname.find('Conv') != -1:
         nn.init.orthogonal_(m.weight.data, 1.0)
@@ -45,8 +47,10 @@ def weights_init(m):
 
 
 def load_params(model, new_param):
+    from ... import ops
     for p, new_p in zip(model.parameters(), new_param):
         p.data.copy_(new_p)
+    ops.invalidate_packed(model)      # the packed conv operands of every weight are stale now
 
 
 def copy_G_params(model):

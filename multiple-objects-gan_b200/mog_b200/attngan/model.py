@@ -135,6 +135,59 @@ class BBOX_NET(nn.Module):
 
 
 # ############## DAMSM image encoder ###################
+class RNN_ENCODER(nn.Module):
+    """Frozen DAMSM text encoder (model.py:120-204): embedding -> dropout -> bidirectional LSTM / GRU over the packed captions;
+    ``words_emb`` [B, nhidden, T] are the per-token outputs, ``sent_emb`` [B, nhidden] the final hidden states of both
+    directions.  Same constructor, ``init_hidden`` / ``forward`` signatures and ``state_dict`` keys (``encoder.weight``,
+    ``rnn.weight_ih_l0`` ...) as the reference, so ``text_encoder*.pth`` checkpoints load unchanged.  It runs before the
+    G/D hot path, once per batch, frozen and in eval mode (trainer.py:78-88): a <= 18-token recurrence with B x 128 states
+    is host-side plumbing here (torch's LSTM), not a libmog kernel -- SURVEY.md section 8(f) row f3."""
+
+    def __init__(self, ntoken, ninput=300, drop_prob=0.5, nhidden=128, nlayers=1, bidirectional=True):
+        super().__init__()
+        self.n_steps = cfg.TEXT.WORDS_NUM
+        self.ntoken, self.ninput, self.drop_prob, self.nlayers = ntoken, ninput, drop_prob, nlayers
+        self.bidirectional = bidirectional
+        self.rnn_type = cfg.RNN_TYPE
+        self.num_directions = 2 if bidirectional else 1
+        self.nhidden = nhidden // self.num_directions
+        self.define_module()
+        self.init_weights()
+
+    def define_module(self):
+        self.encoder = nn.Embedding(self.ntoken, self.ninput)
+        self.drop = nn.Dropout(self.drop_prob)
+        if self.rnn_type not in ('LSTM', 'GRU'):
+            raise NotImplementedError
+        rnn = nn.LSTM if self.rnn_type == 'LSTM' else nn.GRU
+        # (dropout between stacked layers only applies for nlayers > 1; torch warns for 1 layer exactly as in the reference)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.rnn = rnn(self.ninput, self.nhidden, self.nlayers, batch_first=True, dropout=self.drop_prob,
+                           bidirectional=self.bidirectional)
+
+    def init_weights(self):
+        self.encoder.weight.data.uniform_(-0.1, 0.1)
+
+    def init_hidden(self, bsz):
+        weight = next(self.parameters())
+        z = lambda: weight.new_zeros(self.nlayers * self.num_directions, bsz, self.nhidden)   # noqa: E731
+        return (z(), z()) if self.rnn_type == 'LSTM' else z()
+
+    def forward(self, captions, cap_lens, hidden, mask=None):
+        from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+        emb = self.drop(self.encoder(captions))
+        lens = cap_lens.detach().cpu().tolist() if torch.is_tensor(cap_lens) else list(cap_lens)
+        emb = pack_padded_sequence(emb, lens, batch_first=True)
+        output, hidden = self.rnn(emb, hidden)
+        output = pad_packed_sequence(output, batch_first=True)[0]
+        words_emb = output.transpose(1, 2)
+        h = hidden[0] if self.rnn_type == 'LSTM' else hidden
+        sent_emb = h.transpose(0, 1).contiguous().view(-1, self.nhidden * self.num_directions)
+        return words_emb, sent_emb
+
+
 class CNN_ENCODER(nn.Module):
     """model.py:207-313 -- frozen Inception-v3 trunk (torchvision layer names, see ``inception.py``) + the two
     trainable-in-DAMSM-pretraining projections ``emb_features`` (1x1 conv 768 -> nef on the 17x17 region map) and

@@ -13,9 +13,10 @@ Differences, all behind the same results:
   discards them, trainer.py:271,328);
 * no ``.item()`` host syncs inside the step: losses are returned as device scalars.
 
-Sampling / visualisation (trainer.py:201-247, 368-667) and the frozen DAMSM encoders
-(``build_models`` 56-84) are outside the hot path; ``build_models`` accepts
-pre-built encoders instead of loading them from ``cfg.TRAIN.NET_E``.
+``build_models`` loads the frozen DAMSM encoders from ``cfg.TRAIN.NET_E`` like trainer.py:56-88 (or takes pre-built
+ones); ``train()`` runs as the reference's ``main.py:152`` calls it (no arguments).  ``sampling`` / ``sample`` /
+``gen_example`` (trainer.py:387-667) generate images from a checkpoint with the generator in eval mode; the attention-map
+collages of ``save_img_results`` / ``build_super_images`` (host-side PIL drawing) are not reproduced.
 """
 from __future__ import annotations
 
@@ -31,11 +32,16 @@ from .. import parallel
 from .miscc.config import cfg
 from .miscc.losses import KL_loss, discriminator_loss, format_logs, generator_loss
 from .miscc.utils import copy_G_params, load_params, mkdir_p, weights_init
-from .model import D_NET64, D_NET128, D_NET256, G_NET
+from .model import CNN_ENCODER, D_NET64, D_NET128, D_NET256, G_NET, RNN_ENCODER
 
 
 class condGANTrainer(object):
     def __init__(self, output_dir, data_loader, n_words, ixtoword, resume=False):
+        # one process per GPU: under torchrun this joins the process group and selects cuda:LOCAL_RANK (a no-op for a
+        # plain ``python main.py`` launch); cfg.MOG.PRECISION selects the conv operand precision (default bf16x3)
+        from .. import ops
+        parallel.init_from_env()
+        ops.precision_from_cfg(cfg)
         if cfg.TRAIN.FLAG and output_dir:
             self.model_dir = os.path.join(output_dir, 'Model')
             self.image_dir = os.path.join(output_dir, 'Image')
@@ -46,6 +52,8 @@ class condGANTrainer(object):
         self.snapshot_interval = cfg.TRAIN.SNAPSHOT_INTERVAL
         self.resume = resume
         self.gpus = [int(ix) for ix in str(cfg.GPU_ID).split(',')]
+        if cfg.CUDA and torch.cuda.is_available() and parallel.world() == 1:
+            torch.cuda.set_device(self.gpus[0])       # trainer.py:50 (torchrun ranks use LOCAL_RANK instead)
         self.n_words = n_words
         self.ixtoword = ixtoword
         self.data_loader = data_loader
@@ -55,8 +63,35 @@ class condGANTrainer(object):
         self.image_encoder = None
 
     # ------------------------------------------------------------------ models / optimisers
-    def build_models(self, text_encoder=None, image_encoder=None):
-        """trainer.py:53-137.  Returns [text_encoder, image_encoder, netG, netsD, epoch]."""
+    def _load_encoders(self):
+        """trainer.py:56-88 -- frozen CNN_ENCODER / RNN_ENCODER from ``cfg.TRAIN.NET_E`` (the text-encoder checkpoint; the
+        image encoder's path is derived from it), eval mode."""
+        if cfg.TRAIN.NET_E == '':
+            raise RuntimeError("cfg.TRAIN.NET_E is empty: no pretrained DAMSM text / image encoders (trainer.py:56-58). "
+                               "Pass encoders to build_models(text_encoder=..., image_encoder=...) or set "
+                               "train(damsm=False) explicitly to train without the DAMSM terms.")
+        image_encoder = CNN_ENCODER(cfg.TEXT.EMBEDDING_DIM)
+        img_encoder_path = cfg.TRAIN.NET_E.replace('text_encoder', 'image_encoder')
+        image_encoder.load_state_dict(torch.load(img_encoder_path, map_location='cpu'))
+        text_encoder = RNN_ENCODER(self.n_words, nhidden=cfg.TEXT.EMBEDDING_DIM)
+        text_encoder.load_state_dict(torch.load(cfg.TRAIN.NET_E, map_location='cpu'))
+        for enc in (image_encoder, text_encoder):
+            for p in enc.parameters():
+                p.requires_grad = False
+            enc.eval()
+            if cfg.CUDA:
+                enc.cuda()
+        return text_encoder, image_encoder
+
+    def build_models(self, text_encoder=None, image_encoder=None, load_encoders=True):
+        """trainer.py:53-137.  Returns [text_encoder, image_encoder, netG, netsD, epoch].  Encoders that were passed in (here
+        or to an earlier call) are kept; otherwise they are loaded from ``cfg.TRAIN.NET_E`` as in the reference."""
+        text_encoder = text_encoder if text_encoder is not None else self.text_encoder
+        image_encoder = image_encoder if image_encoder is not None else self.image_encoder
+        if load_encoders and (text_encoder is None or image_encoder is None):
+            te, ie = self._load_encoders()
+            text_encoder = text_encoder if text_encoder is not None else te
+            image_encoder = image_encoder if image_encoder is not None else ie
         netsD = []
         netG = G_NET()
         if cfg.TREE.BRANCH_NUM > 0:
@@ -232,34 +267,227 @@ class condGANTrainer(object):
         return errD_total, errG_total.detach(), kl_loss.detach()
 
     # ------------------------------------------------------------------ epoch loop
-    def train(self, prepare_data=None, text_encoder=None, image_encoder=None):
-        """trainer.py:249-366.  ``data_loader`` must yield what the reference's ``prepare_data``
-        consumes (datasets.py:28-68) unless a custom ``prepare_data`` callable is given; caption
-        embeddings come from ``text_encoder`` (frozen)."""
+    def encode_text(self, text_encoder, captions, cap_lens):
+        """trainer.py:281-289 -- frozen text encoder, caption mask trimmed to the longest caption of the batch."""
+        hidden = text_encoder.init_hidden(captions.size(0))
+        with torch.no_grad():
+            words_embs, sent_emb = text_encoder(captions, cap_lens, hidden)
+        words_embs, sent_emb = words_embs.detach(), sent_emb.detach()
+        mask = (captions == 0)
+        num_words = words_embs.size(2)
+        if mask.size(1) > num_words:
+            mask = mask[:, :num_words]
+        return words_embs, sent_emb, mask
+
+    def train(self, prepare_data=None, text_encoder=None, image_encoder=None, damsm=True, max_steps=None):
+        """trainer.py:249-366, callable exactly as ``main.py:152`` does (``algo.train()``): the frozen DAMSM encoders come
+        from ``cfg.TRAIN.NET_E``, batches go through ``datasets.prepare_data``.  Optional arguments: a custom
+        ``prepare_data`` callable, pre-built encoders, ``damsm=False`` to train WITHOUT the DAMSM words / sentence terms
+        (never silently: without encoders and without this flag ``build_models`` raises), ``max_steps`` to stop early."""
+        if prepare_data is None:
+            from .datasets import prepare_data
         text_encoder, image_encoder, netG, netsD, start_epoch = self.build_models(text_encoder, image_encoder)
+        if not damsm:
+            self.image_encoder = None
         optimizerG, optimizersD = self.define_optimizers(netG, netsD)
         st = self.make_step_state(netG, netsD, optimizerG, optimizersD)
         gen_iterations = 0
         errD = errG = torch.zeros(())
         epoch = start_epoch
+        done = False
         for epoch in range(start_epoch, self.max_epoch):
             start_t = time.time()
             for data in self.data_loader:
                 imgs, captions, cap_lens, class_ids, keys, tms, label_one_hot = prepare_data(data)
-                hidden = text_encoder.init_hidden(self.batch_size)
-                with torch.no_grad():
-                    words_embs, sent_emb = text_encoder(captions, cap_lens, hidden)
-                mask = (captions == 0)
-                if mask.size(1) > words_embs.size(2):
-                    mask = mask[:, :words_embs.size(2)]
+                words_embs, sent_emb, mask = self.encode_text(text_encoder, captions, cap_lens)
                 errD, errG, _ = self.train_step(st, imgs, sent_emb, words_embs, mask, tms[0], tms[1],
                                                 label_one_hot, cap_lens, class_ids)
                 gen_iterations += 1
                 if gen_iterations % 1000 == 0 and parallel.rank() == 0:
                     print(format_logs(st["last_logs"]))
+                if max_steps is not None and gen_iterations >= max_steps:
+                    done = True
+                    break
             if parallel.rank() == 0:
                 print('[%d/%d][%d] Loss_D: %.2f Loss_G: %.2f Time: %.2fs'
                       % (epoch, self.max_epoch, self.num_batches, float(errD), float(errG), time.time() - start_t))
+            if done:
+                break
             if epoch % cfg.TRAIN.SNAPSHOT_INTERVAL == 0:
                 self.save_model(netG, st["avg_param_G"], netsD, optimizerG, optimizersD, epoch)
-        self.save_model(netG, st["avg_param_G"], netsD, optimizerG, optimizersD, epoch)
+        if getattr(self, "model_dir", None):
+            self.save_model(netG, st["avg_param_G"], netsD, optimizerG, optimizersD, epoch)
+        return st
+
+    # ------------------------------------------------------------------ sampling (generator in eval mode)
+    def _load_text_encoder(self):
+        text_encoder = RNN_ENCODER(self.n_words, nhidden=cfg.TEXT.EMBEDDING_DIM)
+        text_encoder.load_state_dict(torch.load(cfg.TRAIN.NET_E, map_location='cpu'))
+        if cfg.CUDA:
+            text_encoder.cuda()
+        return text_encoder.eval()
+
+    def _load_generator(self):
+        """trainer.py:392-420 -- G_NET from the checkpoint dict written by ``save_model`` (``state_dict["netG"]`` = EMA weights)."""
+        netG = G_NET()
+        state_dict = torch.load(cfg.TRAIN.NET_G, map_location='cpu')
+        netG.load_state_dict(state_dict["netG"] if "netG" in state_dict else state_dict)
+        if cfg.CUDA:
+            netG.cuda()
+        return netG.eval()
+
+    @staticmethod
+    def _to_uint8_hwc(img_chw):
+        """[-1, 1] float CHW -> uint8 HWC exactly as trainer.py:453-457."""
+        import numpy as np
+        im = img_chw.detach().float().cpu().numpy()
+        im = ((im + 1.0) * 127.5).astype(np.uint8)
+        return np.transpose(im, (1, 2, 0))
+
+    def save_singleimages(self, images, filenames, save_dir, split_dir, sentenceID=0):
+        """trainer.py:368-385"""
+        from PIL import Image
+        for i in range(images.size(0)):
+            s_tmp = '%s/single_samples/%s/%s' % (save_dir, split_dir, filenames[i])
+            folder = s_tmp[:s_tmp.rfind('/')]
+            if not os.path.isdir(folder):
+                mkdir_p(folder)
+            img = images[i].add(1).div(2).mul(255).clamp(0, 255).byte()
+            Image.fromarray(img.permute(1, 2, 0).contiguous().cpu().numpy()).save('%s_%d.jpg' % (s_tmp, sentenceID))
+
+    def sampling(self, split_dir, num_samples=30000, prepare_data=None):
+        """trainer.py:387-459 -- one 256^2 image per caption of the loader, saved as ``<NET_G>/<split>/single/<key>_s-1.png``."""
+        from PIL import Image
+        if cfg.TRAIN.NET_G == '':
+            print('Error: the path for morels is not found!')
+            return None
+        if prepare_data is None:
+            from .datasets import prepare_data
+        if split_dir == 'test':
+            split_dir = 'valid'
+        netG = self._load_generator()
+        text_encoder = self.text_encoder if self.text_encoder is not None else self._load_text_encoder()
+        nz = cfg.GAN.Z_DIM
+        model_dir = cfg.TRAIN.NET_G
+        save_dir = '%s/%s' % (model_dir[:model_dir.rfind('.pth')], split_dir)
+        mkdir_p(save_dir)
+        written = []
+        for step, data in enumerate(self.data_loader, 0):
+            if step >= num_samples:
+                break
+            imgs, captions, cap_lens, class_ids, keys, tms, label_one_hot = prepare_data(data)
+            words_embs, sent_emb, mask = self.encode_text(text_encoder, captions, cap_lens)
+            noise = torch.empty(captions.size(0), nz, device=sent_emb.device).normal_(0, 1)
+            with torch.no_grad():
+                fake_imgs, _, _, _ = netG(noise, sent_emb, words_embs, mask, tms[1], label_one_hot)
+            for j in range(captions.size(0)):
+                s_tmp = '%s/single/%s' % (save_dir, keys[j])
+                folder = s_tmp[:s_tmp.rfind('/')]
+                if not os.path.isdir(folder):
+                    mkdir_p(folder)
+                k = -1
+                fullpath = '%s_s%d.png' % (s_tmp, k)
+                Image.fromarray(self._to_uint8_hwc(fake_imgs[k][j])).save(fullpath)
+                written.append(fullpath)
+        return written
+
+    def sample(self, split_dir, num_samples=25, draw_bbox=False, prepare_data=None):
+        """trainer.py:461-579 -- per loader batch: the first caption, 9 noise draws, one row [real | 9 fakes] (optionally with
+        the bounding boxes drawn), saved as ``<NET_G>_<split>/<caption>_<step>.png``."""
+        import torchvision.utils as vutils
+        if cfg.TRAIN.NET_G == '':
+            print('Error: the path for model NET_G is not found!')
+            return None
+        if prepare_data is None:
+            from .datasets import prepare_data
+        if split_dir == 'test':
+            split_dir = 'valid'
+        text_encoder = self.text_encoder if self.text_encoder is not None else self._load_text_encoder()
+        netG = self._load_generator()
+        nz = cfg.GAN.Z_DIM
+        model_dir = cfg.TRAIN.NET_G
+        save_dir = '%s_%s' % (model_dir[:model_dir.rfind('.pth')], split_dir)
+        mkdir_p(save_dir)
+        imsize = cfg.TREE.BASE_SIZE * (2 ** (cfg.TREE.BRANCH_NUM - 1))
+        written = []
+        for step, data in enumerate(self.data_loader, 0):
+            if step >= num_samples:
+                break
+            imgs, captions, cap_lens, class_ids, keys, tms, label_one_hot, bbox = prepare_data(data, eval=True)
+            transf_matrices_inv = tms[1][0].unsqueeze(0).repeat(9, 1, 1, 1)
+            label9 = label_one_hot[0].unsqueeze(0).repeat(9, 1, 1)
+            val_image = imgs[-1][0].reshape(1, 3, imsize, imsize)
+            words_embs, sent_emb, mask = self.encode_text(text_encoder, captions, cap_lens)
+            words_embs = words_embs[0].unsqueeze(0).repeat(9, 1, 1)
+            sent_emb = sent_emb[0].unsqueeze(0).repeat(9, 1)
+            mask = mask[0].unsqueeze(0).repeat(9, 1)
+            noise = torch.empty(9, nz, device=sent_emb.device).normal_(0, 1)
+            with torch.no_grad():
+                fake_imgs, _, _, _ = netG(noise, sent_emb, words_embs, mask, transf_matrices_inv, label9)
+            data_img = torch.zeros(10, 3, imsize, imsize)
+            data_img[0] = val_image.cpu()
+            data_img[1:10] = fake_imgs[-1].detach().float().cpu()
+            if draw_bbox:
+                for idx in range(bbox.shape[1]):
+                    x, y, w, h = tuple([int(imsize * float(v)) for v in bbox[0, idx]])
+                    w = imsize - 1 if w > imsize - 1 else w
+                    h = imsize - 1 if h > imsize - 1 else h
+                    if x <= -1:
+                        break
+                    x2, y2 = min(x + w, imsize - 1), min(y + h, imsize - 1)
+                    data_img[:10, :, y, x:x + w] = 1
+                    data_img[:10, :, y:y + h, x] = 1
+                    data_img[:10, :, y2, x:x + w] = 1
+                    data_img[:10, :, y:y + h, x2] = 1
+            cap = captions[0].detach().cpu().numpy()
+            words = []
+            for j in range(len(cap)):
+                if cap[j] == 0:
+                    break
+                words.append(str(self.ixtoword[int(cap[j])]).encode('ascii', 'ignore').decode('ascii'))
+            path = '{}/{}_{}.png'.format(save_dir, " ".join(words), step)
+            vutils.save_image(data_img, path, normalize=True, nrow=10)
+            written.append(path)
+        print("Saved {} files to {}".format(len(written), save_dir))
+        return written
+
+    def gen_example(self, data_dic, transf_matrices_inv=None, label_one_hot=None):
+        """trainer.py:581-667 -- images for hand-written captions: ``data_dic[key] = [cap_array, cap_lens, sorted_indices]``.
+        The reference calls ``netG(noise, sent_emb, words_embs, mask)`` here (trainer.py:636), which its own
+        ``G_NET.forward`` (six arguments) rejects; this version takes the layout as optional arguments and defaults to an
+        EMPTY layout (three empty slots: bbox -1 => theta^-1 = [[-1,0,-4],[0,-1,-4]], label 80), i.e. the global pathway only."""
+        from PIL import Image
+        from .miscc.utils import compute_transformation_matrix_inverse
+        if cfg.TRAIN.NET_G == '':
+            print('Error: the path for morels is not found!')
+            return None
+        text_encoder = self.text_encoder if self.text_encoder is not None else self._load_text_encoder()
+        netG = self._load_generator()
+        s_tmp = cfg.TRAIN.NET_G[:cfg.TRAIN.NET_G.rfind('.pth')]
+        dev = next(netG.parameters()).device
+        written = []
+        for key in data_dic:
+            save_dir = '%s/%s' % (s_tmp, key)
+            mkdir_p(save_dir)
+            captions, cap_lens, sorted_indices = data_dic[key]
+            batch_size = captions.shape[0]
+            captions = torch.as_tensor(captions).to(dev)
+            cap_lens = torch.as_tensor(cap_lens.copy() if hasattr(cap_lens, "copy") else cap_lens).to(dev)
+            tmi, onehot = transf_matrices_inv, label_one_hot
+            if tmi is None:
+                empty = -torch.ones(batch_size * 3, 4)
+                tmi = compute_transformation_matrix_inverse(empty).view(batch_size, 3, 2, 3).to(dev)
+            if onehot is None:
+                onehot = torch.zeros(batch_size, 3, 81, device=dev)
+                onehot[:, :, 80] = 1.0
+            words_embs, sent_emb, mask = self.encode_text(text_encoder, captions, cap_lens)
+            noise = torch.empty(batch_size, cfg.GAN.Z_DIM, device=dev).normal_(0, 1)
+            with torch.no_grad():
+                fake_imgs, attention_maps, _, _ = netG(noise, sent_emb, words_embs, mask, tmi, onehot)
+            for j in range(batch_size):
+                save_name = '%s/%d_s_%d' % (save_dir, 0, sorted_indices[j])
+                for k in range(len(fake_imgs)):
+                    fullpath = '%s_g%d.png' % (save_name, k)
+                    Image.fromarray(self._to_uint8_hwc(fake_imgs[k][j])).save(fullpath)
+                    written.append(fullpath)
+        return written

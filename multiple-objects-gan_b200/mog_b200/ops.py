@@ -16,13 +16,28 @@ from ._lib import (ACT_GLU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH
 
 import ctypes as C
 
-_default_precision = PREC_NAMES[os.environ.get("MOG_PRECISION", "fp32")]
+# Product default: bf16x3 (tcgen05, fp32-equivalent: meets the 1e-3 end-to-end bound).  MOG_PRECISION / cfg.MOG.PRECISION
+# (applied by the trainers through ``set_precision``) / ``set_precision`` override it; 'fp32' is the CUDA-core parity mode.
+_default_precision = PREC_NAMES[os.environ.get("MOG_PRECISION", "bf16x3")]
 
 
 def set_precision(name: str):
     """Operand precision of the convolution kernels: 'fp32' | 'bf16x3' | 'bf16'."""
     global _default_precision
+    if isinstance(name, int) and name in PREC_NAMES.values():      # a value returned by get_precision()
+        _default_precision = name
+        return
+    if name not in PREC_NAMES:
+        raise ValueError("unknown precision %r (expected one of %s)" % (name, sorted(PREC_NAMES)))
     _default_precision = PREC_NAMES[name]
+
+
+def precision_from_cfg(cfg):
+    """``cfg.MOG.PRECISION`` -> the conv operand precision (called by the trainers' constructors); the environment
+    variable MOG_PRECISION, when set, wins (A/B runs without editing YAML files)."""
+    name = os.environ.get("MOG_PRECISION") or str(getattr(getattr(cfg, "MOG", None), "PRECISION", "") or "bf16x3")
+    set_precision(name)
+    return name
 
 
 def get_precision() -> int:
@@ -136,6 +151,15 @@ def _packed(weight: torch.Tensor, which: str, d: MogConvDesc, dkey=None) -> torc
         call("mog_pack_weight", C.byref(d), wi, w.data_ptr(), ent["out"].data_ptr(), _stream())
         ent["ver"] = ver
     return ent["out"]
+
+
+def invalidate_packed(module_or_params):
+    """Mark the packed GEMM operands of the given parameters stale.  Needed after any write that bypasses both torch's
+    version counter and ``mog_b200.optim.Adam``: ``p.data.copy_(...)`` / ``p.data.normal_()`` / ``dist.broadcast(p.data)``
+    do not bump ``p._version`` (``load_params``, ``weights_init`` and ``parallel.broadcast_params`` call this)."""
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    for p in params:
+        p._mog_ver = getattr(p, "_mog_ver", 0) + 1
 
 
 _repack_tables = {}
@@ -422,7 +446,7 @@ def bn_act(x, bn, act=ACT_NONE, residual=None, segments=1):
     """Apply a train-mode ``nn.BatchNorm*d``-compatible module ``bn`` (weight, bias,
     running_mean, running_var, num_batches_tracked, momentum, eps) followed by ``act``."""
     if not bn.training:
-        raise RuntimeError("libmog implements the training path (batch statistics) only")
+        return _bn_act_eval(x, bn, act, residual)
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked += segments
     # in the tensor-core precisions the apply kernel also emits y as pre-split bf16 planes: the usual consumer is a conv
@@ -438,9 +462,32 @@ def bn_act(x, bn, act=ACT_NONE, residual=None, segments=1):
     return y
 
 
+def _bn_act_eval(x, bn, act, residual):
+    """Inference form (``netG.eval()`` in sampling / gen_example, trainer.py:399,504,599): y = act(x * scale + shift) with
+    the running statistics folded into per-channel scale / shift; forward only."""
+    if torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad):
+        raise RuntimeError("libmog: eval-mode BatchNorm is forward-only (sampling); wrap the call in torch.no_grad()")
+    _chk(x, "bn input")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    with torch.no_grad():
+        scale = (bn.weight * torch.rsqrt(bn.running_var + bn.eps)).contiguous()
+        shift = (bn.bias - bn.running_mean * scale).contiguous()
+        Co = Cc // 2 if act == ACT_GLU else Cc
+        y = torch.empty(x.shape[:-1] + (Co,), device=x.device, dtype=torch.float32)
+        if residual is not None:
+            _chk(residual, "bn residual")
+        call("mog_affine_act_fwd", x.data_ptr(), scale.data_ptr(), shift.data_ptr(), _ptr(residual), y.data_ptr(), 1, rows, Cc,
+             act, _stream())
+    return y
+
+
 # ---------------------------------------------------------------------------------------------
 # spatial transformer
 # ---------------------------------------------------------------------------------------------
+_STN_CHECK = os.environ.get("MOG_DEBUG", "0") == "1"
+
+
 class StnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, theta, extra, mode, B, S, Ho, Wo, align):
@@ -450,6 +497,10 @@ class StnFn(torch.autograd.Function):
         n_in, Hi, Wi, Cc = x.shape
         if theta.shape != (B, S, 2, 3):
             raise RuntimeError("stn: theta must be [B,S,2,3], got %s" % (tuple(theta.shape),))
+        if _STN_CHECK and bool((theta[..., 0, 1] != 0).any() | (theta[..., 1, 0] != 0).any()):
+            # (host sync: only with MOG_DEBUG=1) the backward kernel builds separable row / column tables
+            raise RuntimeError("stn: only axis-aligned theta (no rotation / shear terms) is supported, as produced by "
+                               "compute_transformation_matrix[_inverse] (miscc/utils.py:16-49)")
         if n_in != (S * B if mode == 0 else B):
             raise RuntimeError("stn: input batch %d inconsistent with mode %d, B=%d, S=%d" % (n_in, mode, B, S))
         Cy = Cc
@@ -504,7 +555,9 @@ class WordAttnFn(torch.autograd.Function):
         attn = torch.empty((B, T, Q), device=h.device, dtype=torch.float32) if want_attn else None
         m = None
         if mask is not None:
-            m = mask.to(torch.uint8).contiguous()
+            if mask.dim() != 2 or mask.shape[0] != B or mask.shape[1] < T:
+                raise RuntimeError("word attention: mask must be [B=%d, >=T=%d], got %s" % (B, T, tuple(mask.shape)))
+            m = mask[:, :T].to(torch.uint8).contiguous()   # a caption mask wider than the word embeddings is trimmed (trainer.py:288-289)
         call("mog_word_attention_fwd", h.data_ptr(), src.data_ptr(), _ptr(m), out.data_ptr(), _ptr(attn),
              B, Q, D, T, int(quirk), _stream())
         ctx.cfg = (B, Q, D, T, int(quirk))

@@ -44,6 +44,10 @@ class Adam(torch.optim.Optimizer):
             step = None
             for p in group["params"]:
                 if p.grad is None:
+                    # no Adam update, but the reference's EMA loop (trainer.py:341-342) still averages every parameter
+                    e = ema_params.get(p) if ema_params is not None else None
+                    if e is not None:
+                        e.mul_(ema_decay).add_(p.detach(), alpha=1.0 - ema_decay)
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("mog_b200.optim.Adam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)")

@@ -93,3 +93,5 @@ def broadcast_params(module, src=0):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src)
+    from . import ops
+    ops.invalidate_packed(module)

@@ -235,6 +235,7 @@ def compute_generator_loss(netD, fake_imgs, real_labels, local_label, transf_mat
 
 
 def weights_init(m):
+    ops.invalidate_packed(m.parameters(recurse=False))     # .data writes below are invisible to torch's version counter
     """multi-mnist/miscc/utils.py:127-137 -- N(0, 0.02) by class name."""
     classname = m.__class__.__name__
     if classname.find('Conv') != -1:

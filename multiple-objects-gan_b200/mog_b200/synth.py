@@ -268,3 +268,32 @@ def encoder_probe(B: int, nef: int, seed: int):
     pf = rng.standard_normal((B, nef, 17, 17)).astype(np.float32)
     pc = rng.standard_normal((B, nef)).astype(np.float32)
     return torch.from_numpy(img), torch.from_numpy(pf), torch.from_numpy(pc)
+
+
+class SyntheticTextDataset(torch.utils.data.Dataset):
+    """Stand-in for the reference's ``TextDataset`` (``attngan/datasets.py:71-399``, COCO files + PIL decoding): yields the
+    same per-sample tuple -- ``(imgs [3 x (3,S,S)], caption (WORDS_NUM,1) int64, cap_len, class_id, key,
+    [theta (3,2,3), theta^-1 (3,2,3)], label one-hot (3,81)[, bbox (3,4)])`` -- from seeded random data, so that
+    ``DataLoader`` -> ``prepare_data`` -> ``condGANTrainer.train`` can be driven end to end without the dataset files."""
+
+    def __init__(self, n=8, n_words=40, words_num=18, seed=0, eval=False, sizes=(64, 128, 256)):
+        self.n, self.n_words, self.words_num, self.seed, self.eval, self.sizes = n, n_words, words_num, seed, eval, sizes
+        self.ixtoword = {i: ("w%d" % i) for i in range(1, n_words)}
+        self.ixtoword[0] = "<end>"
+        self.wordtoix = {v: k for k, v in self.ixtoword.items()}
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, index):
+        rng = np.random.RandomState(self.seed * 100003 + index)
+        imgs = [torch.from_numpy(rng.uniform(-1, 1, size=(3, s, s)).astype(np.float32)) for s in self.sizes]
+        ln = int(rng.randint(3, self.words_num + 1))
+        cap = np.zeros((self.words_num, 1), np.int64)
+        cap[:ln, 0] = rng.randint(1, self.n_words, size=ln)
+        bbox, label, onehot, theta, theta_inv = bboxes_and_labels(rng, 1)
+        out = (imgs, cap, ln, index, "img%04d" % index, [torch.from_numpy(theta[0]), torch.from_numpy(theta_inv[0])],
+               torch.from_numpy(onehot[0]))
+        if self.eval:
+            out = out + (torch.from_numpy(bbox[0]),)
+        return out

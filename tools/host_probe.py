@@ -14,7 +14,7 @@ tr = condGANTrainer("", None, 0, None)
 enc = CNN_ENCODER(256); enc.load_state_dict(synth.fill_encoder_state_dict(enc.state_dict(), 9))
 for p in enc.parameters(): p.requires_grad = False
 enc.cuda().eval()
-_, _, netG, netsD, _ = tr.build_models(image_encoder=enc)
+_, _, netG, netsD, _ = tr.build_models(image_encoder=enc, load_encoders=False)
 h = synth.attngan_batch(B, seed=1234)
 d = {k: v.cuda() for k, v in h.items() if torch.is_tensor(v)}
 imgs = [t.cuda() for t in h["imgs"]]

@@ -20,7 +20,7 @@ if os.environ.get("MOG_NO_DAMSM", "0") != "1":
     for p in enc.parameters():
         p.requires_grad = False
     enc.cuda().eval()
-_, _, netG, netsD, _ = tr.build_models(image_encoder=enc)
+_, _, netG, netsD, _ = tr.build_models(image_encoder=enc, load_encoders=False)
 optG, optDs = tr.define_optimizers(netG, netsD)
 st = tr.make_step_state(netG, netsD, optG, optDs)
 h = synth.attngan_batch(B, seed=1234)
