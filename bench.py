@@ -256,12 +256,23 @@ def run_mog(args):
             ms = float(t)
         return ms
 
-    for _ in range(W):
-        step(d, imgs)
-    n0 = _lib.launch_count()
-    with ClockSampler(local) as cs:
-        ms = timed(lambda: step(d, imgs), K)
-    launches = _lib.launch_count() - n0
+    gs = None
+    if not args.no_graph:
+        # the whole step as ONE CUDA graph (condGANTrainer.graphed_step): its eager warm-up steps count as warm-up
+        gs = tr.graphed_step(st, imgs, d["sent_emb"], d["words_embs"], d["mask"], d["transf_matrices"], d["transf_matrices_inv"],
+                             d["label_one_hot"], host["cap_lens"], host["class_ids"], warmup=max(1, min(W, 2)))
+        for _ in range(max(0, W - 2)):
+            gs.replay()
+        with ClockSampler(local) as cs:
+            ms = timed(gs.replay, K)
+        launches = gs.launches * K
+    else:
+        for _ in range(W):
+            step(d, imgs)
+        n0 = _lib.launch_count()
+        with ClockSampler(local) as cs:
+            ms = timed(lambda: step(d, imgs), K)
+        launches = _lib.launch_count() - n0
     clocks = cs.summary()
     host_enqueue_ms = host_ms[0]
     value = ws * B * K / (ms / 1e3)
@@ -270,8 +281,12 @@ def run_mog(args):
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        dd, ii = upload()
-        eD, eG, kl = step(dd, ii)
+        if gs is not None:   # pinned host -> the graph's static input buffers, replay, losses back
+            eD, eG, kl = gs(pinned_imgs, pinned["sent_emb"], pinned["words_embs"], pinned["mask"], pinned["transf_matrices"],
+                            pinned["transf_matrices_inv"], pinned["label_one_hot"], host["cap_lens"], host["class_ids"])
+        else:
+            dd, ii = upload()
+            eD, eG, kl = step(dd, ii)
         loss_host.copy_(torch.stack((eD, eG, kl)), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -298,7 +313,8 @@ def run_mog(args):
                 "config": {"workload": workload(args), "batch_per_gpu": B, "global_batch": ws * B, "words": CFG5["T"],
                            "parallelism": "dp%d (NCCL grad all-reduce per net)" % ws,
                            "precision": args.precision, "l2": "working set per step (>5 GB) exceeds the 126 MB L2; no flush needed",
-                           "optimizer": "fused libmog Adam + EMA (mog_adam_multi) inside the timed region",
+                           "optimizer": "fused libmog Adam + EMA (mog_adam_multi_dev) inside the timed region",
+                           "cuda_graph": gs is not None,
                            "algorithmic_gflop_per_image": 2 * gmac(args),
                            "step_tflops_achieved": 2 * gmac(args) * 1e9 * value / 1e12},
                 "clocks": clocks, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
@@ -359,6 +375,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
     ap.add_argument("--precision", default=os.environ.get("MOG_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph of the step")
     ap.add_argument("--no-damsm", action="store_true", help="time the G+D-only step (no DAMSM loss / Inception-v3 encoder)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mog":

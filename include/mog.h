@@ -248,6 +248,12 @@ int mog_sigmoid_bce_bwd(const float* z, const float* target /*[n]*/, float weigh
 int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
                    const long long* numel, double lr, double beta1, double beta2, double eps, long long step,
                    double ema_decay, float grad_scale, void* stream);
+/* Same with the step count in DEVICE memory (one double, the number of steps taken so far): the call first increments
+ * *step_dev, then forms the bias corrections from it on the device, in double, like the host form.  No argument changes from
+ * step to step, so a CUDA graph that captured the call replays the whole optimiser step (trainer.py:326,340 inside the graph). */
+int mog_adam_multi_dev(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
+                       const long long* numel, double lr, double beta1, double beta2, double eps, double* step_dev,
+                       double ema_decay, float grad_scale, void* stream);
 
 /* ---- pooling / resize of the DAMSM image encoder -------------------------------------------- */
 /* replaces: F.max_pool2d(x, 3, 2) (attngan/model.py:264,271; Mixed_6a/7a of torchvision's Inception-v3),

@@ -30,28 +30,39 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int M, int C, int r
   const long long r_begin = (long long)blockIdx.y * rpb;
   long long r_end = r_begin + rpb;
   if (r_end > M) r_end = M;
+  // Shifted sums: the fp32 partials accumulate d = x - x0 (x0 = the channel's value in the first row of the segment), so
+  // that sum(x^2)/M - mean^2 does not cancel for channels whose mean is large against their spread (measured: mean/std = 300
+  // lost 3 digits of the variance with plain fp32 partials; torch uses Welford).  The shift is folded back exactly in double.
   float a = 0.f, b = 0.f;
+  float x0 = 0.f;
+  int n = 0;
   if (c < C) {
     const float* xp = x + ((size_t)s * M) * C + c;
+    x0 = __ldg(xp);
     for (long long r = r_begin + rl; r < r_end; r += RED_ROWS) {
-      float v = __ldg(xp + (size_t)r * C);
+      float v = __ldg(xp + (size_t)r * C) - x0;
       a += v;
       b = fmaf(v, v, b);
+      ++n;
     }
   }
   __shared__ float sa[RED_ROWS][33], sb[RED_ROWS][33];
+  __shared__ int sn[RED_ROWS][33];
   sa[rl][lane] = a;
   sb[rl][lane] = b;
+  sn[rl][lane] = n;
   __syncthreads();
   if (rl == 0 && c < C) {
-    double ta = 0.0, tb = 0.0;
+    double ta = 0.0, tb = 0.0, tn = 0.0;
 #pragma unroll
     for (int i = 0; i < RED_ROWS; ++i) {
       ta += (double)sa[i][lane];
       tb += (double)sb[i][lane];
+      tn += (double)sn[i][lane];
     }
-    atomicAdd(sum + (size_t)s * C + c, ta);
-    atomicAdd(sqsum + (size_t)s * C + c, tb);
+    const double s0 = (double)x0;
+    atomicAdd(sum + (size_t)s * C + c, ta + tn * s0);
+    atomicAdd(sqsum + (size_t)s * C + c, tb + 2.0 * s0 * ta + tn * s0 * s0);
   }
 }
 
@@ -383,19 +394,28 @@ __global__ void bn_stats_v4_kernel(const float* __restrict__ x, int M, int C, V4
   double v[2][4] = {{0., 0., 0., 0.}, {0., 0., 0., 0.}};
   if (valid) {
     const float* xp = x + ((size_t)s * M) * C + c;
+    // shifted sums (see bn_stats_kernel): fp32 partials of d = x - x0, folded back exactly in double
+    float x0[4];
+    to_arr(ld4(xp), x0);
     for (long long r_begin = (long long)blockIdx.y * g.rpb; r_begin < M; r_begin += (long long)gridDim.y * g.rpb) {
       long long r_end = r_begin + g.rpb;
       if (r_end > M) r_end = M;
       float f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // fp32 over <= rpb / R rows, then folded into the doubles
+      int n = 0;
 #pragma unroll 8
       for (long long r = r_begin + rl; r < r_end; r += g.R) {
         float a[4];
         to_arr(ld4(xp + (size_t)r * C), a);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { f[0][j] += a[j]; f[1][j] = fmaf(a[j], a[j], f[1][j]); }
+        for (int j = 0; j < 4; ++j) { const float dd = a[j] - x0[j]; f[0][j] += dd; f[1][j] = fmaf(dd, dd, f[1][j]); }
+        ++n;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[0][j] += (double)f[0][j]; v[1][j] += (double)f[1][j]; }
+      for (int j = 0; j < 4; ++j) {
+        const double s0 = (double)x0[j], fa = (double)f[0][j];
+        v[0][j] += fa + (double)n * s0;
+        v[1][j] += (double)f[1][j] + 2.0 * s0 * fa + (double)n * s0 * s0;
+      }
     }
   }
   double* const dst[2] = {sum + (size_t)s * C + c, sqsum + (size_t)s * C + c};

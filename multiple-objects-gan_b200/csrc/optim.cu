@@ -49,8 +49,32 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
   if (ema) *ema = *ema * s.ema_decay + s.ema_in * p;
 }
 
+// Hyper-parameters of the device-step form: the step count lives in device memory (a CUDA graph replays the launch with
+// fixed arguments, so nothing that changes from step to step may be a kernel parameter), the bias corrections are formed
+// from it in double by one thread per block -- the same arithmetic the host form does.
+struct AdamHyper {
+  double lr, beta1, beta2;
+  const double* step;   // null: use the host-computed scalars
+};
+
+__global__ void adam_step_inc_kernel(double* step) { *step += 1.0; }
+
 template <bool VEC>
-__global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const __grid_constant__ AdamTensors T, const __grid_constant__ AdamScalars S) {
+__global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const __grid_constant__ AdamTensors T, const __grid_constant__ AdamScalars S0,
+                                                                  const __grid_constant__ AdamHyper H) {
+  __shared__ AdamScalars sS;
+  if (H.step != nullptr) {
+    if (threadIdx.x == 0) {
+      AdamScalars q = S0;
+      const double t = *H.step;
+      const double bc1 = 1.0 - pow(H.beta1, t), bc2 = 1.0 - pow(H.beta2, t);
+      q.bc2_sqrt = (float)sqrt(bc2);
+      q.neg_step = (float)(-H.lr / bc1);
+      sS = q;
+    }
+    __syncthreads();
+  }
+  const AdamScalars& S = H.step != nullptr ? sS : S0;
   // which tensor does this block belong to (uniform scan over <= 56 entries)
   int t = 0;
   while (t + 1 < T.n && (int)blockIdx.x >= T.block_start[t + 1]) ++t;
@@ -106,14 +130,22 @@ using namespace mog;
 
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-extern "C" int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
-                              const long long* numel, double lr, double beta1, double beta2, double eps, long long step,
-                              double ema_decay, float grad_scale, void* stream) {
+static int adam_multi_impl(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
+                           const long long* numel, double lr, double beta1, double beta2, double eps, long long step, double* step_dev,
+                           double ema_decay, float grad_scale, void* stream) {
   MOG_REQUIRE(n >= 0 && (n == 0 || (p && g && m && v && numel)), "mog_adam_multi: null array");
-  MOG_REQUIRE(step >= 1, "mog_adam_multi: step must be >= 1 (the step being taken)");
+  MOG_REQUIRE(step_dev || step >= 1, "mog_adam_multi: step must be >= 1 (the step being taken)");
   MOG_REQUIRE(lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., "mog_adam_multi: bad hyper-parameter");
   cudaStream_t st = as_stream(stream);
   AdamScalars S;
+  AdamHyper H;
+  H.lr = lr; H.beta1 = beta1; H.beta2 = beta2; H.step = step_dev;
+  if (step_dev) {
+    step = 1;   // (placeholder for the host-side scalars below; the kernel recomputes them from *step_dev)
+    adam_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+    int rc0 = check_launch("adam_step_inc_kernel");
+    if (rc0) return rc0;
+  }
   // hyper-parameters arrive as doubles (Python floats): 1 - beta must be formed in double like torch does, not from
   // the rounded fp32 beta (1 - float(0.999) is off by 1.3e-5 relative)
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
@@ -148,11 +180,24 @@ extern "C" int mog_adam_multi(int n, float* const* p, const float* const* g, flo
     T.block_start[k] = blocks;
     T.n = k;
     if (vec)
-      adam_multi_kernel<true><<<(unsigned)blocks, ADAM_THREADS, 0, st>>>(T, S);
+      adam_multi_kernel<true><<<(unsigned)blocks, ADAM_THREADS, 0, st>>>(T, S, H);
     else
-      adam_multi_kernel<false><<<(unsigned)blocks, ADAM_THREADS, 0, st>>>(T, S);
+      adam_multi_kernel<false><<<(unsigned)blocks, ADAM_THREADS, 0, st>>>(T, S, H);
     int rc = check_launch("adam_multi_kernel");
     if (rc) return rc;
   }
   return MOG_OK;
+}
+
+extern "C" int mog_adam_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
+                              const long long* numel, double lr, double beta1, double beta2, double eps, long long step,
+                              double ema_decay, float grad_scale, void* stream) {
+  return adam_multi_impl(n, p, g, m, v, ema, numel, lr, beta1, beta2, eps, step, nullptr, ema_decay, grad_scale, stream);
+}
+
+extern "C" int mog_adam_multi_dev(int n, float* const* p, const float* const* g, float* const* m, float* const* v, float* const* ema,
+                                  const long long* numel, double lr, double beta1, double beta2, double eps, double* step_dev,
+                                  double ema_decay, float grad_scale, void* stream) {
+  MOG_REQUIRE(step_dev != nullptr, "mog_adam_multi_dev: null step counter");
+  return adam_multi_impl(n, p, g, m, v, ema, numel, lr, beta1, beta2, eps, 0, step_dev, ema_decay, grad_scale, stream);
 }

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mog_resize_bilinear_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_resize_bilinear_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_adam_multi": (_i, [_i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_longlong, C.c_double, _f, _p]),
+    "mog_adam_multi_dev": (_i, [_i, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, _p, C.c_double, _f, _p]),
 }
 
 _lib = None

@@ -109,12 +109,20 @@ def KL_loss(mu, logvar):
 
 
 def _class_masks(class_ids, batch_size, device):
-    """losses.py:24-34 -- mis-match samples of the same class are masked out of the negatives."""
+    """losses.py:24-34 -- mis-match samples of the same class are masked out of the negatives.  ``class_ids`` may already be
+    the B x B boolean mask on the device (``class_mask`` below: built once per batch, outside a captured CUDA graph)."""
+    if torch.is_tensor(class_ids) and class_ids.dtype == torch.bool and class_ids.dim() == 2:
+        return class_ids
     import numpy as np
     ids = np.asarray(class_ids)
     m = (ids[:, None] == ids[None, :])
     m[np.arange(batch_size), np.arange(batch_size)] = False
     return torch.from_numpy(m).to(device)
+
+
+def class_mask(class_ids, batch_size, device):
+    """The B x B mask of ``_class_masks`` as a device tensor (host -> device copy happens here, once per batch)."""
+    return _class_masks(class_ids, batch_size, device)
 
 
 def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size):

@@ -30,7 +30,7 @@ import torch.optim as optim
 from .. import optim as mog_optim
 from .. import parallel
 from .miscc.config import cfg
-from .miscc.losses import KL_loss, discriminator_loss, format_logs, generator_loss
+from .miscc.losses import KL_loss, class_mask, discriminator_loss, format_logs, generator_loss
 from .miscc.utils import copy_G_params, load_params, mkdir_p, weights_init
 from .model import CNN_ENCODER, D_NET64, D_NET128, D_NET256, G_NET, RNN_ENCODER
 
@@ -266,6 +266,16 @@ class condGANTrainer(object):
         st["last_logs"] = logs
         return errD_total, errG_total.detach(), kl_loss.detach()
 
+    # ------------------------------------------------------------------ CUDA-graph form of the step
+    def graphed_step(self, st, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv, label_one_hot,
+                     cap_lens=None, class_ids=None, warmup=2, pool=None, noise=None, eps=None, dry_warmup=False):
+        """Capture :meth:`train_step` (for these tensor shapes) into one CUDA graph: ~2000 kernel launches, the gradient
+        all-reduces and the four fused optimiser steps replay with a single ``cudaGraphLaunch`` and no Python in between
+        (the host needs ~40 ms to enqueue a step it takes the device less than that to run).  Returns a
+        :class:`GraphedStep`; call it with the next batch's tensors."""
+        return GraphedStep(self, st, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv, label_one_hot,
+                           cap_lens, class_ids, warmup=warmup, pool=pool, noise=noise, eps=eps, dry_warmup=dry_warmup)
+
     # ------------------------------------------------------------------ epoch loop
     def encode_text(self, text_encoder, captions, cap_lens):
         """trainer.py:281-289 -- frozen text encoder, caption mask trimmed to the longest caption of the batch."""
@@ -295,13 +305,25 @@ class condGANTrainer(object):
         errD = errG = torch.zeros(())
         epoch = start_epoch
         done = False
+        use_graph = bool(cfg.MOG.CUDA_GRAPH) and cfg.CUDA and torch.cuda.is_available()
+        graphs, pool = {}, None     # one captured graph per caption length T (words_embs is B x nef x T), one memory pool
         for epoch in range(start_epoch, self.max_epoch):
             start_t = time.time()
             for data in self.data_loader:
                 imgs, captions, cap_lens, class_ids, keys, tms, label_one_hot = prepare_data(data)
                 words_embs, sent_emb, mask = self.encode_text(text_encoder, captions, cap_lens)
-                errD, errG, _ = self.train_step(st, imgs, sent_emb, words_embs, mask, tms[0], tms[1],
-                                                label_one_hot, cap_lens, class_ids)
+                if use_graph:
+                    key = (tuple(words_embs.shape), tuple(imgs[-1].shape))
+                    g = graphs.get(key)
+                    if g is None:
+                        if pool is None:
+                            pool = torch.cuda.graph_pool_handle()
+                        g = graphs[key] = self.graphed_step(st, imgs, sent_emb, words_embs, mask, tms[0], tms[1], label_one_hot,
+                                                            cap_lens, class_ids, pool=pool)
+                    errD, errG, _ = g(imgs, sent_emb, words_embs, mask, tms[0], tms[1], label_one_hot, cap_lens, class_ids)
+                else:
+                    errD, errG, _ = self.train_step(st, imgs, sent_emb, words_embs, mask, tms[0], tms[1],
+                                                    label_one_hot, cap_lens, class_ids)
                 gen_iterations += 1
                 if gen_iterations % 1000 == 0 and parallel.rank() == 0:
                     print(format_logs(st["last_logs"]))
@@ -491,3 +513,90 @@ class condGANTrainer(object):
                     Image.fromarray(self._to_uint8_hwc(fake_imgs[k][j])).save(fullpath)
                     written.append(fullpath)
         return written
+
+
+class GraphedStep:
+    """One ``condGANTrainer.train_step`` captured as a CUDA graph (fixed shapes).  The inputs live in static device buffers
+    that every call refreshes (device-to-device or pinned-host-to-device copies on the current stream), the three returned
+    losses and ``st["last_logs"]`` are static outputs.  Everything that changes from step to step is device-resident: the
+    noise and CA_NET draws come from torch's graph-safe generator, Adam's step count from ``mog_adam_multi_dev``.
+    The warm-up steps it runs eagerly before capturing ARE training steps (they update the networks with the given batch)
+    unless ``dry_warmup=True``: then they run without the optimiser steps and the BatchNorm running statistics are restored,
+    so capturing leaves the training state untouched (needs optimiser state from at least one earlier real step)."""
+
+    def __init__(self, trainer, st, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv, label_one_hot,
+                 cap_lens=None, class_ids=None, warmup=2, pool=None, noise=None, eps=None, dry_warmup=False):
+        self.trainer, self.st = trainer, st
+        dev = sent_emb.device
+        B = sent_emb.shape[0]
+        self.B = B
+        self.static = {
+            "imgs": [t.detach().to(dev).clone() for t in imgs],
+            "sent_emb": sent_emb.detach().clone(), "words_embs": words_embs.detach().clone(), "mask": mask.detach().clone(),
+            "transf_matrices": transf_matrices.detach().clone(), "transf_matrices_inv": transf_matrices_inv.detach().clone(),
+            "label_one_hot": label_one_hot.detach().clone(),
+            "cap_lens": None if cap_lens is None else torch.as_tensor(cap_lens).to(device=dev, dtype=torch.int32).clone(),
+            "class_mask": None if class_ids is None else class_mask(class_ids, B, dev).clone(),
+            # optional: injected noise / CA_NET draw as static inputs (parity tests); None = drawn inside the graph
+            "noise": None if noise is None else noise.detach().clone(), "eps": None if eps is None else eps.detach().clone(),
+        }
+        s = self.static
+        self.opts = [o for o in [st["optG"]] + list(st["optDs"]) if isinstance(o, mog_optim.Adam)]
+
+        def run(optimize=True):
+            return trainer.train_step(st, s["imgs"], s["sent_emb"], s["words_embs"], s["mask"], s["transf_matrices"],
+                                      s["transf_matrices_inv"], s["label_one_hot"], s["cap_lens"], s["class_mask"],
+                                      noise=s["noise"], eps=s["eps"], optimize=optimize)
+
+        self.launches = 0
+        saved = None
+        if dry_warmup:
+            saved = [(bf, bf.detach().clone()) for net in [st["netG"]] + list(st["netsD"]) for bf in net.buffers()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):     # >= 1: optimiser state and every lazily packed operand must exist
+                run(optimize=not dry_warmup)
+            if saved is not None:
+                for bf, v in saved:
+                    bf.copy_(v)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from .. import _lib
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, pool=pool):
+            self.out = run()
+        self.launches = _lib.launch_count() - n0      # libmog kernels per replay
+        self.logs = st.get("last_logs")
+        # the capture pass executed no kernel, but the host-side step counts moved: take that step back
+        for o in self.opts:
+            o.advance_host_steps(-1)
+
+    def __call__(self, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv, label_one_hot, cap_lens=None,
+                 class_ids=None, noise=None, eps=None):
+        s = self.static
+        for k, v in (("noise", noise), ("eps", eps)):
+            if s[k] is not None:
+                s[k].copy_(v, non_blocking=True)
+        for dst, src in zip(s["imgs"], imgs):
+            dst.copy_(src, non_blocking=True)
+        for k, v in (("sent_emb", sent_emb), ("words_embs", words_embs), ("mask", mask), ("transf_matrices", transf_matrices),
+                     ("transf_matrices_inv", transf_matrices_inv), ("label_one_hot", label_one_hot)):
+            s[k].copy_(v, non_blocking=True)
+        if s["cap_lens"] is not None:
+            s["cap_lens"].copy_(torch.as_tensor(cap_lens), non_blocking=True)
+        if s["class_mask"] is not None:
+            s["class_mask"].copy_(class_mask(class_ids, self.B, s["class_mask"].device), non_blocking=True)
+        self.graph.replay()
+        for o in self.opts:
+            o.advance_host_steps(1)
+        self.st["last_logs"] = self.logs
+        return self.out
+
+    def replay(self):
+        """Replay on the batch already in the static buffers."""
+        self.graph.replay()
+        for o in self.opts:
+            o.advance_host_steps(1)
+        return self.out

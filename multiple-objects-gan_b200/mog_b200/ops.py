@@ -276,8 +276,13 @@ def _alloc_planes(shape, precision, device):
     return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
 
 
+_NO_PRODUCER_PLANES = os.environ.get("MOG_NO_PRODUCER_PLANES", "0") == "1"
+
+
 def _attach_planes(y: torch.Tensor, planes: torch.Tensor, precision: int):
     """Remember the pre-split planes of ``y`` (written by the producing kernel) for a consuming convolution."""
+    if _NO_PRODUCER_PLANES:      # debug knob (MOG_NO_PRODUCER_PLANES=1): every consumer runs its own split pass
+        return
     y._mog_planes = (planes, precision, y._version, y.data_ptr())
 
 

@@ -7,6 +7,11 @@ Same constructor, ``param_groups`` and ``state_dict`` layout as ``torch.optim.Ad
 ``mog_adam_multi`` call per parameter group (a handful of launches for a whole network instead of ~7 foreach
 kernels per 30 tensors); the EMA copy of the generator is updated in the same pass when ``ema_params`` is given.
 There is no CPU path: parameters must live on a CUDA device.
+
+The step count the bias corrections need lives in DEVICE memory (one double per parameter group, incremented by the
+kernel launch itself: ``mog_adam_multi_dev``), so a captured CUDA graph replays the optimiser step correctly; the
+per-parameter ``state['step']`` tensors of the ``state_dict`` are kept in step on the host (``advance_host_steps`` after
+a graph replay).
 """
 from __future__ import annotations
 
@@ -39,7 +44,7 @@ class Adam(torch.optim.Optimizer):
         if ema_params is not None and not isinstance(ema_params, dict):
             allp = [p for g in self.param_groups for p in g["params"]]
             ema_params = dict(zip(allp, ema_params))
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             ps, gs, ms, vs, es, ns = [], [], [], [], [], []
             step = None
             for p in group["params"]:
@@ -75,7 +80,7 @@ class Adam(torch.optim.Optimizer):
                 # the kernel writes p through its raw pointer: tell the packed-weight cache (ops._packed) that p changed
                 p._mog_ver = getattr(p, "_mog_ver", 0) + 1
             if ps:
-                self._launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale)
+                self._launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale, dev_slot=gi)
         updated = []
         for group in self.param_groups:
             for p in group["params"]:
@@ -86,11 +91,39 @@ class Adam(torch.optim.Optimizer):
         ops.repack(updated)
         return loss
 
-    @staticmethod
-    def _launch(group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale):
+    def advance_host_steps(self, n=1):
+        """After ``n`` replays of a CUDA graph that captured ``step()``: the device counters advanced by themselves, the
+        per-parameter ``state['step']`` of the ``state_dict`` (host tensors) are brought along."""
+        for slot in getattr(self, "_dev_steps", {}).values():
+            slot[1] += n
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and "step" in st:
+                    st["step"] += n
+
+    def _launch(self, group, ps, gs, ms, vs, es, ns, step, ema_decay, grad_scale, dev_slot=None):
         n = len(ps)
         arr = lambda xs: (C.c_void_p * n)(*xs)
         b1, b2 = group["betas"]
-        call("mog_adam_multi", n, arr(ps), arr(gs), arr(ms), arr(vs), arr(es) if any(e is not None for e in es) else None,
-             (C.c_longlong * n)(*ns), float(group["lr"]), float(b1), float(b2), float(group["eps"]), int(step),
-             float(ema_decay), float(grad_scale), torch.cuda.current_stream().cuda_stream)
+        stream = torch.cuda.current_stream().cuda_stream
+        ema = arr(es) if any(e is not None for e in es) else None
+        if dev_slot is not None:
+            # all parameters of the group are at the same step (always, in the reference's loops): device-resident counter
+            # [tensor, host mirror], kept outside param_groups / state so that state_dict() stays torch.optim.Adam's.
+            # It is (re)synchronised with the host count only when they disagree (first step, after load_state_dict).
+            slots = self.__dict__.setdefault("_dev_steps", {})
+            slot = slots.get(dev_slot)
+            if slot is None:
+                slot = slots[dev_slot] = [torch.zeros(1, dtype=torch.float64, device="cuda"), 0]
+            if slot[1] != step - 1:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("mog_b200.optim.Adam: the device step counter is out of sync inside a CUDA graph "
+                                       "capture -- run at least one eager step before capturing")
+                slot[0].fill_(float(step - 1))
+            call("mog_adam_multi_dev", n, arr(ps), arr(gs), arr(ms), arr(vs), ema, (C.c_longlong * n)(*ns), float(group["lr"]),
+                 float(b1), float(b2), float(group["eps"]), slot[0].data_ptr(), float(ema_decay), float(grad_scale), stream)
+            slot[1] = step
+            return
+        call("mog_adam_multi", n, arr(ps), arr(gs), arr(ms), arr(vs), ema, (C.c_longlong * n)(*ns), float(group["lr"]), float(b1),
+             float(b2), float(group["eps"]), int(step), float(ema_decay), float(grad_scale), stream)

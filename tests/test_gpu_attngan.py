@@ -170,7 +170,7 @@ def test_train_step_matches_reference(precision):
     cfg = _set_cfg(c)
     cfg.TRAIN.SMOOTH.GAMMA1, cfg.TRAIN.SMOOTH.GAMMA2, cfg.TRAIN.SMOOTH.GAMMA3, cfg.TRAIN.SMOOTH.LAMBDA = 4.0, 5.0, 10.0, 50.0
     old = ops.get_precision()
-    ops.set_precision(precision)
+    cfg.MOG.PRECISION = precision          # (the trainer's constructor applies cfg.MOG.PRECISION)
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False      # the stand-in encoder is a torch conv (test infrastructure)
     try:
@@ -183,6 +183,7 @@ def test_train_step_matches_reference(precision):
         for d in netsD:
             d.cuda().train()
         tr = condGANTrainer("", None, 0, None)
+        assert ops.get_precision() == ops.PREC_NAMES[precision]
         tr.image_encoder = synth.StandInEncoder(c["EMBEDDING_DIM"], device="cuda")
         optG, optDs = tr.define_optimizers(netG, netsD)
         st = tr.make_step_state(netG, netsD, optG, optDs)
@@ -203,4 +204,74 @@ def test_train_step_matches_reference(precision):
         check_train_state(G, nets, ema, scale=1.0 if precision == "fp32" else 2.0)
     finally:
         ops.set_precision(old)
+        torch.backends.cudnn.allow_tf32 = tf32
+
+
+def test_graphed_step_equals_eager_steps():
+    """The CUDA-graph form of the step (``condGANTrainer.graphed_step``: what bench.py and ``train()`` replay) against the
+    eager ``train_step`` on the same noise / eps / batches: parameters, EMA and Adam state after 2 warm-up + 3 replayed
+    steps (device-resident Adam step counter, repacked weights, BatchNorm running statistics all advance inside the graph)."""
+    from mog_b200 import ops
+    from mog_b200.attngan import model as M
+    from mog_b200.attngan.trainer import condGANTrainer
+    c = dict(GF_DIM=8, DF_DIM=8, Z_DIM=20, R_NUM=1, EMBEDDING_DIM=32, T=6, B=4)
+    cfg = _set_cfg(c)
+    cfg.MOG.PRECISION = "bf16x3"
+    seed, K = 77, 5
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+
+    def make():
+        netG, netsD = _build(c, seed)
+        tr = condGANTrainer("", None, 0, None)
+        tr.image_encoder = synth.StandInEncoder(c["EMBEDDING_DIM"], device="cuda")
+        optG, optDs = tr.define_optimizers(netG, netsD)
+        return tr, tr.make_step_state(netG, netsD, optG, optDs)
+
+    try:
+        b = _dev(synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=seed))
+        rng = np.random.RandomState(5)
+        noises = [torch.from_numpy(rng.standard_normal((c["B"], c["Z_DIM"])).astype(np.float32)).cuda() for _ in range(K)]
+        epss = [torch.from_numpy(rng.standard_normal((c["B"], 100)).astype(np.float32)).cuda() for _ in range(K)]
+        args = (b["imgs"], b["sent_emb"], b["words_embs"], b["mask"], b["transf_matrices"], b["transf_matrices_inv"], b["label_one_hot"],
+                b["cap_lens"], b["class_ids"])
+        tr1, st1 = make()
+        losses1 = [tr1.train_step(st1, *args, noise=noises[k], eps=epss[k]) for k in range(K)]
+        tr2, st2 = make()
+        # two eager steps, then three replays of the captured graph
+        gs = None
+        losses2 = []
+        for k in range(K):
+            if k < 2:
+                losses2.append(tr2.train_step(st2, *args, noise=noises[k], eps=epss[k]))
+            else:
+                if gs is None:     # capture without training (dry warm-up): the replays continue where the eager steps stopped
+                    gs = tr2.graphed_step(st2, *args, warmup=1, noise=noises[k], eps=epss[k], dry_warmup=True)
+                losses2.append([t.clone() for t in gs(*args, noise=noises[k], eps=epss[k])])
+        torch.cuda.synchronize()
+        # (the BatchNorm reductions end in fp64 atomics, so two runs agree to rounding, not bit for bit; Adam then moves
+        # near-zero-gradient entries by +-lr either way -- same gates as the reference comparison)
+        rel = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm().clamp_min(1e-30))   # noqa: E731
+        for k in range(K):
+            for a, r in zip(losses2[k], losses1[k]):
+                assert abs(float(a) - float(r)) <= 1e-4 * abs(float(r)) + 1e-6, (k, float(a), float(r))
+        moved = 0.0
+        for n1, n2 in zip([st1["netG"]] + st1["netsD"], [st2["netG"]] + st2["netsD"]):
+            num = den = 0.0
+            for (name, p1), (_, p2) in zip(n1.named_parameters(), n2.named_parameters()):
+                assert rel(p2, p1) <= 1e-3, (name, rel(p2, p1))
+                num += float((p1.double() - p2.double()).pow(2).sum()); den += float(p1.double().pow(2).sum())
+            assert (num / den) ** 0.5 <= 2e-4
+            for (name, v1), (_, v2) in zip(n1.named_buffers(), n2.named_buffers()):
+                assert rel(v2.float(), v1.float()) <= 2e-3, name
+        for a1, a2 in zip(st1["avg_param_G"], st2["avg_param_G"]):
+            assert rel(a2, a1) <= 1e-5
+        # the replays really stepped: Adam counts advanced to K on host and device, the weights moved since capture
+        for o1, o2 in zip([st1["optG"]] + st1["optDs"], [st2["optG"]] + st2["optDs"]):
+            s1, s2 = o1.state_dict()["state"], o2.state_dict()["state"]
+            for i in s1:
+                assert float(s1[i]["step"]) == float(s2[i]["step"]) == K
+            for slot in o2._dev_steps.values():
+                assert float(slot[0]) == K and slot[1] == K
+    finally:
         torch.backends.cudnn.allow_tf32 = tf32

@@ -178,8 +178,17 @@ def test_train_steps_with_adam_and_ema(keys):
 # gradient (m / sqrt(v) = +-1 at t = 1), so summation-order noise on near-zero gradient entries shows up at full size in
 # those elements: fp32-vs-fp32 restatements of the same step differ by up to 1.2e-4 per parameter tensor (5e-5 per network)
 # and up to 2e-2 in the moments of single tensors whose gradient nearly cancels (6e-4 per network; measured: oracle vs
-# reference, both CPU fp32).  A missing or doubled update would be >= 6e-3 on the parameters and O(1) on the moments.
-TS_PARAM, TS_PARAM_NET, TS_MOM_NET, TS_MOM, TS_EMA, TS_BUF = 5e-4, 2e-4, 2e-3, 0.05, 1e-5, 2e-4
+# reference, both CPU fp32; the GPU fp32 path, whose summation order differs, reaches 6e-4 on h_net1.bbox_net.encode.0.weight --
+# one-hot label planes, gradient entries spanning 7 decades -- and 1.1e-3 on the running mean of the BatchNorm behind it).
+# The tiny nets are also ill-conditioned: perturbing the discriminator parameters by 2e-4 (one Adam step of sign noise) changes
+# the ORACLE's own gradients by 1-2e-3 over a whole network and up to 5e-2 on single tensors (measured), so from the second
+# step on the moments cannot agree better than a few 1e-2.
+# D_NET256 is the worst: a 3e-6 perturbation of the generated 256^2 image -- the rounding difference between two fp32
+# implementations of G -- changes its fp64 gradients by up to 2.5e-3 (img_code_s16.3.bias; measured on the CPU oracle).
+# The moments are gated per NETWORK (norm-weighted); the per-tensor gate is a sanity bound only (tensors whose gradient nearly
+# cancels -- img_net2.img.0.weight, the label BatchNorm bias -- sit at 0.02-0.13 from rounding alone).
+# A missing or doubled update would be >= 6e-3 on the parameters, O(1) on the moments and >= 0.1 on a running statistic.
+TS_PARAM_RMS, TS_PARAM_NET, TS_MOM_NET, TS_MOM, TS_EMA, TS_BUF = 1e-4, 5e-4, 5e-2, 0.5, 1e-5, 2e-3
 
 
 def check_train_state(G, nets, ema, scale=1.0):
@@ -189,7 +198,14 @@ def check_train_state(G, nets, ema, scale=1.0):
         for name, p in P.items():
             if ("%s/param/%s" % (tag, name)) in G:
                 e = ap.add(p, G["%s/param/%s" % (tag, name)], name)
-                assert e <= scale * TS_PARAM, "%s param %s: %.3e" % (tag, name, e)
+                # per tensor: rms deviation below half an Adam step (lr = 2e-4 moves every entry by ~lr per step; a skipped or
+                # doubled step would show as >= lr).  Small-valued tensors (BatchNorm beta ~ 0.02) make rel-L2 meaningless here.
+                summ = G["%s/param/%s" % (tag, name)]
+                ref = np.asarray(summ["full"] if "full" in summ else summ["sample"], np.float64)
+                a = p.detach().cpu().double().numpy().reshape(-1)
+                got = a if "full" in summ else a[gu._idx(a.size)]
+                rms = float(np.sqrt(np.mean((got - ref) ** 2)))
+                assert rms <= scale * TS_PARAM_RMS, "%s param %s: rms deviation %.3e (rel-L2 %.3e)" % (tag, name, rms, e)
                 s = ostate[p]
                 e = am.add(s["exp_avg"], G["%s/exp_avg/%s" % (tag, name)], name)
                 assert e <= scale * TS_MOM, "%s exp_avg %s: %.3e" % (tag, name, e)

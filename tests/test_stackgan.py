@@ -106,7 +106,7 @@ def test_libmog_matches_reference(stage, prec):
         e1, e2 = gu.full(G, "eps1").cuda(), gu.full(G, "eps2").cuda()
         # bf16x3 gradients: LeakyReLU/ReLU sign flips of ~1e-8 pre-activations (label layouts are exactly zero outside the
         # boxes) move a few small weight gradients by percent; outputs and losses stay at 1e-4
-        tol_o, tol_g = (5e-5, 1e-3 if stage == 1 else 1e-2) if prec == "fp32" else (2e-4, 0.15)
+        tol_o, tol_g = (5e-5, 1e-3 if stage == 1 else 2e-2) if prec == "fp32" else (2e-4, 0.15)
         # (stage II, fp32: the 8-channel STAGE2_D stack amplifies summation-order noise: conv1.weight 3.7e-3, local.0 1.1e-3)
         if stage == 1:
             _, fake, mu, logvar, ll = netG(b["txt_embedding"], b["noise"], b["transf_matrices_inv"], b["label_one_hot"], eps=e1)
