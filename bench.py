@@ -121,9 +121,37 @@ def set_cfg():
 
 
 # --------------------------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline: the oracle port of the reference on the host cores
+# Reference arm / cpu_baseline: the UNMODIFIED reference modules (baseline/_ref, staged by __graft_entry__.build()) through
+# baseline/ref_harness.py -- trainer.py:294-342 with the reference's G_NET / D_NET64/128/256 / CNN_ENCODER, losses,
+# optim.Adam(betas=(0.5, 0.999)) and EMA -- on the host cores.  The oracle port is the fall-back when the staged sources
+# are missing (kind "port").
 # --------------------------------------------------------------------------------------------
+CPU_S_PER_IMAGE = 0.40      # measured on the gpurun host (16 threads): 2.7 images/s for the full step
+
+
+def ref_sample_batch(steps, warmup, batch, budget_s=200.0):
+    """Bounded sample: the largest power-of-two batch <= the workload's whose (steps + warmup) CPU steps fit the budget."""
+    b = batch
+    while b > 2 and (steps + warmup) * b * CPU_S_PER_IMAGE > budget_s:
+        b //= 2
+    return b
+
+
 def cpu_reference_run(steps, warmup, batch, damsm=True):
+    from baseline import ref_harness as H
+    cores = os.cpu_count() or 1
+    if H.available():
+        r = H.time_attngan(batch, steps, warmup, "cpu", damsm, threads=cores)
+        return {"value": r["images_per_s"], "unit": "images/s", "cores": cores, "kind": "reference",
+                "sample": "unmodified reference modules (baseline/_ref: G_NET, D_NET64/128/256, CNN_ENCODER, miscc/losses.py) "
+                          "driven as trainer.py:294-342 incl. optim.Adam + EMA%s, torch CPU fp32, %d threads, config 5 at a "
+                          "bounded batch of %d, %d warm-up + %d timed steps"
+                          % (" and the DAMSM / Inception-v3 branch" if damsm else "", cores, batch, warmup, steps),
+                "ms_per_step": r["ms_per_step"], "batch": batch}
+    return cpu_port_run(steps, warmup, batch, damsm)
+
+
+def cpu_port_run(steps, warmup, batch, damsm=True):
     from mog_b200 import synth
     from oracle import attngan_oracle as O
     from mog_b200.attngan import model as M
@@ -131,7 +159,6 @@ def cpu_reference_run(steps, warmup, batch, damsm=True):
     torch.set_num_threads(cores)
     set_cfg()
     torch.manual_seed(1234)
-    # parameter shapes from the host-side modules (never moved to a device here); N(0, 1/fan_in) fill
     sdG = synth.fill_state_dict(M.G_NET().state_dict(), 1)
     sdDs = [synth.fill_state_dict(c().state_dict(), 2 + i) for i, c in enumerate((M.D_NET64, M.D_NET128, M.D_NET256))]
     PG, PDs = O.leafify(sdG), [O.leafify(s) for s in sdDs]
@@ -140,34 +167,58 @@ def cpu_reference_run(steps, warmup, batch, damsm=True):
     PE = None
     if damsm:
         PE = {k: v for k, v in synth.fill_encoder_state_dict(M.CNN_ENCODER(CFG5["EMBEDDING_DIM"]).state_dict(), 9).items()}
+    state = O.make_train_state(PG, PDs)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.gd_step(PG, PDs, ocfg, b, PE=PE)
+        O.train_step(PG, PDs, state, ocfg, b, PE=PE)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     tot = sum(times)
     return {"value": batch * len(times) / tot, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "oracle/attngan_oracle.gd_step (torch CPU fp32 port of the reference step, fwd+bwd%s, no "
-                      "optimiser) at config 5, batch %d, %d warm-up + %d timed steps"
-                      % (" incl. DAMSM / Inception-v3" if damsm else "", batch, warmup, len(times)),
-            "ms_per_step": 1e3 * tot / len(times)}
+            "sample": "oracle/attngan_oracle.train_step (torch CPU fp32 port of trainer.py:294-342 incl. Adam + EMA%s) at config 5, "
+                      "batch %d, %d warm-up + %d timed steps (reference sources not staged on this box)"
+                      % (" and DAMSM / Inception-v3" if damsm else "", batch, warmup, len(times)),
+            "ms_per_step": 1e3 * tot / len(times), "batch": batch}
+
+
+def workload_config(args, ws):
+    """The workload both arms run (identical dict in both JSON lines); arm-specific details travel outside `config`."""
+    return {"workload": workload(args), "batch_per_gpu": args.batch, "global_batch": ws * args.batch, "words": CFG5["T"],
+            "l2": "working set per step (>5 GB) exceeds the 126 MB L2; no flush needed",
+            "optimizer": "Adam(2e-4, betas=(0.5, 0.999)) x4 + EMA of G inside the timed region",
+            "algorithmic_gflop_per_image": 2 * gmac(args)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, args.ref_batch, not args.no_damsm)
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    bs = args.ref_batch or ref_sample_batch(args.steps, args.warmup, args.batch)
+    r = cpu_reference_run(args.steps, args.warmup, bs, not args.no_damsm)
     line = {"impl": "reference", "metric": "images/sec (G+D fwd+bwd) COCO-AttnGAN 256^2", "value": r["value"],
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": workload(args), "batch_per_step": args.ref_batch, "device": "cpu"},
+            "dtype": "fp32", "data": "synthetic", "config": workload_config(args, ws),
+            "arm": {"device": "cpu", "threads": r["cores"], "sample_batch_per_step": bs,
+                    "note": "images/s of the same step on a bounded batch (CPU time per image is flat in the batch size)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def subprocess_json(cmd, timeout):
+    """Run a helper (reference timing) in its own process -- the harness rebinds torch globals -- and parse its JSON line."""
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=timeout, cwd=ROOT).stdout
+        for ln in reversed(out.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+    return {"error": "no output"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -298,10 +349,21 @@ def run_mog(args):
     roof = cpu = None
     if rank == 0:
         roof = roofline_probe(dev, args, B)
+    cudnn = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        # free the device-side state first? not needed: the CPU leg only touches host memory
-        cpu = cpu_reference_run(1, 1, args.ref_batch, not args.no_damsm)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # the reference's own step on the host cores: bounded sample (batch 8, 1 warm-up + 2 timed steps), own process
+        py = sys.executable
+        extra = ["--no-damsm"] if args.no_damsm else []
+        ref = subprocess_json([py, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                               "--ref-batch", "8", "--batch", str(B)] + extra, 600)
+        cpu = ref.get("cpu_baseline") or {"error": ref.get("error", "failed")}
+        # reported, not the headline: the same reference modules on this B200 under stock torch + cuDNN (cudnn.benchmark as in
+        # trainer.py:51), with torch's default TF32 convolutions and with TF32 disabled
+        cudnn = {}
+        for tag, flag in (("tf32", "1"), ("fp32", "0")):
+            r = subprocess_json([py, os.path.join(ROOT, "baseline", "ref_harness.py"), "--device", "cuda", "--batch", str(B),
+                                 "--steps", "5", "--warmup", "3", "--tf32", flag] + extra, 600)
+            cudnn[tag] = {"images_per_s": r.get("images_per_s"), "ms_per_step": r.get("ms_per_step")} if "error" not in r else r
     if rank == 0:
         pk, src = peaks()
         line = {"metric": "images/sec (G+D fwd+bwd) COCO-AttnGAN 256^2", "value": value, "unit": "images/s",
@@ -310,21 +372,52 @@ def run_mog(args):
                 "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (3-pass split, fp32-equivalent) + fp32 accumulate",
                           "bf16": "bf16 operands, fp32 accumulate"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": workload(args), "batch_per_gpu": B, "global_batch": ws * B, "words": CFG5["T"],
-                           "parallelism": "dp%d (NCCL grad all-reduce per net)" % ws,
-                           "precision": args.precision, "l2": "working set per step (>5 GB) exceeds the 126 MB L2; no flush needed",
-                           "optimizer": "fused libmog Adam + EMA (mog_adam_multi_dev) inside the timed region",
-                           "cuda_graph": gs is not None,
-                           "algorithmic_gflop_per_image": 2 * gmac(args),
-                           "step_tflops_achieved": 2 * gmac(args) * 1e9 * value / 1e12},
+                "config": workload_config(args, ws),
+                "arm": {"parallelism": "dp%d (one process per GPU, NCCL grad all-reduce per net)" % ws, "precision": args.precision,
+                        "optimizer_kernel": "fused libmog Adam + EMA (mog_adam_multi_dev)", "cuda_graph": gs is not None,
+                        "step_tflops_achieved": 2 * gmac(args) * 1e9 * value / 1e12 / ws, "built": ge.BUILD_MODE},
                 "clocks": clocks, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K},
-                "roofline": roof, "cpu_baseline": cpu, "peaks": src}
+                "roofline": roof, "cpu_baseline": cpu, "torch_cudnn_b200": cudnn, "peaks": src}
+        if roof is not None:
+            # whole-step fraction: algorithmic FLOPs of the step / step time / SUSTAINED bf16 peak (kernels timed inside a long step)
+            sus = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            roof["step_tflops"] = 2 * gmac(args) * 1e9 * value / 1e12 / ws
+            roof["step_frac"] = roof["step_tflops"] / sus
+            roof["step_peak"] = sus
         print(json.dumps(line))
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant conv's launches, read from the committed `ncu --set full`
+    capture (profiles/*conv_halo_up*.raw.csv, taken at B = 32 with the same ops.conv2d call); None when no capture is there."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_halo_up*.raw.csv")))
+    if not files:
+        return None, None
+    path = files[-1]
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        units = rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot, n = 0.0, 0
+        for r in rows[2:]:
+            if "conv_halo" in r[ik] and n < FWD_LAUNCHES_IN_CAPTURE:
+                tot += float(r[ir].replace(",", "")) * scale.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * scale.get(units[iw], 1.0)
+                n += 1
+        return tot * (B / 32.0), os.path.relpath(path, ROOT) + " (first %d conv_halo launches = the forward)" % n
+    except Exception as e:  # noqa: BLE001
+        return None, "unreadable capture %s: %s" % (os.path.basename(path), e)
+
+
+FWD_LAUNCHES_IN_CAPTURE = 4     # the forward of up2x + 3x3 is four sub-pixel phase launches in the r1c capture
 
 
 def roofline_probe(dev, args, B):
@@ -353,11 +446,9 @@ def roofline_probe(dev, args, B):
     flops = 2.0 * B * 256 * 256 * 96 * 864
     achieved = flops / (ms / 1e3) / 1e12
     peak = pk["bf16_tflops"]
-    # DRAM bytes of this conv from the committed ncu --set full capture (profiles/r1c_conv_halo_up.raw.csv: four sub-pixel
-    # phase launches, 201.6 MB read + ~158.7 MB written each, at B = 32); algorithmic: 201 MB planes in + 805 MB fp32 out
-    traffic = 4 * (201.56e6 + 158.67e6) * (B / 32.0)
+    traffic, traffic_src = ncu_traffic(B)
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": traffic, "executed_tflops": achieved * 3.0 / 2.25,
+            "traffic": traffic, "traffic_source": traffic_src, "executed_tflops": achieved * 3.0 / 2.25,
             "note": "achieved counts the dense fp32-equivalent FLOPs of the upsampled 3x3 conv; the kernel executes 2.25x fewer "
                     "MACs (sub-pixel phases) x 3 bf16 passes (hi*hi + lo*hi + hi*lo)",
             "kernel": "conv fwd G.h_net3.upsample (up2x + 3x3, 96->96 @256^2), precision=%s" % args.precision,
@@ -372,7 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mog", choices=["mog", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=2, help="bounded CPU sample: images per CPU step")
+    ap.add_argument("--ref-batch", type=int, default=0, help="bounded CPU sample: images per CPU step (0 = sized to the time budget)")
     ap.add_argument("--precision", default=os.environ.get("MOG_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph of the step")
