@@ -140,10 +140,16 @@ int mog_conv2d_wgrad(const MogConvDesc* d, const float* x, const void* x_planes,
 /* x is [S*M][C] (S segments of M rows; the object pathway calls the same BN once per object
  * with separate statistics, model.py:393-401,685-693).
  * replaces: nn.BatchNorm2d/1d train-mode forward (model.py:53,62,72,75,96,100,366,372,...). */
-int mog_bn_stats(const float* x, int S, int M, int C, double* sum /*[S][C]*/, double* sqsum /*[S][C]*/, void* stream);
+/* Reductions are two-stage and bit-reproducible: the streaming kernel leaves one fp64 partial per (block row p, quantity,
+ * segment, channel) in part[P][2][S][C] (P = mog_bn_parts(S, M, C, act, which): which = 0 forward statistics, 1 backward
+ * sums), the consumer adds the P partials in a fixed order.  The fp32 partial sums are taken relative to the channel's
+ * first value, so the variance does not cancel for channels whose mean is large against their spread. */
+int mog_bn_parts(int S, int M, int C, int act, int which);
+int mog_bn_stats(const float* x, int S, int M, int C, double* part /*[P][2][S][C]: sum, sum of squares*/, int nparts,
+                 void* stream);
 /* Finalises statistics: mean, invstd [S][C]; scale = gamma*invstd, shift = beta - mean*scale;
  * running stats updated once per segment in order (momentum, unbiased variance) when not NULL. */
-int mog_bn_finalize(const double* sum, const double* sqsum, int S, int M, int C, const float* gamma,
+int mog_bn_finalize(const double* part, int nparts, int S, int M, int C, const float* gamma,
                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                     float* mean, float* invstd, float* scale, float* shift, void* stream);
 /* y = act(x*scale + shift) (+ residual).  scale/shift may be NULL (plain activation).  For
@@ -162,17 +168,18 @@ int mog_affine_act_fwd_planes(const float* x, const float* scale, const float* s
  * of the pre-activation x (dx = dy * act'(x); used for GLU without BN, model.py:328). */
 int mog_bn_act_bwd_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
                           const float* gamma, const float* beta, int S, int M, int C, int act,
-                          double* dgamma_seg /*[S][C]*/, double* dbeta_seg /*[S][C]*/, void* stream);
+                          double* part /*[P][2][S][C]: sum dz, sum dz*xhat*/, int nparts, double* dgamma_seg /*[S][C]*/,
+                          double* dbeta_seg /*[S][C]*/, float* dgamma /*[C], summed over segments, or NULL*/, float* dbeta,
+                          void* stream);
 int mog_bn_act_bwd_apply(const float* x, const float* dy, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const double* dgamma_seg,
-                         const double* dbeta_seg, int S, int M, int C, int act, float* dx,
-                         float* dgamma /*[C], summed over segments*/, float* dbeta, void* stream);
+                         const double* dbeta_seg, int S, int M, int C, int act, float* dx, void* stream);
 /* Same, and additionally emits dx as the pre-split bf16 planes (hi [rows][C], then lo for MOG_PREC_BF16X3) that the data /
  * weight gradient kernels of the producing convolution read, saving the separate split pass over dx.  C % 8 == 0. */
 int mog_bn_act_bwd_apply_planes(const float* x, const float* dy, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, const double* dgamma_seg,
                                 const double* dbeta_seg, int S, int M, int C, int act, float* dx, void* dx_planes,
-                                int precision, float* dgamma, float* dbeta, void* stream);
+                                int precision, void* stream);
 /* dz = dy * act'(.) given the activation OUTPUT y (LRELU / RELU / TANH / SIGMOID). */
 int mog_act_bwd(const float* dy, const float* y, float* dz, size_t n, int act, void* stream);
 
@@ -202,9 +209,13 @@ int mog_stn_bwd(const float* dy, const float* theta, float* dx, int mode, int B,
  * out [B,Q,D]; attn (may be NULL) [B,T,Q] as returned by the reference. */
 int mog_word_attention_fwd(const float* h, const float* src, const uint8_t* mask, float* out, float* attn,
                            int B, int Q, int D, int T, int mask_quirk, void* stream);
-/* dh [B,Q,D]; dsrc [B,T,D] (must be zero-initialised by the caller; accumulated atomically). */
+/* dh [B,Q,D]; dsrc [B,T,D].  With a workspace of mog_word_attention_bwd_workspace_bytes (D % 4 == 0) every block leaves its
+ * partial [T][D] there and a second kernel sums them in a fixed order (deterministic; dsrc is written, not accumulated).
+ * Without one (workspace NULL, or D % 4 != 0) dsrc must be zero-initialised by the caller and is accumulated atomically. */
+size_t mog_word_attention_bwd_workspace_bytes(int B, int Q, int D, int T);
 int mog_word_attention_bwd(const float* h, const float* src, const uint8_t* mask, const float* dout,
-                           float* dh, float* dsrc, int B, int Q, int D, int T, int mask_quirk, void* stream);
+                           float* dh, float* dsrc, int B, int Q, int D, int T, int mask_quirk, void* workspace,
+                           size_t ws_bytes, void* stream);
 
 /* ---- DAMSM word-region matching (AttnGAN) ---------------------------------------------------- */
 /* replaces: the per-caption loop of words_loss, each a func_attention call + cosine similarity +

@@ -21,78 +21,107 @@ inline int rows_per_block(int M) {
 }
 
 // ---- statistics -------------------------------------------------------------------------
-__global__ void bn_stats_kernel(const float* __restrict__ x, int M, int C, int rpb, double* __restrict__ sum,
-                                double* __restrict__ sqsum) {
-  // grid: (ceil(C/32), row chunks, S)
+// Partial sums: every reducing kernel leaves ONE partial per (block row p, quantity k, segment, channel) in
+// part[p][k][S][C] (fp64); the consumer (bn_finalize / bn_bwd_sum) adds the P partials in a fixed order, so the
+// statistics are bit-reproducible run to run (the first version ended in fp64 atomics, which are not) and no atomics
+// serialise in L2.
+__device__ __forceinline__ double* part_slot(double* part, int p, int k, int S, int C, int s, int c) {
+  return part + (((size_t)p * 2 + k) * S + s) * C + c;
+}
+
+__global__ void bn_stats_kernel(const float* __restrict__ x, int M, int C, int rpb, double* __restrict__ part, int S) {
+  // grid: (ceil(C/32), P row-chunk groups, S); block p takes the row chunks p, p + P, ...
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const int s = blockIdx.z;
-  const long long r_begin = (long long)blockIdx.y * rpb;
-  long long r_end = r_begin + rpb;
-  if (r_end > M) r_end = M;
   // Shifted sums: the fp32 partials accumulate d = x - x0 (x0 = the channel's value in the first row of the segment), so
   // that sum(x^2)/M - mean^2 does not cancel for channels whose mean is large against their spread (measured: mean/std = 300
   // lost 3 digits of the variance with plain fp32 partials; torch uses Welford).  The shift is folded back exactly in double.
-  float a = 0.f, b = 0.f;
+  double da = 0.0, db = 0.0;
   float x0 = 0.f;
-  int n = 0;
   if (c < C) {
     const float* xp = x + ((size_t)s * M) * C + c;
     x0 = __ldg(xp);
-    for (long long r = r_begin + rl; r < r_end; r += RED_ROWS) {
-      float v = __ldg(xp + (size_t)r * C) - x0;
-      a += v;
-      b = fmaf(v, v, b);
-      ++n;
+    for (long long r_begin = (long long)blockIdx.y * rpb; r_begin < M; r_begin += (long long)gridDim.y * rpb) {
+      long long r_end = r_begin + rpb;
+      if (r_end > M) r_end = M;
+      float a = 0.f, b = 0.f;
+      int n = 0;
+      for (long long r = r_begin + rl; r < r_end; r += RED_ROWS) {
+        float v = __ldg(xp + (size_t)r * C) - x0;
+        a += v;
+        b = fmaf(v, v, b);
+        ++n;
+      }
+      const double s0 = (double)x0;
+      da += (double)a + (double)n * s0;
+      db += (double)b + 2.0 * s0 * (double)a + (double)n * s0 * s0;
     }
   }
-  __shared__ float sa[RED_ROWS][33], sb[RED_ROWS][33];
-  __shared__ int sn[RED_ROWS][33];
-  sa[rl][lane] = a;
-  sb[rl][lane] = b;
-  sn[rl][lane] = n;
+  __shared__ double sa[RED_ROWS][33], sb[RED_ROWS][33];
+  sa[rl][lane] = da;
+  sb[rl][lane] = db;
   __syncthreads();
   if (rl == 0 && c < C) {
-    double ta = 0.0, tb = 0.0, tn = 0.0;
+    double ta = 0.0, tb = 0.0;
 #pragma unroll
     for (int i = 0; i < RED_ROWS; ++i) {
-      ta += (double)sa[i][lane];
-      tb += (double)sb[i][lane];
-      tn += (double)sn[i][lane];
+      ta += sa[i][lane];
+      tb += sb[i][lane];
     }
-    const double s0 = (double)x0;
-    atomicAdd(sum + (size_t)s * C + c, ta + tn * s0);
-    atomicAdd(sqsum + (size_t)s * C + c, tb + 2.0 * s0 * ta + tn * s0 * s0);
+    *part_slot(part, blockIdx.y, 0, S, C, s, c) = ta;
+    *part_slot(part, blockIdx.y, 1, S, C, s, c) = tb;
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, int S, int M,
+// One warp per channel: the lanes add the P partials (lane-strided, then a fixed xor-shuffle tree: the order never
+// changes, so the result is bit-reproducible), lane 0 finalises.  (One THREAD per channel looping over up to ~600 partials
+// took 30 us per layer.)
+__device__ __forceinline__ void part_sum2(const double* __restrict__ part, int P, int S, int C, int s, int c, int lane, double* o0,
+                                          double* o1) {
+  double a = 0.0, b = 0.0;
+  for (int p = lane; p < P; p += 32) {
+    a += part[(((size_t)p * 2 + 0) * S + s) * C + c];
+    b += part[(((size_t)p * 2 + 1) * S + s) * C + c];
+  }
+  *o0 = warp_sum_d(a);
+  *o1 = warp_sum_d(b);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ part, int P, int S, int M,
                                    int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean,
                                    float* invstd, float* scale, float* shift) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   float rm = running_mean ? running_mean[c] : 0.f;
   float rv = running_var ? running_var[c] : 0.f;
   for (int s = 0; s < S; ++s) {
-    double mu = sum[(size_t)s * C + c] / (double)M;
-    double var = sqsum[(size_t)s * C + c] / (double)M - mu * mu;
+    double sum, sqsum;
+    part_sum2(part, P, S, C, s, c, lane, &sum, &sqsum);
+    double mu = sum / (double)M;
+    double var = sqsum / (double)M - mu * mu;
     if (var < 0.0) var = 0.0;
     float is = (float)(1.0 / sqrt(var + (double)eps));
     float muf = (float)mu;
-    mean[(size_t)s * C + c] = muf;
-    invstd[(size_t)s * C + c] = is;
     float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     float sc = g * is;
-    scale[(size_t)s * C + c] = sc;
-    shift[(size_t)s * C + c] = b - muf * sc;
+    if (lane == 0) {
+      mean[(size_t)s * C + c] = muf;
+      invstd[(size_t)s * C + c] = is;
+      scale[(size_t)s * C + c] = sc;
+      shift[(size_t)s * C + c] = b - muf * sc;
+    }
     // nn.BatchNorm: running = (1-m)*running + m*stat, unbiased variance for running_var
     double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
     rm = (1.f - momentum) * rm + momentum * muf;
     rv = (1.f - momentum) * rv + momentum * (float)unb;
   }
-  if (running_mean) running_mean[c] = rm;
-  if (running_var) running_var[c] = rv;
+  if (lane == 0) {
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+  }
 }
 
 // ---- forward ------------------------------------------------------------------------------
@@ -238,39 +267,68 @@ __device__ __forceinline__ float dz_of(const ChanConst& k, float xv, const float
   }
 }
 
-__global__ void bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ dgamma, double* __restrict__ dbeta) {
+// part[p][0] = sum dz (d beta), part[p][1] = sum dz * xhat (d gamma)
+__global__ void bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ part) {
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const int s = blockIdx.z;
   const int Co = a.act == MOG_ACT_GLU ? a.C / 2 : a.C;
-  const long long r_begin = (long long)blockIdx.y * a.rows_per_block;
-  long long r_end = r_begin + a.rows_per_block;
-  if (r_end > a.M) r_end = a.M;
-  float g1 = 0.f, g2 = 0.f;
+  double d1 = 0.0, d2 = 0.0;
   if (c < a.C) {
     const ChanConst k = chan_const(a, s, c);
-    for (long long r = r_begin + rl; r < r_end; r += RED_ROWS) {
-      size_t row = (size_t)s * a.M + r;
-      const float* xr = a.x + row * a.C;
-      float xv = __ldg(xr + c);
-      float dz = dz_of(k, xv, xr, a.dy + row * Co, a.act);
-      g1 += dz;
-      g2 = fmaf(dz, (xv - k.mu) * k.is, g2);
+    for (long long r_begin = (long long)blockIdx.y * a.rows_per_block; r_begin < a.M; r_begin += (long long)gridDim.y * a.rows_per_block) {
+      long long r_end = r_begin + a.rows_per_block;
+      if (r_end > a.M) r_end = a.M;
+      float g1 = 0.f, g2 = 0.f;
+      for (long long r = r_begin + rl; r < r_end; r += RED_ROWS) {
+        size_t row = (size_t)s * a.M + r;
+        const float* xr = a.x + row * a.C;
+        float xv = __ldg(xr + c);
+        float dz = dz_of(k, xv, xr, a.dy + row * Co, a.act);
+        g1 += dz;
+        g2 = fmaf(dz, (xv - k.mu) * k.is, g2);
+      }
+      d1 += (double)g1;
+      d2 += (double)g2;
     }
   }
-  __shared__ float sa[RED_ROWS][33], sb[RED_ROWS][33];
-  sa[rl][lane] = g1;
-  sb[rl][lane] = g2;
+  __shared__ double sa[RED_ROWS][33], sb[RED_ROWS][33];
+  sa[rl][lane] = d1;
+  sb[rl][lane] = d2;
   __syncthreads();
   if (rl == 0 && c < a.C) {
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
     for (int i = 0; i < RED_ROWS; ++i) {
-      t1 += (double)sa[i][lane];
-      t2 += (double)sb[i][lane];
+      t1 += sa[i][lane];
+      t2 += sb[i][lane];
     }
-    atomicAdd(dbeta + (size_t)s * a.C + c, t1);
-    atomicAdd(dgamma + (size_t)s * a.C + c, t2);
+    *part_slot(part, blockIdx.y, 0, a.S, a.C, s, c) = t1;
+    *part_slot(part, blockIdx.y, 1, a.S, a.C, s, c) = t2;
+  }
+}
+
+// adds the P partials of the backward sums in a fixed order -> dbeta_seg / dgamma_seg [S][C] (what the apply pass reads),
+// and the parameter gradients (sum over segments) in the same launch
+__global__ void bn_bwd_sum_kernel(const double* __restrict__ part, int P, int S, int C, double* __restrict__ dgamma_seg,
+                                  double* __restrict__ dbeta_seg, float* dgamma, float* dbeta) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double gt = 0.0, bt = 0.0;
+  for (int s = 0; s < S; ++s) {
+    double b, g;
+    part_sum2(part, P, S, C, s, c, lane, &b, &g);
+    if (lane == 0) {
+      dbeta_seg[(size_t)s * C + c] = b;
+      dgamma_seg[(size_t)s * C + c] = g;
+    }
+    gt += g;
+    bt += b;
+  }
+  if (lane == 0) {
+    if (dgamma) dgamma[c] = (float)gt;
+    if (dbeta) dbeta[c] = (float)bt;
   }
 }
 
@@ -295,19 +353,6 @@ __global__ void bn_bwd_apply_kernel(BnBwdArgs a, const double* __restrict__ dgam
     float xh = (xv - k.mu) * k.is;
     dx[row * a.C + c] = k.sc * (dz - k1 - xh * k2);
   }
-}
-
-__global__ void bn_bwd_param_kernel(const double* __restrict__ dgamma_seg, const double* __restrict__ dbeta_seg,
-                                    int S, int C, float* dgamma, float* dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double g = 0.0, b = 0.0;
-  for (int s = 0; s < S; ++s) {
-    g += dgamma_seg[(size_t)s * C + c];
-    b += dbeta_seg[(size_t)s * C + c];
-  }
-  if (dgamma) dgamma[c] = (float)g;
-  if (dbeta) dbeta[c] = (float)b;
 }
 
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
@@ -350,10 +395,10 @@ static V4Geom v4_geom(int width, int M, int S = 1, bool reduce = false) {
   if (reduce) {
     static int per_sm = -1;
     if (per_sm < 0) {
-      const char* e = getenv("MOG_BN_BLOCKS_PER_SM");   // tuning knob; 0 = one block per row chunk (no cap)
-      per_sm = e ? atoi(e) : 2;
+      const char* e = getenv("MOG_BN_BLOCKS_PER_SM");   // tuning knob: resident reducing blocks per SM (each leaves one partial)
+      per_sm = e ? atoi(e) : 4;
+      if (per_sm < 1) per_sm = 1;
     }
-    if (per_sm == 0) return g;
     int cap = (per_sm * kNumSMs) / (g.nxb * (S > 0 ? S : 1));
     if (cap < 1) cap = 1;
     if (g.nyb > cap) g.nyb = cap;
@@ -364,7 +409,7 @@ static V4Geom v4_geom(int width, int M, int S = 1, bool reduce = false) {
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void to_arr(const float4& v, float (&a)[4]) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
-// block-level sum over the R row lanes of NV per-thread values (4 channels each), then one double atomicAdd per channel
+// block-level sum over the R row lanes of NV per-thread values (4 channels each), then one partial store per channel
 template <int NV>
 __device__ __forceinline__ void v4_block_reduce(double (&v)[NV][4], int GB, int R, int cgl, int rl, bool valid, double* const (&dst)[NV]) {
   __shared__ double red[NV][256 * 4];
@@ -381,12 +426,12 @@ __device__ __forceinline__ void v4_block_reduce(double (&v)[NV][4], int GB, int 
       for (int j = 0; j < 4; ++j) {
         double acc = 0.0;
         for (int i = 0; i < R; ++i) acc += red[k][(i * GB + cgl) * 4 + j];
-        atomicAdd(dst[k] + j, acc);
+        dst[k][j] = acc;
       }
   }
 }
 
-__global__ void bn_stats_v4_kernel(const float* __restrict__ x, int M, int C, V4Geom g, double* __restrict__ sum, double* __restrict__ sqsum) {
+__global__ void __launch_bounds__(256, 3) bn_stats_v4_kernel(const float* __restrict__ x, int M, int C, V4Geom g, double* __restrict__ part, int S) {
   const int cgl = threadIdx.x % g.GB, rl = threadIdx.x / g.GB;
   const int cg = blockIdx.x * g.GB + cgl;
   const bool valid = cg < g.Cv;
@@ -418,7 +463,7 @@ __global__ void bn_stats_v4_kernel(const float* __restrict__ x, int M, int C, V4
       }
     }
   }
-  double* const dst[2] = {sum + (size_t)s * C + c, sqsum + (size_t)s * C + c};
+  double* const dst[2] = {part_slot(part, blockIdx.y, 0, S, C, s, c), part_slot(part, blockIdx.y, 1, S, C, s, c)};
   v4_block_reduce<2>(v, g.GB, g.R, cgl, rl, valid, dst);
 }
 
@@ -467,8 +512,9 @@ __device__ __forceinline__ void dz_row(const Aff4& kv, const Aff4& kg, const flo
   }
 }
 
+// (ncu: 160 registers per thread left ONE 240-thread block per SM, 12 % of the warps active; bounded to 2 blocks per SM)
 template <int ACT>
-__global__ void bn_bwd_reduce_v4_kernel(BnBwdArgs a, V4Geom g, double* __restrict__ dgamma, double* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_v4_kernel(BnBwdArgs a, V4Geom g, double* __restrict__ part) {
   constexpr bool GLU = ACT == MOG_ACT_GLU;
   const int Co = GLU ? a.C / 2 : a.C;
   const int cgl = threadIdx.x % g.GB, rl = threadIdx.x / g.GB;
@@ -537,12 +583,13 @@ __global__ void bn_bwd_reduce_v4_kernel(BnBwdArgs a, V4Geom g, double* __restric
         for (int j = 0; j < 4; ++j) v[k][j] += (double)f[k][j];
     }
   }
+  const int p = blockIdx.y;
   if constexpr (GLU) {
-    double* const dst[4] = {dbeta + (size_t)s * a.C + c, dgamma + (size_t)s * a.C + c, dbeta + (size_t)s * a.C + c + Co,
-                            dgamma + (size_t)s * a.C + c + Co};
+    double* const dst[4] = {part_slot(part, p, 0, a.S, a.C, s, c), part_slot(part, p, 1, a.S, a.C, s, c),
+                            part_slot(part, p, 0, a.S, a.C, s, c + Co), part_slot(part, p, 1, a.S, a.C, s, c + Co)};
     v4_block_reduce<4>(v, g.GB, g.R, cgl, rl, valid, dst);
   } else {
-    double* const dst[2] = {dbeta + (size_t)s * a.C + c, dgamma + (size_t)s * a.C + c};
+    double* const dst[2] = {part_slot(part, p, 0, a.S, a.C, s, c), part_slot(part, p, 1, a.S, a.C, s, c)};
     v4_block_reduce<2>(v, g.GB, g.R, cgl, rl, valid, dst);
   }
 }
@@ -558,7 +605,7 @@ __device__ __forceinline__ void emit_planes4(const float (&o)[4], __nv_bfloat16*
 }
 
 template <int ACT>
-__global__ void bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __restrict__ dgamma, const double* __restrict__ dbeta,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_v4_kernel(BnBwdArgs a, V4Geom g, const double* __restrict__ dgamma, const double* __restrict__ dbeta,
                                        float* __restrict__ dx, __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo) {
   constexpr bool GLU = ACT == MOG_ACT_GLU;
   const int Co = GLU ? a.C / 2 : a.C;
@@ -627,7 +674,7 @@ static void launch_bwd_v4(bool reduce, const BnBwdArgs& a, const V4Geom& g, doub
                           __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr) {
   dim3 grid(g.nxb, g.nyb, a.S);
   if (reduce)
-    bn_bwd_reduce_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta);
+    bn_bwd_reduce_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma /* = the partial buffer */);
   else
     bn_bwd_apply_v4_kernel<ACT><<<grid, g.GB * g.R, 0, st>>>(a, g, dgamma, dbeta, dx, phi, plo);
 }
@@ -652,33 +699,41 @@ static bool bwd_v4(bool reduce, const BnBwdArgs& a, double* dgamma, double* dbet
 
 using namespace mog;
 
-extern "C" int mog_bn_stats(const float* x, int S, int M, int C, double* sum, double* sqsum, void* stream) {
-  MOG_REQUIRE(x && sum && sqsum && S > 0 && M > 0 && C > 0, "mog_bn_stats: bad argument");
+// number of partial slots P of the reducing kernels for a problem (which = 0: forward statistics, 1: backward sums)
+static int bn_parts_of(int S, int M, int C, int act, int which) {
+  const int width = (which == 1 && act == MOG_ACT_GLU) ? C / 2 : C;
+  if ((C & 3) == 0 && (width & 3) == 0 && S <= 65535) return v4_geom(width, M, S, true).nyb;
+  const int chunks = ceil_div(M, rows_per_block(M));
+  return chunks < 64 ? chunks : 64;
+}
+
+extern "C" int mog_bn_parts(int S, int M, int C, int act, int which) {
+  if (S <= 0 || M <= 0 || C <= 0) return 0;
+  return bn_parts_of(S, M, C, act, which);
+}
+
+extern "C" int mog_bn_stats(const float* x, int S, int M, int C, double* part, int nparts, void* stream) {
+  MOG_REQUIRE(x && part && S > 0 && M > 0 && C > 0, "mog_bn_stats: bad argument");
+  MOG_REQUIRE(nparts == bn_parts_of(S, M, C, MOG_ACT_NONE, 0), "mog_bn_stats: nparts must be mog_bn_parts(S, M, C, act, 0)");
   cudaStream_t st = as_stream(stream);
-  if (sqsum == sum + (size_t)S * C) {     // the two accumulators back to back (how ops.py allocates them): one memset
-    cudaMemsetAsync(sum, 0, 2 * sizeof(double) * S * C, st);
-  } else {
-    cudaMemsetAsync(sum, 0, sizeof(double) * S * C, st);
-    cudaMemsetAsync(sqsum, 0, sizeof(double) * S * C, st);
-  }
   MOG_REQUIRE(S <= 65535, "mog_bn_stats: too many segments");
   if ((C & 3) == 0) {
     const V4Geom g = v4_geom(C, M, S, true);
-    bn_stats_v4_kernel<<<dim3(g.nxb, g.nyb, S), g.GB * g.R, 0, st>>>(x, M, C, g, sum, sqsum);
+    bn_stats_v4_kernel<<<dim3(g.nxb, g.nyb, S), g.GB * g.R, 0, st>>>(x, M, C, g, part, S);
     return check_launch("bn_stats_v4_kernel");
   }
   const int rpb = rows_per_block(M);
-  dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
-  bn_stats_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(x, M, C, rpb, sum, sqsum);
+  dim3 grid(ceil_div(C, 32), nparts, S);
+  bn_stats_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(x, M, C, rpb, part, S);
   return check_launch("bn_stats_kernel");
 }
 
-extern "C" int mog_bn_finalize(const double* sum, const double* sqsum, int S, int M, int C, const float* gamma,
+extern "C" int mog_bn_finalize(const double* part, int nparts, int S, int M, int C, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean,
                                float* running_var, float* mean, float* invstd, float* scale, float* shift,
                                void* stream) {
-  MOG_REQUIRE(sum && sqsum && mean && invstd && scale && shift && S > 0 && M > 0 && C > 0, "mog_bn_finalize: bad argument");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(sum, sqsum, S, M, C, gamma, beta, eps, momentum,
+  MOG_REQUIRE(part && nparts > 0 && mean && invstd && scale && shift && S > 0 && M > 0 && C > 0, "mog_bn_finalize: bad argument");
+  bn_finalize_kernel<<<ceil_div(C, 8), 256, 0, as_stream(stream)>>>(part, nparts, S, M, C, gamma, beta, eps, momentum,
                                                                      running_mean, running_var, mean, invstd, scale, shift);
   return check_launch("bn_finalize_kernel");
 }
@@ -715,36 +770,39 @@ extern "C" int mog_affine_act_fwd_planes(const float* x, const float* scale, con
 
 extern "C" int mog_bn_act_bwd_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
                                      const float* gamma, const float* beta, int S, int M, int C, int act,
-                                     double* dgamma_seg, double* dbeta_seg, void* stream) {
-  MOG_REQUIRE(x && dy && mean && invstd && dgamma_seg && dbeta_seg && S > 0 && M > 0 && C > 0, "mog_bn_act_bwd_reduce: bad argument");
+                                     double* part, int nparts, double* dgamma_seg, double* dbeta_seg, float* dgamma,
+                                     float* dbeta, void* stream) {
+  MOG_REQUIRE(x && dy && mean && invstd && part && dgamma_seg && dbeta_seg && S > 0 && M > 0 && C > 0, "mog_bn_act_bwd_reduce: bad argument");
+  MOG_REQUIRE(nparts == bn_parts_of(S, M, C, act, 1), "mog_bn_act_bwd_reduce: nparts must be mog_bn_parts(S, M, C, act, 1)");
   cudaStream_t st = as_stream(stream);
-  if (dbeta_seg == dgamma_seg + (size_t)S * C) {
-    cudaMemsetAsync(dgamma_seg, 0, 2 * sizeof(double) * S * C, st);
-  } else {
-    cudaMemsetAsync(dgamma_seg, 0, sizeof(double) * S * C, st);
-    cudaMemsetAsync(dbeta_seg, 0, sizeof(double) * S * C, st);
-  }
   const int rpb = rows_per_block(M);
   BnBwdArgs a{x, dy, mean, invstd, gamma, beta, S, M, C, act, rpb};
-  if (bwd_v4(true, a, dgamma_seg, dbeta_seg, nullptr, st)) return check_launch("bn_bwd_reduce_v4_kernel");
-  dim3 grid(ceil_div(C, 32), ceil_div(M, rpb), S);
-  MOG_REQUIRE(grid.z <= 65535, "mog_bn_act_bwd_reduce: too many segments");
-  bn_bwd_reduce_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, dgamma_seg, dbeta_seg);
-  return check_launch("bn_bwd_reduce_kernel");
+  int rc;
+  if (bwd_v4(true, a, part, nullptr, nullptr, st)) {
+    rc = check_launch("bn_bwd_reduce_v4_kernel");
+  } else {
+    dim3 grid(ceil_div(C, 32), nparts, S);
+    MOG_REQUIRE(grid.z <= 65535, "mog_bn_act_bwd_reduce: too many segments");
+    bn_bwd_reduce_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, part);
+    rc = check_launch("bn_bwd_reduce_kernel");
+  }
+  if (rc) return rc;
+  // partials -> per-segment sums (read by the apply pass) + parameter gradients, fixed order
+  bn_bwd_sum_kernel<<<ceil_div(C, 8), 256, 0, st>>>(part, nparts, S, C, dgamma_seg, dbeta_seg, dgamma, dbeta);
+  return check_launch("bn_bwd_sum_kernel");
 }
 
 extern "C" int mog_bn_act_bwd_apply(const float* x, const float* dy, const float* mean, const float* invstd,
                                     const float* gamma, const float* beta, const double* dgamma_seg,
-                                    const double* dbeta_seg, int S, int M, int C, int act, float* dx, float* dgamma,
-                                    float* dbeta, void* stream) {
+                                    const double* dbeta_seg, int S, int M, int C, int act, float* dx, void* stream) {
   return mog_bn_act_bwd_apply_planes(x, dy, mean, invstd, gamma, beta, dgamma_seg, dbeta_seg, S, M, C, act, dx, nullptr, MOG_PREC_FP32,
-                                     dgamma, dbeta, stream);
+                                     stream);
 }
 
 extern "C" int mog_bn_act_bwd_apply_planes(const float* x, const float* dy, const float* mean, const float* invstd,
                                            const float* gamma, const float* beta, const double* dgamma_seg,
                                            const double* dbeta_seg, int S, int M, int C, int act, float* dx, void* dx_planes,
-                                           int precision, float* dgamma, float* dbeta, void* stream) {
+                                           int precision, void* stream) {
   MOG_REQUIRE(x && dy && dx && S > 0 && M > 0 && C > 0, "mog_bn_act_bwd_apply: bad argument");
   __nv_bfloat16* phi = nullptr;
   __nv_bfloat16* plo = nullptr;
@@ -771,12 +829,7 @@ extern "C" int mog_bn_act_bwd_apply_planes(const float* x, const float* dy, cons
     bn_bwd_apply_kernel<<<grid, 32 * RED_ROWS, 0, st>>>(a, dgamma_seg, dbeta_seg, dx);
     rc = check_launch("bn_bwd_apply_kernel");
   }
-  if (rc) return rc;
-  if (has_bn && (dgamma || dbeta)) {
-    bn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dgamma_seg, dbeta_seg, S, C, dgamma, dbeta);
-    return check_launch("bn_bwd_param_kernel");
-  }
-  return MOG_OK;
+  return rc;
 }
 
 extern "C" int mog_act_bwd(const float* dy, const float* y, float* dz, size_t n, int act, void* stream) {

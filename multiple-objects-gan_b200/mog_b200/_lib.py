@@ -58,19 +58,21 @@ SIGNATURES = {
     "mog_conv2d_fwd": (_i, [_dp, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mog_conv2d_dgrad": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
     "mog_conv2d_wgrad": (_i, [_dp, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "mog_bn_stats": (_i, [_p, _i, _i, _i, _p, _p, _p]),
-    "mog_bn_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "mog_bn_parts": (_i, [_i, _i, _i, _i, _i]),
+    "mog_bn_stats": (_i, [_p, _i, _i, _i, _p, _i, _p]),
+    "mog_bn_finalize": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "mog_affine_act_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "mog_affine_act_fwd_planes": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "mog_bn_act_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
-    "mog_bn_act_bwd_apply": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "mog_bn_act_bwd_apply_planes": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
+    "mog_bn_act_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
+    "mog_bn_act_bwd_apply": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "mog_bn_act_bwd_apply_planes": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "mog_act_bwd": (_i, [_p, _p, _p, _sz, _i, _p]),
     "mog_sumpool2x2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mog_stn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_stn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mog_word_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "mog_word_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mog_word_attention_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mog_word_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "mog_damsm_words_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     "mog_damsm_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mog_damsm_words_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _sz, _p]),

@@ -372,9 +372,48 @@ class Conv2dFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None, None
 
 
+def _tile_eff(H, W):
+    """Fraction of the 8 (w) x 16 (h) pixel sub-tiles of the halo-tile kernels that holds real pixels."""
+    return (H * W) / float(((H + 15) // 16) * ((W + 7) // 8) * 128)
+
+
+def _retile(x, weight, stride, pad, up2x, precision):
+    """Pixel-grid view that tiles better, for filters without taps along an axis (tcgen05 precisions).  The halo-tile kernels
+    cover an image with 8 x 16 pixel sub-tiles: a 17 x 17 map of the DAMSM image encoder fills 38 % of its 6 sub-tiles.
+    A 1 x 1 filter does not care which pixels are neighbours -- all N*H*W pixels become one [M/8, 8] grid (~100 %); a 1 x k
+    filter (taps along W only) lets the rows of all images stack into one [N*H, W] image (17 wide: 71 %).  Pure views: the
+    kernels, the packed weights and the bf16 planes ([pixels][C8]) are unchanged."""
+    if precision == PREC_FP32 or up2x or stride != 1 or x.dim() != 4 or weight.dim() != 4:
+        return None
+    N, H, W, Cc = x.shape
+    KH, KW = weight.shape[2], weight.shape[3]
+    ph, pw = (pad if isinstance(pad, (tuple, list)) else (pad, pad))
+    if KH != 1 or ph != 0 or N * H * W < 4096:
+        return None
+    M = N * H * W
+    if KW == 1 and pw == 0 and M % 8 == 0:
+        shape = (1, M // 8, 8, Cc)
+    elif N > 1:
+        shape = (1, N * H, W, Cc)
+    else:
+        return None
+    if _tile_eff(shape[1], shape[2]) < 1.15 * _tile_eff(H, W):
+        return None
+    return shape
+
+
 def conv2d(x, weight, bias=None, stride=1, pad=0, up2x=False, act=ACT_NONE, precision=None):
     if precision is None:
         precision = _default_precision
+    shape = _retile(x, weight, stride, pad, up2x, precision)
+    if shape is not None:
+        N, H, W, _ = x.shape
+        xv = x.reshape(shape)
+        cached = getattr(x, "_mog_planes", None)
+        if cached is not None and cached[2] == x._version and cached[3] == x.data_ptr():
+            xv._mog_planes = (cached[0], cached[1], xv._version, xv.data_ptr())     # same rows, same planes
+        y = Conv2dFn.apply(xv, weight, bias, stride, pad, False, act, precision)
+        return y.reshape(N, H, W, y.shape[-1])
     return Conv2dFn.apply(x, weight, bias, stride, pad, bool(up2x), act, precision)
 
 
@@ -388,6 +427,17 @@ def linear(x, weight, bias=None, act=ACT_NONE, precision=None):
 # ---------------------------------------------------------------------------------------------
 # BatchNorm (train) + activation (+ residual)
 # ---------------------------------------------------------------------------------------------
+_bn_parts_cache = {}
+
+
+def _bn_parts(S, M, Cc, act, which):
+    k = (S, M, Cc, act, which)
+    v = _bn_parts_cache.get(k)
+    if v is None:
+        v = _bn_parts_cache[k] = _lib.lib().mog_bn_parts(S, M, Cc, act, which)
+    return v
+
+
 class BnActFn(torch.autograd.Function):
     """y = act(BN_train(x)) (+ residual) over rows [S*M, C] with per-segment statistics."""
 
@@ -401,12 +451,13 @@ class BnActFn(torch.autograd.Function):
         M = rows // S
         dev = x.device
         st = _stream()
-        stats = torch.empty((2, S, Cc), device=dev, dtype=torch.float64)
-        call("mog_bn_stats", x.data_ptr(), S, M, Cc, stats[0].data_ptr(), stats[1].data_ptr(), st)
+        P = _bn_parts(S, M, Cc, act, 0)
+        part = torch.empty((P, 2, S, Cc), device=dev, dtype=torch.float64)     # per-block partial sums (summed in a fixed order)
+        call("mog_bn_stats", x.data_ptr(), S, M, Cc, part.data_ptr(), P, st)
         mis = torch.empty((4, S, Cc), device=dev, dtype=torch.float32)  # mean, invstd, scale, shift
         g = gamma.detach().contiguous()
         b = beta.detach().contiguous()
-        call("mog_bn_finalize", stats[0].data_ptr(), stats[1].data_ptr(), S, M, Cc, g.data_ptr(), b.data_ptr(),
+        call("mog_bn_finalize", part.data_ptr(), P, S, M, Cc, g.data_ptr(), b.data_ptr(),
              eps, momentum, _ptr(running_mean), _ptr(running_var), mis[0].data_ptr(), mis[1].data_ptr(),
              mis[2].data_ptr(), mis[3].data_ptr(), st)
         Co = Cc // 2 if act == ACT_GLU else Cc
@@ -428,19 +479,21 @@ class BnActFn(torch.autograd.Function):
         dy = dy.contiguous()
         st = _stream()
         dev = x.device
-        red = torch.empty((2, S, Cc), device=dev, dtype=torch.float64)
-        call("mog_bn_act_bwd_reduce", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
-             g.data_ptr(), b.data_ptr(), S, M, Cc, act, red[0].data_ptr(), red[1].data_ptr(), st)
-        dx = torch.empty_like(x)
+        P = _bn_parts(S, M, Cc, act, 1)
+        red = torch.empty((P + 1, 2, S, Cc), device=dev, dtype=torch.float64)   # P partials + the per-segment sums
         dgb = torch.empty((2, Cc), device=dev, dtype=torch.float32)
+        call("mog_bn_act_bwd_reduce", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
+             g.data_ptr(), b.data_ptr(), S, M, Cc, act, red.data_ptr(), P, red[P, 0].data_ptr(), red[P, 1].data_ptr(),
+             dgb[0].data_ptr(), dgb[1].data_ptr(), st)
+        dx = torch.empty_like(x)
         # dx usually is the output gradient of a convolution: emit it as bf16 planes too (saves that conv's split pass)
         prec = ctx.precision
         planes = None
         if prec != PREC_FP32 and x.dim() == 4 and Cc % 8 == 0:
             planes = torch.empty((_planes_bytes(S * M, Cc, prec) + 3) // 4, device=dev, dtype=torch.float32)
         call("mog_bn_act_bwd_apply_planes", x.data_ptr(), dy.data_ptr(), mis[0].data_ptr(), mis[1].data_ptr(),
-             g.data_ptr(), b.data_ptr(), red[0].data_ptr(), red[1].data_ptr(), S, M, Cc, act, dx.data_ptr(), _ptr(planes), prec,
-             dgb[0].data_ptr(), dgb[1].data_ptr(), st)
+             g.data_ptr(), b.data_ptr(), red[P, 0].data_ptr(), red[P, 1].data_ptr(), S, M, Cc, act, dx.data_ptr(), _ptr(planes), prec,
+             st)
         if planes is not None:
             _attach_planes(dx, planes, prec)
         dres = dy if ctx.has_res else None
@@ -578,9 +631,11 @@ class WordAttnFn(torch.autograd.Function):
         B, Q, D, T, quirk = ctx.cfg
         dout = dout.contiguous()
         dh = torch.empty_like(h)
-        dsrc = torch.zeros_like(src)
+        nws = _lib.lib().mog_word_attention_bwd_workspace_bytes(B, Q, D, T)
+        ws = torch.empty((nws + 3) // 4, device=h.device, dtype=torch.float32) if nws else None
+        dsrc = torch.empty_like(src) if nws else torch.zeros_like(src)     # (scalar fallback kernel accumulates atomically)
         call("mog_word_attention_bwd", h.data_ptr(), src.data_ptr(), _ptr(m), dout.data_ptr(), dh.data_ptr(),
-             dsrc.data_ptr(), B, Q, D, T, quirk, _stream())
+             dsrc.data_ptr(), B, Q, D, T, quirk, _ptr(ws), nws, _stream())
         return dh, dsrc, None, None, None
 
 
@@ -649,7 +704,7 @@ class ActFn(torch.autograd.Function):
         rows = x.numel() // Cc
         dx = torch.empty_like(x)
         call("mog_bn_act_bwd_apply", x.data_ptr(), dy.data_ptr(), None, None, None, None, None, None, 1, rows, Cc,
-             ctx.act, dx.data_ptr(), None, None, _stream())
+             ctx.act, dx.data_ptr(), _stream())
         return dx, None
 
 
