@@ -388,8 +388,15 @@ def run_mog(args):
             roof["step_peak"] = sus
         print(json.dumps(line))
     if ws > 1:
+        # Captured CUDA graphs hold NCCL kernels: tearing the communicator down under them hung (observed: 10 minutes, killed).
+        # Everything is finished and printed -- synchronise, meet at a barrier, and leave without the NCCL teardown.
+        sys.stdout.flush()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def ncu_traffic(B):
