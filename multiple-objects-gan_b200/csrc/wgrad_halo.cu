@@ -55,6 +55,7 @@ struct WHParams {
   int Cx8, Cy8;           // channel pitch of the x / dy planes
   int Cin, Cout;
   int tiles_w, tiles_h;
+  int tw, th, tn;         // pixel tile: tw x th pixels of tn images = 64 pixels (8 x 8 x 1, or 4 x 4 x 4 on 4 x 4 grids)
   long long total_tiles, tiles_per_split;
   int splits, passes, stages, tmem_cols;
   float* ws;              // [split][group * maxtaps + tap][co][ci]
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int nplanes = p.passes == 3 ? 2 : 1;
   const int blk_plain = PT * PT * 128;        // one 64-channel block of the un-shifted operand (dy)
-  const int blk_halo = PT * p.HH * 128;       // ... of the shifted operand (x)
+  const int blk_halo = p.tw * p.HH * p.tn * 128;   // ... of the shifted operand (x)
   const int blkA = p.swap ? blk_halo : blk_plain, blkB = p.swap ? blk_plain : blk_halo;
   const int regA = p.nblkA * blkA, regB = p.nblkB * blkB;
   const int plane_bytes = regA + regB;
@@ -140,17 +141,17 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
         const long long tile = tile_begin + it;
         const int tw_ = (int)(tile % p.tiles_w);
         const int th_ = (int)((tile / p.tiles_w) % p.tiles_h);
-        const int n = (int)(tile / tiles_per_img);
+        const int n = (int)(tile / tiles_per_img) * p.tn;    // (images beyond N: the TMA unit zero-fills)
         mbar_wait(&empty[s], ph ^ 1u);
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         wh_expect_tx(&full[s], tx);
         for (int pl = 0; pl < nplanes; ++pl) {
           const uint32_t pb = st + (uint32_t)(pl * plane_bytes);
           for (int b = 0; b < lx; ++b)
-            wh_tma_load_4d(pb + off_x + b * blk_halo, &maps.x[g.xview][pl], &full[s], cx0 + 64 * b, tw_ * PT + g.w_off,
-                           th_ * PT + g.h_org, n);
+            wh_tma_load_4d(pb + off_x + b * blk_halo, &maps.x[g.xview][pl], &full[s], cx0 + 64 * b, tw_ * p.tw + g.w_off,
+                           th_ * p.th + g.h_org, n);
           for (int b = 0; b < ly; ++b)
-            wh_tma_load_4d(pb + off_y + b * blk_plain, &maps.dy[g.yview][pl], &full[s], cy0 + 64 * b, tw_ * PT, th_ * PT, n);
+            wh_tma_load_4d(pb + off_y + b * blk_plain, &maps.dy[g.yview][pl], &full[s], cy0 + 64 * b, tw_ * p.tw, th_ * p.th, n);
         }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -297,13 +298,14 @@ static WhEncodeFn wh_encode_fn() {
 
 // 4-D (C, W, H, N) map of a bf16 NHWC plane [N][Hp][Wp][C8], optionally its stride-`vs` parity view (voh, vow);
 // box = {64 channels, 8 pixels, box_h rows, 1 image}, SWIZZLE_128B
-static int wh_encode(CUtensorMap* tm, const __nv_bfloat16* base, int N, int Hp, int Wp, int C8, int vs, int voh, int vow, int box_h) {
+static int wh_encode(CUtensorMap* tm, const __nv_bfloat16* base, int N, int Hp, int Wp, int C8, int vs, int voh, int vow, int box_w,
+                     int box_h, int box_n) {
   WhEncodeFn enc = wh_encode_fn();
   if (!enc) return fail(MOG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int Hv = (Hp - voh + vs - 1) / vs, Wv = (Wp - vow + vs - 1) / vs;
   cuuint64_t dims[4] = {(cuuint64_t)C8, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)vs * C8 * 2, (cuuint64_t)vs * Wp * C8 * 2, (cuuint64_t)Hp * Wp * C8 * 2};
-  cuuint32_t box[4] = {64u, (cuuint32_t)PT, (cuuint32_t)box_h, 1u};
+  cuuint32_t box[4] = {64u, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
   cuuint32_t es[4] = {1, 1, 1, 1};
   void* ptr = const_cast<__nv_bfloat16*>(base + ((size_t)voh * Wp + vow) * C8);
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -371,7 +373,11 @@ static bool wh_make_plan(const MogConvDesc& d, int Ho, int Wo, int passes, WHPla
   p = WHParams{};
   pl->Hg = mode == 1 ? d.H : Ho;
   pl->Wg = mode == 1 ? d.W : Wo;
-  if (pl->Hg < PT || pl->Wg < PT) return false;   // tiny grids: an 8 x 8 tile would be mostly padding
+  // 4 x 4 grids (the deep discriminator layers: img_code_s64*, jointConv): a tile packs 4 x 4 pixels of 4 images; rows of
+  // different images are not a uniform stride apart, so there is no halo -- every filter tap is its own group (own box)
+  const bool small = pl->Hg == 4 && pl->Wg == 4 && mode != 1;
+  if (!small && (pl->Hg < PT || pl->Wg < PT)) return false;   // other tiny grids: an 8 x 8 tile would be mostly padding
+  p.tw = small ? 4 : PT; p.th = small ? 4 : PT; p.tn = small ? 4 : 1;
   for (int k = 0; k < 16; ++k) pl->nsrc[k] = 0;
   const int nview = mode == 0 ? 1 : 2;   // per axis
   pl->nxv = mode == 2 ? 4 : 1;
@@ -389,6 +395,27 @@ static bool wh_make_plan(const MogConvDesc& d, int Ho, int Wo, int passes, WHPla
       const int ntw = wh_axis(mode, vb, d.KW, d.pad, d.stride, ow, mw);
       if (nth < 0 || ntw < 0) return false;
       if (nth == 0 || ntw == 0) continue;
+      if (small) {
+        for (int i = 0; i < nth; ++i)
+          for (int j = 0; j < ntw; ++j) {
+            if (ng == WH_MAXGROUPS) return false;
+            WHGroup& g = p.grp[ng];
+            g.xview = mode == 2 ? va * 2 + vb : 0;
+            g.yview = 0;
+            g.w_off = ow[j]; g.h_org = oh[i]; g.nth = 1; g.shift[0] = 0;
+            for (int x = 0; x < 2; ++x)
+              for (int y = 0; y < 2; ++y) {
+                const int kh = mh[i][x], kw = mw[j][y];
+                if (kh < 0 || kw < 0) continue;
+                const int k = kh * d.KW + kw;
+                if (pl->nsrc[k] == 4) return false;
+                pl->src[k][pl->nsrc[k]++] = ng * 4;   // provisional stride 4, fixed below
+              }
+            if (maxtaps < 1) maxtaps = 1;
+            ++ng;
+          }
+        continue;
+      }
       for (int j = 0; j < ntw; ++j) {
         if (ng == WH_MAXGROUPS) return false;
         WHGroup& g = p.grp[ng];
@@ -420,7 +447,7 @@ static bool wh_make_plan(const MogConvDesc& d, int Ho, int Wo, int passes, WHPla
   p.maxtaps = maxtaps;
   for (int k = 0; k < d.KH * d.KW; ++k)
     for (int u = 0; u < pl->nsrc[k]; ++u) pl->src[k][u] = (pl->src[k][u] / 4) * maxtaps + (pl->src[k][u] % 4);
-  p.HH = PT + maxshift;
+  p.HH = p.th + maxshift;
   p.Cx8 = whp8(d.Cin); p.Cy8 = whp8(d.Cout);
   p.Cin = d.Cin; p.Cout = d.Cout;
   // operand roles: the M operand is padded to 128 channels, the N operand to 16
@@ -436,9 +463,9 @@ static bool wh_make_plan(const MogConvDesc& d, int Ho, int Wo, int passes, WHPla
   p.n_mb = ceil_div(CA, 128);
   p.nblkA = 2;
   p.nblkB = ceil_div(p.Nmma, 64);
-  p.tiles_w = ceil_div(pl->Wg, PT);
-  p.tiles_h = ceil_div(pl->Hg, PT);
-  p.total_tiles = (long long)d.N * p.tiles_w * p.tiles_h;
+  p.tiles_w = ceil_div(pl->Wg, p.tw);
+  p.tiles_h = ceil_div(pl->Hg, p.th);
+  p.total_tiles = (long long)ceil_div(d.N, p.tn) * p.tiles_w * p.tiles_h;
   const long long per_split_ctas = (long long)ng * p.n_mb * p.n_nb;
   long long splits = (2 * kNumSMs) / per_split_ctas;
   if (splits < 1) splits = 1;
@@ -448,7 +475,7 @@ static bool wh_make_plan(const MogConvDesc& d, int Ho, int Wo, int passes, WHPla
   p.splits = (int)ceil_div_ll(p.total_tiles, p.tiles_per_split);
   p.passes = passes;
   const int nplanes = passes == 3 ? 2 : 1;
-  const int blk_plain = PT * PT * 128, blk_halo = PT * p.HH * 128;
+  const int blk_plain = PT * PT * 128, blk_halo = p.tw * p.HH * p.tn * 128;
   const int regA = p.nblkA * (p.swap ? blk_halo : blk_plain), regB = p.nblkB * (p.swap ? blk_plain : blk_halo);
   const int stage_bytes = nplanes * (regA + regB);
   int stages = (222 * 1024) / stage_bytes;
@@ -490,9 +517,9 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
       const int src = plane < nplanes ? plane : 0;   // unused maps alias plane 0 (never dereferenced)
       const WHView& xv = pl.xv[v < pl.nxv ? v : 0];
       const WHView& yv = pl.yv[v < pl.nyv ? v : 0];
-      int rc = wh_encode(&maps.x[v][plane], xb + src * x_elems, d.N, d.H, d.W, p.Cx8, xv.vs, xv.voh, xv.vow, p.HH);
+      int rc = wh_encode(&maps.x[v][plane], xb + src * x_elems, d.N, d.H, d.W, p.Cx8, xv.vs, xv.voh, xv.vow, p.tw, p.HH, p.tn);
       if (rc) return rc;
-      rc = wh_encode(&maps.dy[v][plane], yb + src * y_elems, d.N, Ho, Wo, p.Cy8, yv.vs, yv.voh, yv.vow, PT);
+      rc = wh_encode(&maps.dy[v][plane], yb + src * y_elems, d.N, Ho, Wo, p.Cy8, yv.vs, yv.voh, yv.vow, p.tw, p.th, p.tn);
       if (rc) return rc;
     }
   static bool attr_set = false;

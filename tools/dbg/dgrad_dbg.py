@@ -27,12 +27,9 @@ def run(N, H, Ci, Co, k, s, p, prec, scale=1.0):
     print("%s N%d H%d %d->%d k%d s%d p%d: y %.2e dx %.2e dw %.2e | dx err mean/ch %s" % (prec, N, H, Ci, Co, k, s, p, rely, rel, relw,
           ["%.1e" % v for v in e.mean(dim=(0, 2, 3))[:4].tolist()]))
 for prec in ("bf16x3",):
-    run(8, 4, 128, 64, 3, 1, 1, prec)
-    run(8, 4, 256, 128, 3, 1, 1, prec)
-    run(8, 8, 128, 256, 4, 2, 1, prec)
-    run(8, 4, 128, 64, 3, 1, 1, "fp32")
-    run(64, 4, 1536, 768, 3, 1, 1, prec)
-    run(16, 4, 128, 64, 3, 1, 1, prec)
-    run(8, 8, 128, 64, 3, 1, 1, prec)
-    run(8, 4, 128, 128, 3, 1, 1, prec)
-    run(8, 4, 64, 64, 3, 1, 1, prec)
+    run(64, 4, 256, 128, 3, 1, 1, prec)
+    run(31, 4, 1024, 768, 3, 1, 1, prec)
+    run(64, 8, 128, 256, 4, 2, 1, prec)
+    run(6, 4, 64, 64, 3, 1, 1, prec)
+    run(64, 4, 3072, 1536, 3, 1, 1, prec)
+    run(64, 8, 1536, 3072, 4, 2, 1, prec)
