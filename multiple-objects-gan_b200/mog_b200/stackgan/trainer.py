@@ -9,8 +9,8 @@ Differences, all behind the same results: one process per GPU with an NCCL all-r
 (``mog_b200.parallel.GradBucket``) instead of ``nn.parallel.data_parallel``; the discriminator's
 weight gradients are not computed during the G step (the reference computes them and never uses
 them: ``netD.zero_grad()`` precedes the next D step, trainer.py:204); no ``.item()`` host syncs in
-the step.  TensorBoard summaries and image dumps (trainer.py:237-266) and ``sample`` (:285-420) are
-outside the hot path.
+the step.  TensorBoard summaries and image dumps (trainer.py:237-266) are outside the hot path; ``sample`` (:287-420)
+generates the reference's [real | 9 fakes] rows from a checkpoint with the generator in eval mode.
 """
 from __future__ import annotations
 
@@ -29,6 +29,9 @@ from .miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator
 
 class GANTrainer(object):
     def __init__(self, output_dir):
+        from .. import ops
+        parallel.init_from_env()          # one process per GPU under torchrun (no-op for a plain launch)
+        ops.precision_from_cfg(cfg)
         if cfg.TRAIN.FLAG and output_dir:
             self.model_dir = os.path.join(output_dir, 'Model')
             self.image_dir = os.path.join(output_dir, 'Image')
@@ -191,3 +194,88 @@ class GANTrainer(object):
                     save_model(netG, netD, optimizerG, optimizerD, epoch, self.model_dir)
         if parallel.rank() == 0:
             save_model(netG, netD, optimizerG, optimizerD, epoch, self.model_dir)
+
+    # ------------------------------------------------------------------ sampling (generator in eval mode)
+    def sample(self, datapath, num_samples=25, stage=1, draw_bbox=True, max_objects=3, data=None):
+        """trainer.py:287-420 -- ``num_samples`` rows [validation image | 9 generated images] for random validation captions,
+        saved to ``<NET_G>_visualize_bbox/<caption>.png``.  ``data`` (optional) supplies what the reference reads from
+        ``datapath`` (``val_captions.t7`` via torchfile, ``filenames.pickle``, the label / bbox pickles, the jpg images):
+        ``{"embeddings" [n,1024], "captions" [n], "label" [n,3,1], "bbox" [n,3,4] (stage II: a pair), "images" [n,3,S,S] or None}``."""
+        import numpy as np
+        import torchvision.utils as vutils
+        nets = self.load_network_stageI() if stage == 1 else self.load_network_stageII()
+        if nets is None:
+            return None
+        netG = nets[0].eval()
+        dev = next(netG.parameters()).device
+        if data is None:
+            data = self._load_sample_data(datapath, stage)
+        embeddings = np.asarray(data["embeddings"], np.float32)
+        captions_list, n = list(data["captions"]), len(data["captions"])
+        label = torch.as_tensor(data["label"]).to(dev)
+        bbox = data["bbox"]
+        bbox = [torch.as_tensor(b).to(dev).float() for b in bbox] if stage == 2 else torch.as_tensor(bbox).to(dev).float()
+        bbox_ = (bbox[0] if stage == 2 else bbox).clone()
+        first = bbox[0] if stage == 2 else bbox
+        tinv = compute_transformation_matrix_inverse(first.view(-1, 4)).view(n, max_objects, 2, 3)
+        if stage == 2:
+            tinv2 = compute_transformation_matrix_inverse(bbox[1].view(-1, 4)).view(n, max_objects, 2, 3)
+            t2 = compute_transformation_matrix(bbox[1].view(-1, 4)).view(n, max_objects, 2, 3)
+        _labels = label.long().view(n, max_objects, 1).clone()
+        _labels[_labels < 0] = 80
+        label_one_hot = torch.zeros(n, max_objects, 81, device=dev).scatter_(2, _labels, 1.0)
+        save_dir = cfg.NET_G[:cfg.NET_G.find('.pth')] + "_visualize_bbox"
+        mkdir_p(save_dir)
+        imsize = 64 if stage == 1 else 256
+        written = []
+        for count in range(num_samples):
+            index = int(np.random.randint(0, n, 1)[0])
+            val_image = torch.zeros(1, 3, imsize, imsize)
+            if data.get("images") is not None:
+                val_image = torch.as_tensor(data["images"][index]).float().view(1, 3, imsize, imsize)
+            txt = torch.from_numpy(np.reshape(embeddings[index], (1, -1)).repeat(9, 0)).to(dev)
+            rep = lambda t: t[index].view(1, max_objects, 2, 3).repeat(9, 1, 1, 1)   # noqa: E731
+            onehot9 = label_one_hot[index].view(1, max_objects, 81).repeat(9, 1, 1)
+            noise = torch.empty(9, cfg.Z_DIM, device=dev).normal_(0, 1)
+            with torch.no_grad():
+                if stage == 1:
+                    _, fake_imgs, _, _, _ = netG(txt, noise, rep(tinv), onehot9)
+                else:
+                    _, fake_imgs, _, _, _ = netG(txt, noise, rep(tinv), rep(t2), rep(tinv2), onehot9)
+            data_img = torch.zeros(10, 3, imsize, imsize)
+            data_img[0] = val_image
+            data_img[1:10] = fake_imgs.detach().float().cpu()
+            if draw_bbox:
+                for idx in range(max_objects):
+                    x, y, w, h = tuple([int(imsize * float(v)) for v in bbox_[index, idx]])
+                    w = imsize - 1 if w > imsize - 1 else w
+                    h = imsize - 1 if h > imsize - 1 else h
+                    if x <= -1:
+                        break
+                    x2, y2 = min(x + w, imsize - 1), min(y + h, imsize - 1)
+                    data_img[:10, :, y, x:x + w] = 1
+                    data_img[:10, :, y:y + h, x] = 1
+                    data_img[:10, :, y2, x:x + w] = 1
+                    data_img[:10, :, y:y + h, x2] = 1
+            path = '{}/{}.png'.format(save_dir, str(captions_list[index]).replace("/", "_")[:150])
+            vutils.save_image(data_img, path, normalize=True, nrow=10)
+            written.append(path)
+        print("Saved {} files to {}".format(len(written), save_dir))
+        return written
+
+    @staticmethod
+    def _load_sample_data(datapath, stage):
+        """The validation files of trainer.py:299-309 (needs the ``torchfile`` package for ``val_captions.t7``)."""
+        import pickle
+        import numpy as np
+        try:
+            import torchfile
+        except ImportError as e:
+            raise RuntimeError("sample(): reading %sval_captions.t7 needs the `torchfile` package; pass data=... instead" % datapath) from e
+        t_file = torchfile.load(datapath + "val_captions.t7")
+        with open(os.path.join(datapath, 'bboxes.pickle'), 'rb') as f:
+            bbox = np.asarray(pickle.load(f, encoding='latin1'))
+        with open(os.path.join(datapath, 'labels.pickle'), 'rb') as f:
+            label = np.asarray(pickle.load(f, encoding='latin1'))
+        return {"embeddings": np.concatenate(t_file.fea_txt, axis=0), "captions": list(t_file.raw_txt), "label": label,
+                "bbox": [bbox, bbox] if stage == 2 else bbox, "images": None}

@@ -235,8 +235,8 @@ def compute_generator_loss(netD, fake_imgs, real_labels, local_label, transf_mat
 
 
 def weights_init(m):
-    ops.invalidate_packed(m.parameters(recurse=False))     # .data writes below are invisible to torch's version counter
     """multi-mnist/miscc/utils.py:127-137 -- N(0, 0.02) by class name."""
+    ops.invalidate_packed(m.parameters(recurse=False))     # .data writes below are invisible to torch's version counter
     classname = m.__class__.__name__
     if classname.find('Conv') != -1:
         m.weight.data.normal_(0.0, 0.02)
@@ -247,3 +247,169 @@ def weights_init(m):
         m.weight.data.normal_(0.0, 0.02)
         if m.bias is not None:
             m.bias.data.fill_(0.0)
+
+
+def save_model(netG, netD, optimG, optimD, epoch, model_dir, saveD=False, saveOptim=False, max_to_keep=5):
+    """multi-mnist/miscc/utils.py:160-174 (same checkpoint dict and rotation)."""
+    import glob
+    import os
+    checkpoint = {'epoch': epoch, 'netG': netG.state_dict(), 'optimG': optimG.state_dict() if saveOptim else {},
+                  'netD': netD.state_dict() if saveD else {}, 'optimD': optimD.state_dict() if saveOptim else {}}
+    torch.save(checkpoint, "{}/checkpoint_{:04}.pth".format(model_dir, epoch))
+    if max_to_keep is not None and max_to_keep > 0:
+        ckpts = sorted(glob.glob(model_dir + "/" + '*.pth'))
+        while len(ckpts) > max_to_keep:
+            os.remove(ckpts[0])
+            ckpts = ckpts[1:]
+
+
+class Stage1Trainer(object):
+    """``GANTrainer`` of the single-stage programs -- libmog edition of ``code/multi-mnist/trainer.py`` and
+    ``code/clevr/trainer.py`` (``GANTrainer(output_dir)``, ``load_network_stageI``, ``train(data_loader[, stage])``).  The body of
+    the hot loop (multi-mnist/trainer.py:134-157, clevr/trainer.py:130-154) is :meth:`train_step`; one process per GPU with an
+    NCCL all-reduce per network; the discriminator's never-used weight gradient of the G step is not computed; no ``.item()``
+    host syncs in the step.  TensorBoard summaries / image dumps (trainer.py:159-190) and ``sample`` are outside the hot path."""
+
+    program = None     # 'mnist' | 'clevr' (set by the per-program subclass, with cfg / model / losses)
+
+    def __init__(self, output_dir):
+        import os
+        from . import parallel
+        cfg = self.cfg
+        parallel.init_from_env()
+        ops.precision_from_cfg(cfg)
+        if cfg.TRAIN.FLAG and output_dir:
+            self.model_dir = os.path.join(output_dir, 'Model')
+            self.image_dir = os.path.join(output_dir, 'Image')
+            self.log_dir = os.path.join(output_dir, 'Log')
+            for d in (self.model_dir, self.image_dir, self.log_dir):
+                os.makedirs(d, exist_ok=True)
+        self.max_epoch = cfg.TRAIN.MAX_EPOCH
+        self.snapshot_interval = cfg.TRAIN.SNAPSHOT_INTERVAL
+        self.max_objects = self.n_objects
+        self.gpus = [int(ix) for ix in str(cfg.GPU_ID).split(',')]
+        self.num_gpus = len(self.gpus)
+        self.batch_size = cfg.TRAIN.BATCH_SIZE
+
+    def load_network_stageI(self):
+        """multi-mnist/trainer.py:48-72"""
+        from . import parallel
+        cfg = self.cfg
+        netG, netD = self.model.STAGE1_G(), self.model.STAGE1_D()
+        netG.apply(weights_init)
+        netD.apply(weights_init)
+        if cfg.NET_G != '':
+            netG.load_state_dict(torch.load(cfg.NET_G, map_location='cpu')["netG"])
+        if cfg.NET_D != '':
+            netD.load_state_dict(torch.load(cfg.NET_D, map_location='cpu'))
+        if cfg.CUDA:
+            netG.cuda()
+            netD.cuda()
+        netG.train()
+        netD.train()
+        parallel.broadcast_params(netG)
+        parallel.broadcast_params(netD)
+        return netG, netD
+
+    def define_optimizers(self, netG, netD):
+        from . import optim as mog_optim
+        cfg = self.cfg
+        A = mog_optim.Adam if next(netD.parameters()).is_cuda else torch.optim.Adam
+        optimizerD = A(netD.parameters(), lr=cfg.TRAIN.DISCRIMINATOR_LR, betas=(0.5, 0.999))
+        optimizerG = A([p for p in netG.parameters() if p.requires_grad], lr=cfg.TRAIN.GENERATOR_LR, betas=(0.5, 0.999))
+        return optimizerG, optimizerD
+
+    def make_step_state(self, netG, netD, optimizerG, optimizerD, batch_size=None):
+        from . import parallel
+        B = batch_size or self.batch_size
+        dev = next(netD.parameters()).device
+        st = {"netG": netG, "netD": netD, "optG": optimizerG, "optD": optimizerD,
+              "real_labels": torch.ones(B, device=dev), "fake_labels": torch.zeros(B, device=dev)}
+        if parallel.world() > 1:
+            st["bucketG"] = parallel.GradBucket(netG.parameters())
+            st["bucketD"] = parallel.GradBucket(netD.parameters())
+        return st
+
+    def train_step(self, st, real_imgs, label_one_hot, transf_matrices, transf_matrices_inv, noise=None, optimize=True):
+        """One iteration of multi-mnist/trainer.py:134-157 / clevr/trainer.py:130-154.  Returns (errD, errG) device scalars."""
+        from . import optim as mog_optim
+        from . import parallel
+        netG, netD = st["netG"], st["netD"]
+        multi = parallel.world() > 1
+        B = real_imgs.shape[0]
+        if noise is None:
+            noise = torch.empty(B, self.cfg.Z_DIM, device=real_imgs.device).normal_(0, 1)
+        out = netG(noise, transf_matrices_inv, label_one_hot)
+        fake_imgs = out[1] if isinstance(out, tuple) else out
+        netD.zero_grad(set_to_none=True)
+        errD, _, _, _ = self.losses.compute_discriminator_loss(netD, real_imgs, fake_imgs, st["real_labels"], st["fake_labels"],
+                                                               label_one_hot, transf_matrices, transf_matrices_inv, self.gpus)
+        errD.backward()      # (the reference passes retain_graph=True; nothing of this graph is used again)
+        fusedD = isinstance(st["optD"], mog_optim.Adam)
+        if multi:
+            st["bucketD"].launch()
+            st["bucketD"].finish(scale=not fusedD)
+        if optimize:
+            if fusedD:
+                st["optD"].step(grad_scale=1.0 / parallel.world() if multi else 1.0)
+            else:
+                st["optD"].step()
+        for p in netD.parameters():
+            p.requires_grad_(False)
+        netG.zero_grad(set_to_none=True)
+        errG = self.losses.compute_generator_loss(netD, fake_imgs, st["real_labels"], label_one_hot, transf_matrices,
+                                                  transf_matrices_inv, self.gpus)
+        errG.backward()
+        for p in netD.parameters():
+            p.requires_grad_(True)
+        fusedG = isinstance(st["optG"], mog_optim.Adam)
+        if multi:
+            st["bucketG"].launch()
+            st["bucketG"].finish(scale=not fusedG)
+        if optimize:
+            if fusedG:
+                st["optG"].step(grad_scale=1.0 / parallel.world() if multi else 1.0)
+            else:
+                st["optG"].step()
+        return errD.detach(), errG.detach()
+
+    def unpack_batch(self, data, dev):
+        """DataLoader item -> (real_imgs, label_one_hot, theta, theta^-1) on the device (program specific)."""
+        raise NotImplementedError
+
+    def train(self, data_loader, stage=1, max_steps=None):
+        import time
+        from . import parallel
+        cfg = self.cfg
+        netG, netD = self.load_network_stageI()
+        dev = next(netD.parameters()).device
+        optimizerG, optimizerD = self.define_optimizers(netG, netD)
+        st = self.make_step_state(netG, netD, optimizerG, optimizerD)
+        generator_lr, discriminator_lr = cfg.TRAIN.GENERATOR_LR, cfg.TRAIN.DISCRIMINATOR_LR
+        count, epoch = 0, 0
+        errD = errG = torch.zeros(())
+        for epoch in range(self.max_epoch):
+            start_t = time.time()
+            if epoch % cfg.TRAIN.LR_DECAY_EPOCH == 0 and epoch > 0:      # trainer.py:107-113
+                generator_lr *= 0.5
+                discriminator_lr *= 0.5
+                for g in optimizerG.param_groups:
+                    g['lr'] = generator_lr
+                for g in optimizerD.param_groups:
+                    g['lr'] = discriminator_lr
+            for data in data_loader:
+                real_imgs, label_one_hot, tm, tmi = self.unpack_batch(data, dev)
+                errD, errG = self.train_step(st, real_imgs, label_one_hot, tm, tmi)
+                count += 1
+                if max_steps is not None and count >= max_steps:
+                    break
+            if parallel.rank() == 0:
+                print('[%d/%d] Loss_D: %.4f Loss_G: %.4f Total Time: %.2fsec'
+                      % (epoch, self.max_epoch, float(errD), float(errG), time.time() - start_t))
+                if epoch % self.snapshot_interval == 0 and getattr(self, "model_dir", None):
+                    save_model(netG, netD, optimizerG, optimizerD, epoch, self.model_dir)
+            if max_steps is not None and count >= max_steps:
+                break
+        if parallel.rank() == 0 and getattr(self, "model_dir", None):
+            save_model(netG, netD, optimizerG, optimizerD, epoch, self.model_dir)
+        return st

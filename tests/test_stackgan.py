@@ -174,3 +174,33 @@ def test_trainer_step_stage1_updates_both_networks():
         assert all(p.requires_grad for p in netD.parameters())
     finally:
         ops.set_precision("fp32")
+
+
+@pytest.mark.gpu
+def test_sample_stage1_from_checkpoint(tmp_path):
+    """``GANTrainer.sample`` (stackgan/trainer.py:287-420): rows [validation image | 9 fakes] from a checkpoint written by
+    ``save_model``, generator in eval mode (running statistics)."""
+    import os
+    import numpy as np
+    from mog_b200.stackgan.miscc.utils import save_model
+    from mog_b200.stackgan.trainer import GANTrainer
+    _, meta = gu.load("stackgan_s1")
+    c = meta["cfg"]
+    M, U, cfg = _set_cfg(c, 1)
+    cfg.TRAIN.FLAG = False
+    tr = GANTrainer("")
+    netG, netD = tr.load_network_stageI()
+    optG, optD = tr.define_optimizers(netG, netD)
+    os.makedirs(tmp_path / "Model")
+    save_model(netG, netD, optG, optD, 3, str(tmp_path / "Model"))
+    cfg.NET_G = str(tmp_path / "Model" / "checkpoint_0003.pth")
+    rng = np.random.RandomState(0)
+    n = 5
+    b = _batch(c, 1, 11)
+    bbox = -np.ones((n, 3, 4), np.float32)
+    bbox[:, 0] = (0.1, 0.2, 0.5, 0.4)
+    data = {"embeddings": rng.standard_normal((n, b["txt_embedding"].shape[1])).astype(np.float32),
+            "captions": ["a caption %d" % i for i in range(n)], "label": np.array([[[3], [-1], [-1]]] * n), "bbox": bbox,
+            "images": rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)}
+    files = tr.sample("", num_samples=3, stage=1, draw_bbox=True, data=data)
+    assert len(files) == 3 and all(os.path.isfile(f) for f in files)

@@ -108,3 +108,45 @@ def test_libmog_matches_reference(prog, prec):
                 gu.check(p.grad, G["G/grad/" + k], tol_g, "G grad " + k)
     finally:
         ops.set_precision("fp32")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", ["mnist", "clevr"])
+def test_gan_trainer_trains(prog, tmp_path):
+    """``GANTrainer(output_dir).train(data_loader)`` of the Multi-MNIST / CLEVR programs (multi-mnist/trainer.py:74-190,
+    clevr/trainer.py:73-186): loader tuples of the reference's datasets, fused Adam, checkpoint dict of ``save_model``."""
+    import glob
+    import torch.utils.data
+    _, meta = gu.load("stage1_" + prog)
+    c = meta["cfg"]
+    M, U = _set_cfg(prog, c)
+    if prog == "mnist":
+        from mog_b200.multi_mnist.trainer import GANTrainer
+        from mog_b200.multi_mnist.miscc.config import cfg
+    else:
+        from mog_b200.clevr.trainer import GANTrainer
+        from mog_b200.clevr.miscc.config import cfg
+    cfg.TRAIN.BATCH_SIZE, cfg.TRAIN.MAX_EPOCH, cfg.TRAIN.SNAPSHOT_INTERVAL = 4, 1, 1
+    b = synth.stage1_batch(prog, 8, nz=c["Z_DIM"], seed=3)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 8
+
+        def __getitem__(self, i):
+            if prog == "mnist":    # (image, bbox, label)
+                return b["imgs"][i], b["bbox"][i], b["label_one_hot"][i]
+            return b["imgs"][i], [b["transf_matrices"][i], b["transf_matrices_inv"][i]], b["label_one_hot"][i], 0
+
+    tr = GANTrainer(str(tmp_path))
+    loader = torch.utils.data.DataLoader(DS(), batch_size=4, drop_last=True, shuffle=False)
+    st = tr.train(loader)
+    ck = sorted(glob.glob(str(tmp_path / "Model" / "*.pth")))
+    assert ck
+    sd = torch.load(ck[-1], map_location="cpu")
+    assert set(sd) == {"epoch", "netG", "optimG", "netD", "optimD"}
+    for k, v in st["netG"].state_dict().items():
+        assert torch.equal(sd["netG"][k], v.cpu()), k
+    for p in st["netG"].parameters():
+        assert bool(torch.isfinite(p).all())
+    assert all(float(o.state_dict()["state"][0]["step"]) == 2 for o in (st["optG"], st["optD"]))
