@@ -158,3 +158,42 @@ def test_pack_plan_is_consistent_with_packed_bytes(built):
     # filters beyond 16 taps are left to mog_pack_weight
     d = built.MogConvDesc(2, 35, 35, 48, 64, 5, 5, 1, 2, 0, 0, built.PREC_BF16X3, 0)
     assert L.mog_pack_plan(C.byref(d), 0, C.c_void_p(0x1000), C.c_void_p(base), buf, 16) < 0
+
+
+def test_reference_checkpoint_loads(tmp_path):
+    """f4: a checkpoint written by the UNMODIFIED reference trainer's ``save_model`` (trainer.py:173-199, run here through
+    baseline/write_ref_checkpoint.py) resumes in the libmog trainer: networks, epoch and Adam state."""
+    import subprocess
+    import sys
+    import torch
+    from baseline import ref_harness as H
+    if not H.available():
+        pytest.skip("reference sources not staged (baseline/_ref) on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    model_dir = tmp_path / "Model"
+    os.makedirs(model_dir)
+    r = subprocess.run([sys.executable, os.path.join(root, "baseline", "write_ref_checkpoint.py"), str(model_dir), "7"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "written" in r.stdout, r.stderr[-2000:]
+    ck = torch.load(str(model_dir / "checkpoint_0007.pth"), map_location="cpu")
+    from mog_b200.attngan.miscc.config import cfg, reset_cfg
+    from mog_b200.attngan.trainer import condGANTrainer
+    reset_cfg()
+    cfg.CUDA = False
+    cfg.GAN.GF_DIM, cfg.GAN.DF_DIM, cfg.GAN.Z_DIM, cfg.GAN.R_NUM = 4, 4, 20, 1
+    cfg.TEXT.EMBEDDING_DIM, cfg.TEXT.WORDS_NUM = 16, 6
+    cfg.TRAIN.FLAG = True
+    tr = condGANTrainer(str(tmp_path), [], 10, {}, resume=True)
+    _, _, netG, netsD, epoch = tr.build_models(load_encoders=False)
+    assert epoch == 8
+    for k, v in netG.state_dict().items():
+        assert torch.equal(v, ck["netG"][k]), k
+    for i, d in enumerate(netsD):
+        for k, v in d.state_dict().items():
+            assert torch.equal(v, ck["netD"][i][k]), (i, k)
+    optG, optDs = tr.define_optimizers(netG, netsD)
+    sdG = optG.state_dict()
+    assert len(sdG["state"]) == len(ck["optimG"]["state"]) > 0
+    for i, s in sdG["state"].items():
+        assert float(s["step"]) == 1.0
+        assert torch.equal(s["exp_avg"], ck["optimG"]["state"][i]["exp_avg"])
