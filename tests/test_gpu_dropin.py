@@ -129,3 +129,23 @@ def test_packed_weights_follow_data_writes():
         y2 = d2(x)
     assert float((y1 - y2).abs().max()) > 1e-3       # the two nets differ
     assert float((y12 - y2).norm() / y2.norm()) < 1e-6
+
+
+def test_integration_md_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md section 2 is executed as written (argument count / byte sizes of the C ABI)."""
+    import re
+    import torch.nn.functional as F
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes, torch\n.*?)```", text, re.S).group(1)
+    block = block.replace('ctypes.CDLL("mog_b200/libmog.so")',
+                          'ctypes.CDLL(%r)' % os.path.join(ROOT, "multiple-objects-gan_b200", "mog_b200", "libmog.so"))
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 96, 32, 32, generator=g)
+    w = torch.randn(96, 96, 3, 3, generator=g) / 29.4
+    y = ns["conv3x3_up2x"](x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda())
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, 1, 1)
+    rel = float((y.permute(0, 3, 1, 2).cpu().double() - ref.double()).norm() / ref.double().norm())
+    assert rel < 5e-5, rel
