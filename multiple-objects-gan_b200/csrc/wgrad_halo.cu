@@ -252,7 +252,8 @@ struct WHReduceArgs {
   int nsrc[16];
   int src[16][4];
 };
-__global__ void wgrad_halo_reduce_kernel(const WHReduceArgs a) {
+// many splits (the big generator layers: up to ~100 partials per element): one thread per (tap, co, ci), 8 loads in flight
+__global__ void wgrad_halo_reduce_split_kernel(const WHReduceArgs a) {
   // one thread per (filter tap k, co, ci): reads coalesced along ci, fixed summation order (deterministic),
   // 8 independent partial sums in flight to cover the L2 latency
   const size_t per_tap = (size_t)a.Cin * a.Cout;
@@ -276,6 +277,44 @@ __global__ void wgrad_halo_reduce_kernel(const WHReduceArgs a) {
     }
   }
   a.dw[idx * a.KHW + k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+
+
+// One block per (co, 64-channel chunk of ci): the KHW x 64 sums are formed with reads coalesced along ci (fixed summation
+// order: deterministic; 4 independent partial sums per thread in flight), staged in shared memory and written as ONE contiguous
+// 64 * KHW float run of the OIHW tensor.  (The first version wrote dw[(co*Cin + ci)*KHW + k] from a thread per (k, co, ci):
+// a 4-byte store every KHW floats, 8x write amplification -- 895 us for the 1536 -> 3072 4x4 layer, 0.67 TB/s.)
+constexpr int WR_CI = 64;
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WHReduceArgs a) {
+  __shared__ float tile[16][WR_CI + 1];
+  const size_t per_tap = (size_t)a.Cin * a.Cout;
+  const size_t per_split = (size_t)a.nent * per_tap;
+  const int co = blockIdx.y, c0 = blockIdx.x * WR_CI;
+  const int cl = threadIdx.x % WR_CI, kq = threadIdx.x / WR_CI;      // 4 tap lanes
+  const int ci = c0 + cl;
+  for (int k = kq; k < a.KHW; k += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ci < a.Cin) {
+      const int ns = a.nsrc[k];
+      const int total = a.splits * ns;
+      const size_t idx = (size_t)co * a.Cin + ci;
+      for (int i0 = 0; i0 < total; i0 += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          if (i < total) {
+            const int z = i / ns, u = i - z * ns;
+            acc[j] += __ldg(a.ws + (size_t)z * per_split + (size_t)a.src[k][u] * per_tap + idx);
+          }
+        }
+      }
+    }
+    tile[k][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+  __syncthreads();
+  const int nci = min(WR_CI, a.Cin - c0);
+  float* o = a.dw + ((size_t)co * a.Cin + c0) * a.KHW;
+  for (int e = threadIdx.x; e < nci * a.KHW; e += blockDim.x) o[e] = tile[e % a.KHW][e / a.KHW];
 }
 
 }  // namespace tc
@@ -539,8 +578,15 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
     ra.nsrc[k] = pl.nsrc[k];
     for (int u = 0; u < 4; ++u) ra.src[k][u] = pl.src[k][u];
   }
-  const size_t total = (size_t)d.Cin * d.Cout;
-  wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 128), (unsigned)(d.KH * d.KW)), 128, 0, st>>>(ra);
+  int max_src = 1;
+  for (int k = 0; k < d.KH * d.KW; ++k) max_src = pl.nsrc[k] > max_src ? pl.nsrc[k] : max_src;
+  if (p.splits * max_src <= 8) {
+    // few partials, large tensors (the deep discriminator layers): the pass is a layout change -> coalesced OIHW runs
+    wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div(d.Cin, WR_CI), (unsigned)d.Cout), 256, 0, st>>>(ra);
+  } else {
+    const size_t total = (size_t)d.Cin * d.Cout;
+    wgrad_halo_reduce_split_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 128), (unsigned)(d.KH * d.KW)), 128, 0, st>>>(ra);
+  }
   return check_launch("wgrad_halo_reduce_kernel");
 }
 
