@@ -79,6 +79,8 @@ struct HaloParams {
   const float* bias;
   int act, accum_dst;
   int tma_store;                   // epilogue through shared memory + TMA stores (Cd % 4 == 0, no accumulate)
+  int single;                      // 1: a work item is ONE sub-tile (the second MMA warp idles): small problems that would leave
+                                   // more than half of the SMs without a tile pair
   int N, Hr, Wr, Cd, Hd, Wd, dsh, doh, dsw, dow;
 };
 
@@ -161,6 +163,11 @@ __device__ __forceinline__ void halo_decode(const HaloParams& p, long long sub, 
   *h0 = th_ * p.th;
   *w0 = tw_ * p.tw;
 }
+// sub-tile s (0 / 1) of a work item's pair; in single mode the second sub-tile does not exist (decodes beyond N)
+__device__ __forceinline__ long long halo_sub(const HaloParams& p, long long pair, int s) {
+  if (!p.single) return pair * 2 + s;
+  return s == 0 ? pair : (long long)p.tiles_n * p.tiles_w * p.tiles_h;   // first index past the last sub-tile: n >= N
+}
 // work item -> (sub-tile pair, N tile, K split)
 __device__ __forceinline__ void halo_item(const HaloParams& p, long long tile, long long* pair, int* ntile, int* ks) {
   *ks = (int)(tile % p.ksplit);
@@ -213,8 +220,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         int ntile_, ks;
         halo_item(p, tile, &pair, &ntile_, &ks);
         int n[2], h0[2], w0[2];
-        halo_decode(p, pair * 2, &n[0], &h0[0], &w0[0]);
-        halo_decode(p, pair * 2 + 1, &n[1], &h0[1], &w0[1]);
+        halo_decode(p, halo_sub(p, pair, 0), &n[0], &h0[0], &w0[0]);
+        halo_decode(p, halo_sub(p, pair, 1), &n[1], &h0[1], &w0[1]);
         const int it_end = min((ks + 1) * p.kper, p.niter);
         for (int it = ks * p.kper; it < it_end; ++it) {
           const int gi = it / p.nchunk, c = it - gi * p.nchunk;
@@ -263,6 +270,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     // ===================== MMA issuers: warp 1 -> sub-tile 0, warp 2 -> sub-tile 1 ================
     // (all lanes run the loop so that addresses stay in uniform registers; one elected lane issues)
     const int sub = warp - 1;
+    const bool active = !(p.single && sub == 1);     // single mode: this warp only keeps the barrier protocol going
     const uint32_t idesc = make_idesc_bf16(BM, p.BN);
     const uint32_t dhi = desc_hi_sw64();
     int sa = 0, sb = 0, as = 0;
@@ -286,9 +294,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             const uint32_t sh = (uint32_t)g.shift[a] * (uint32_t)(p.tw * HCH * 2);
             const uint32_t ah = desc_lo(stA + sh, 16), al = desc_lo(stA + planeA + sh, 16);
             const uint32_t bh = desc_lo(stB, 16), bl = desc_lo(stB + planeB, 16);
+            if (active) {
 #pragma unroll
             for (int k16 = 0; k16 < HCH / 16; ++k16) umma_bf16_elect(tacc, ah + 2 * k16, dhi, bh + 2 * k16, dhi, idesc, first | (uint32_t)k16);   // hi*hi
-            if (p.passes == 3) {
+            }
+            if (active && p.passes == 3) {
 #pragma unroll
               for (int k16 = 0; k16 < HCH / 16; ++k16) umma_bf16_elect(tacc, al + 2 * k16, dhi, bh + 2 * k16, dhi, idesc, 1u);   // lo*hi
 #pragma unroll
@@ -327,8 +337,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       tcgen05_fence_after();
       if (p.tma_store) {
         int n, h0, w0;
-        halo_decode(p, pair * 2 + s, &n, &h0, &w0);
-        if (n < p.N) {   // (padding sub-tile of an odd count: nothing to store)
+        halo_decode(p, halo_sub(p, pair, s), &n, &h0, &w0);
+        if (n < p.N) {   // (padding sub-tile of an odd count / idle half of single mode: nothing to store)
           const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((as * 2 + s) * p.BN);
           const int ngrp = min(p.BN, p.Cd - n0c + 15) / 16;   // groups that hold at least one real channel
           uint32_t acc[2][16];
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         }
       } else {
         int n, h0, w0;
-        halo_decode(p, pair * 2 + s, &n, &h0, &w0);
+        halo_decode(p, halo_sub(p, pair, s), &n, &h0, &w0);
         const int rh = h0 + hl, rw = w0 + wl, rn = n + nl;
         const bool ok = rn < p.N && rh < p.Hr && rw < p.Wr;
         float* dptr = nullptr;
@@ -508,6 +518,7 @@ static int halo_plan(const IGemmParams* gs, int n, int passes, HaloParams* out) 
   p.tiles_n = ceil_div(g0.N, ge.tn);
   p.nsub = (long long)p.tiles_n * p.tiles_w * p.tiles_h;
   p.npairs = (p.nsub + 1) / 2;
+  p.single = 0;
   p.passes = passes;
   p.tma_store = ((g0.Cd & 3) == 0 && !g0.accum_dst) ? 1 : 0;
   // N tile: <= 128 columns on the big grids so that two sub-tiles x two accumulator buffers fit the 512 TMEM columns
@@ -515,7 +526,13 @@ static int halo_plan(const IGemmParams* gs, int n, int passes, HaloParams* out) 
   // columns (single-buffered: few tiles per CTA, and the weight chunk is then shared by 2 x 128 rows x 256 columns)
   {
     const int cpad = ceil_div(g0.Cd, 16) * 16;
-    const int tiles = ceil_div(cpad, ge.halo ? 128 : 256);
+    static int halo_bn_max = 0;
+    if (!halo_bn_max) {
+      const char* e = getenv("MOG_HALO_BN_MAX");     // tuning knob: widest N tile of the halo form (default 128: double-buffered TMEM)
+      halo_bn_max = e ? atoi(e) : 128;
+      if (halo_bn_max < 16 || halo_bn_max > 256) halo_bn_max = 128;
+    }
+    const int tiles = ceil_div(cpad, ge.halo ? halo_bn_max : 256);
     p.BN = ceil_div(ceil_div(cpad, tiles), 16) * 16;
   }
   p.n_ntiles = ceil_div(g0.Cd, p.BN);
@@ -537,6 +554,33 @@ static int halo_plan(const IGemmParams* gs, int n, int passes, HaloParams* out) 
       long long ks = want < maxs ? want : maxs;
       if (ks > 32) ks = 32;
       if (ks > 1) p.ksplit = (int)ks;
+    }
+  }
+  if (ge.halo && p.ksplit == 1 && p.nsub > 1) {
+    // small problems on the halo form (the 17 x 17 / 35 x 35 stages of the image encoder at B = 32: 37 tile pairs x 2 N
+    // tiles for 148 SMs): one sub-tile per work item doubles the CTAs; each finishes in about half the time (tensor work per
+    // CTA halves, the weight chunk is no longer shared)
+    static int knob = -1;
+    if (knob < 0) {
+      const char* e = getenv("MOG_HALO_SINGLE");     // tuning knob: 0 disables
+      knob = e ? atoi(e) : 1;
+    }
+    // (a cost model that also switched mid-size problems -- rounds x 0.55 per single item -- was measured SLOWER: 63.2 vs
+    // 61.6 ms per step; singles pay unshared weight chunks.  Only problems whose pairs leave half of the SMs idle switch.)
+    if (knob && p.npairs * p.n_ntiles * 2 <= kNumSMs + kNumSMs / 4) {
+      p.single = 1;
+      p.npairs = p.nsub;
+      // still under half a wave (e.g. 73 sub-tiles x 1 N tile): split the N tile too (A is re-read per N tile: tiny here)
+      static int knob2 = -1;
+      if (knob2 < 0) {
+        const char* e = getenv("MOG_HALO_SINGLE_NSPLIT");
+        knob2 = e ? atoi(e) : 1;
+      }
+      while (knob2 && p.npairs * p.n_ntiles * 2 <= kNumSMs && p.BN >= 64) {
+        p.BN = ceil_div(p.BN / 2, 16) * 16;
+        p.n_ntiles = ceil_div(g0.Cd, p.BN);
+      }
+      p.nbuf = 4 * p.BN <= 512 ? 2 : 1;
     }
   }
   p.kper = ceil_div(p.niter, p.ksplit);

@@ -291,7 +291,14 @@ def planes_of(x: torch.Tensor, precision: int):
     cached = getattr(x, "_mog_planes", None)
     if cached is not None and cached[1] == precision and cached[2] == x._version and cached[3] == x.data_ptr():
         return cached[0]
-    return split_planes(x, precision)
+    planes = split_planes(x, precision)
+    # remember them on x: a tensor with several consumers (the input of an Inception block feeds 3-4 convolutions; x of a
+    # conv is read again by its weight gradient) is split once, not once per consumer
+    try:
+        _attach_planes(x, planes, precision)
+    except Exception:
+        pass
+    return planes
 
 
 def split_planes(x: torch.Tensor, precision: int):
