@@ -119,6 +119,14 @@ int mog_split_planes(const float* x, long long rows, int C, int precision, void*
 int mog_split_planes_act(const float* dy, const float* y, int act, long long rows, int C, int precision, void* planes,
                          void* stream);
 
+/* Planes of the im2col (patch) matrix of x: [N*Ho*Wo][KP] in the layout of mog_split_planes, k = (kh*KW + kw)*C + c,
+ * KP = KH*KW*C rounded up to 8; taps outside the image and the pad columns are zero.  For the thin ends of the networks
+ * (RGB inputs of the discriminators / the image encoder, model.py:595-599,258; the 3-channel image gradient entering
+ * GET_IMAGE_G, model.py:464-474): on the patch matrix the conv is a 1x1 conv with KP input channels
+ * (mog_conv2d_fwd / mog_conv2d_wgrad with x == NULL and these planes). */
+int mog_patch_planes(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int precision,
+                     void* planes, void* stream);
+
 /* replaces: nn.Conv2d forward incl. a preceding nn.Upsample(2,'nearest') (model.py:41-55,
  * 587-609,626,664-677; GlobalAttention.py:25-28) and nn.Linear (H=W=KH=KW=1; model.py:324,
  * 365,371).  y: [N,Ho,Wo,Cout]; bias may be NULL. */

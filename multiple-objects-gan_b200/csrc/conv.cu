@@ -369,6 +369,15 @@ extern "C" int mog_split_planes_act(const float* dy, const float* y, int act, lo
   return launch_split_planes(dy, rows, C, p8(C), planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream), y, act);
 }
 
+extern "C" int mog_patch_planes(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int precision,
+                               void* planes, void* stream) {
+  MOG_REQUIRE(x && planes && N > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "mog_patch_planes: bad argument");
+  MOG_REQUIRE(precision == MOG_PREC_BF16X3 || precision == MOG_PREC_BF16, "mog_patch_planes: precision must be a tcgen05 mode");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  MOG_REQUIRE(H + 2 * pad >= KH && W + 2 * pad >= KW, "mog_patch_planes: filter larger than the padded image");
+  return launch_patch_planes(x, N, H, W, C, KH, KW, stride, pad, Ho, Wo, planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream));
+}
+
 static int build(const MogConvDesc* d, int which, Problem* probs, int* hires) {
   *hires = 0;
   return which == 0 ? build_fwd(d, probs) : build_dgrad(d, probs, hires);

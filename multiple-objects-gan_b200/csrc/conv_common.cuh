@@ -71,6 +71,8 @@ bool wgrad_halo_eligible(const MogConvDesc& d, int Ho, int Wo, int passes);
 size_t wgrad_halo_workspace_bytes(const MogConvDesc& d, int Ho, int Wo, int passes);
 int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes, const void* dy_planes, float* dw, float* ws,
                       int passes, cudaStream_t st);
+int launch_patch_planes(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                        void* planes, int nplanes, cudaStream_t st);
 int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st,
                         const float* y = nullptr, int act = 0);
 

@@ -734,6 +734,51 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
   if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// fp32 NHWC [N][H][W][C] -> bf16 planes of its im2col matrix [N*Ho*Wo][KP]: k = (kh*KW + kw)*C + c, KP = KH*KW*C rounded
+// up to 8 (pad columns and out-of-image taps zero).  For convolutions with a handful of input channels (RGB images, 3-channel
+// image gradients): with C = 3 every filter tap would be its own K = 16 MMA step and its own TMA box, 3 of 64 channels real;
+// on the patch matrix the same conv is a 1x1 conv with KP channels.  One thread per 8-column chunk of a patch row.
+__global__ void patch_planes_kernel(const float* __restrict__ x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                                    int Ho, int Wo, int K, int KP, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  const int cpr = KP >> 3;
+  const long long rows = (long long)N * Ho * Wo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cpr) return;
+  const long long r = idx / cpr;
+  const int k0 = (int)(idx - r * cpr) * 8;
+  const int wo = (int)(r % Wo);
+  const long long q = r / Wo;
+  const int ho = (int)(q % Ho);
+  const int n = (int)(q / Ho);
+  const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+  const float* xn = x + (size_t)n * H * W * C;
+  float f[8];
+  int tap = k0 / C, c = k0 - tap * C;
+  int kh = tap / KW, kw = tap - kh * KW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = 0.f;
+    if (k0 + j < K) {
+      const int hh = h0 + kh, ww = w0 + kw;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(xn + ((size_t)hh * W + ww) * C + c);
+    }
+    f[j] = v;
+    if (++c == C) { c = 0; if (++kw == KW) { kw = 0; ++kh; } }
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    h[e] = *reinterpret_cast<uint32_t*>(&h2);
+    float2 hf = __bfloat1622float2(h2);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+    l[e] = *reinterpret_cast<uint32_t*>(&l2);
+  }
+  const size_t o = (size_t)r * KP + k0;
+  *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -748,6 +793,17 @@ int launch_split_planes(const float* x, long long rows, int C, int CP, void* pla
   const long long n = rows * (CP / 8);
   tc::split_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, rows, C, CP, hi, lo, y, act);
   return check_launch("split_planes_kernel");
+}
+
+int launch_patch_planes(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                        void* planes, int nplanes, cudaStream_t st) {
+  const int K = KH * KW * C, KP = ceil_div(K, 8) * 8;
+  const long long rows = (long long)N * Ho * Wo;
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(planes);
+  __nv_bfloat16* lo = nplanes == 2 ? hi + (size_t)rows * KP : nullptr;
+  const long long n = rows * (KP / 8);
+  tc::patch_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, N, H, W, C, KH, KW, stride, pad, Ho, Wo, K, KP, hi, lo);
+  return check_launch("patch_planes_kernel");
 }
 
 int tc_bn_for(int Cd) {

@@ -62,7 +62,7 @@ __device__ __forceinline__ PairSmem carve(float* sm, int R, int D, int tp) {
 }
 static size_t pair_smem_bytes(int R, int D, int tp, bool bwd) {
   size_t f = al4((size_t)D * (tp + 1)) + al4((size_t)R * (tp + 1)) + (size_t)tp * lda_of(R) + al4(3 * tp * (DT / 32 + 1)) + 4 * tp;
-  if (bwd) f += (size_t)tp * lda_of(R) + (size_t)D * (tp + 1);   // dA, dvs
+  if (bwd) f += (size_t)tp * lda_of(R);   // dA (dv reuses the word-vector buffer)
   return sizeof(float) * f;
 }
 
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(DT) damsm_fwd_kernel(DamsmArgs a) {
 // backward w.r.t. ctx: one CTA per (image b, caption i); its d ctx[b] contribution goes to slice i of the workspace
 // (a.dctx = workspace [NI][B][R][D])
 template <int CPT, int NT>
-__global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
+__global__ void __launch_bounds__(DT, CPT == 1 && NT <= 24 ? 2 : 1) damsm_bwd_kernel(DamsmArgs a) {
   extern __shared__ float sm[];
   const PairSmem s = carve(sm, a.R, a.D, NT);
   float* dA = s.cosv + 4 * NT;   // [NT][R+1]: d a2 -> d(gamma1*a1) -> reused
@@ -284,19 +284,19 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
         dv[k][t] = (t < n && c < a.D) ? dcos * (s.w[c * ldw + t] * inv_wv - c_over_v2 * v[k][t]) : 0.f;
       }
     }
-    // stash dv in the (now free) w-shaped scratch?  w is still needed -> reuse S? S (a1) still needed.
-    // => keep dv in registers and compute d a2[t][r] = sum_c dv_t[c] ctx[r][c] with a block reduction per region chunk:
-    // write dv to global scratch-free path: use dA as [t][r] accumulators via warp-per-region dot products needs dv by
-    // channel across lanes, so stage dv through shared memory in slices of 32 words x D channels: reuse s.red? too small.
-    // Use the w buffer layout for dv (D x ldw) in a dedicated region appended after dA.
-    float* dvs = dA + (size_t)NT * ldA;   // [D][NT+1]
+    // dv goes to shared memory for the d a2 dot products below (lanes over channels).  It takes the place of the word vectors:
+    // a thread reads and writes only its own channel rows here, and from now on nobody reads another row of w -- the
+    // final phase needs just the thread's own row, kept in registers (wr).  Without a separate dv buffer the pair state
+    // is 111 KB: two CTAs per SM.
+    float wr[CPT][NT];
+    float* dvs = s.w;   // [D][NT+1]
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int c = tid + k * DT;
-      if (c < a.D) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t)     // (static indices: dv stays in registers)
-          if (t < n) dvs[c * ldw + t] = dv[k][t];
+      for (int t = 0; t < NT; ++t) {     // (static indices: registers)
+        wr[k][t] = (t < n && c < a.D) ? s.w[c * ldw + t] : 0.f;
+        if (t < n && c < a.D) dvs[c * ldw + t] = dv[k][t];
       }
     }
     __syncthreads();
@@ -347,14 +347,14 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
     }
     __syncthreads();
     // d ctx[r][c] = sum_t dv_t[c] a2[t][r] + dS[r][t] w[c][t]: four regions per step (128-bit loads of a2 / dS), the
-    // thread's word-vector row w[c][:] in registers
+    // thread's word-vector row w[c][:] in registers, its dv row read back from shared memory
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int c = tid + k * DT;
       if (c < a.D) {
-        float wr[NT];
+        float dvr[NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) wr[t] = t < n ? s.w[c * ldw + t] : 0.f;
+        for (int t = 0; t < NT; ++t) dvr[t] = t < n ? dvs[c * ldw + t] : 0.f;
         for (int r = 0; r < a.R; r += 4) {
           float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
@@ -362,10 +362,10 @@ __global__ void __launch_bounds__(DT) damsm_bwd_kernel(DamsmArgs a) {
             if (t < n) {
               const float4 q = *reinterpret_cast<const float4*>(s.A2 + t * ldA + r);
               const float4 e = *reinterpret_cast<const float4*>(dA + t * ldA + r);
-              g0 = fmaf(dv[k][t], q.x, fmaf(e.x, wr[t], g0));
-              g1 = fmaf(dv[k][t], q.y, fmaf(e.y, wr[t], g1));
-              g2 = fmaf(dv[k][t], q.z, fmaf(e.z, wr[t], g2));
-              g3 = fmaf(dv[k][t], q.w, fmaf(e.w, wr[t], g3));
+              g0 = fmaf(dvr[t], q.x, fmaf(e.x, wr[k][t], g0));
+              g1 = fmaf(dvr[t], q.y, fmaf(e.y, wr[k][t], g1));
+              g2 = fmaf(dvr[t], q.z, fmaf(e.z, wr[k][t], g2));
+              g3 = fmaf(dvr[t], q.w, fmaf(e.w, wr[k][t], g3));
             }
           dctx[(size_t)r * a.D + c] = g0;
           if (r + 1 < a.R) dctx[(size_t)(r + 1) * a.D + c] = g1;

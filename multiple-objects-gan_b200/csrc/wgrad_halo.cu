@@ -280,41 +280,62 @@ __global__ void wgrad_halo_reduce_split_kernel(const WHReduceArgs a) {
 }
 
 
-// One block per (co, 64-channel chunk of ci): the KHW x 64 sums are formed with reads coalesced along ci (fixed summation
-// order: deterministic; 4 independent partial sums per thread in flight), staged in shared memory and written as ONE contiguous
-// 64 * KHW float run of the OIHW tensor.  (The first version wrote dw[(co*Cin + ci)*KHW + k] from a thread per (k, co, ci):
-// a 4-byte store every KHW floats, 8x write amplification -- 895 us for the 1536 -> 3072 4x4 layer, 0.67 TB/s.)
+// One block per (WR_CO output channels, 64-channel chunk of ci): the KHW x 64 sums of each co are formed with reads coalesced
+// along ci (partials added in ascending order: deterministic), staged in shared memory and written as ONE contiguous
+// 64 * KHW float run of the OIHW tensor per co.  A thread owns up to 4 taps x WR_CO channels and issues their loads together:
+// 8 independent 4-byte loads in flight per thread.  (History: a thread per (k, co, ci) writing dw[(co*Cin + ci)*KHW + k]
+// -- a 4-byte store every KHW floats, 8x write amplification -- took 895 us for the 1536 -> 3072 4x4 layer, 0.67 TB/s; one
+// (co, chunk) per block with ONE load in flight per thread: 362 us, 1.5 TB/s -- latency bound, ncu r2j.)
 constexpr int WR_CI = 64;
-__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WHReduceArgs a) {
-  __shared__ float tile[16][WR_CI + 1];
+constexpr int WR_CO = 2;
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WHReduceArgs a, const int maxtotal) {
+  __shared__ float tile[WR_CO][16][WR_CI + 1];
   const size_t per_tap = (size_t)a.Cin * a.Cout;
   const size_t per_split = (size_t)a.nent * per_tap;
-  const int co = blockIdx.y, c0 = blockIdx.x * WR_CI;
-  const int cl = threadIdx.x % WR_CI, kq = threadIdx.x / WR_CI;      // 4 tap lanes
+  const int co0 = blockIdx.y * WR_CO, c0 = blockIdx.x * WR_CI;
+  const int cl = threadIdx.x % WR_CI, kq = threadIdx.x / WR_CI;      // 4 tap lanes (uniform per warp)
   const int ci = c0 + cl;
-  for (int k = kq; k < a.KHW; k += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ci < a.Cin) {
-      const int ns = a.nsrc[k];
-      const int total = a.splits * ns;
-      const size_t idx = (size_t)co * a.Cin + ci;
-      for (int i0 = 0; i0 < total; i0 += 4) {
+  float acc[WR_CO][4];
+  int ns[4], tot[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i0 + j;
-          if (i < total) {
-            const int z = i / ns, u = i - z * ns;
-            acc[j] += __ldg(a.ws + (size_t)z * per_split + (size_t)a.src[k][u] * per_tap + idx);
-          }
+  for (int j = 0; j < 4; ++j) {
+    const int k = kq + 4 * j;
+    ns[j] = k < a.KHW ? a.nsrc[k] : 1;
+    tot[j] = k < a.KHW ? a.splits * ns[j] : 0;
+#pragma unroll
+    for (int c = 0; c < WR_CO; ++c) acc[c][j] = 0.f;
+  }
+  if (ci < a.Cin) {
+    for (int i = 0; i < maxtotal; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (i < tot[j]) {
+          const int k = kq + 4 * j;
+          const int z = i / ns[j], u = i - z * ns[j];
+          const float* src = a.ws + (size_t)z * per_split + (size_t)a.src[k][u] * per_tap + ci;
+#pragma unroll
+          for (int c = 0; c < WR_CO; ++c)
+            if (co0 + c < a.Cout) acc[c][j] += __ldg(src + (size_t)(co0 + c) * a.Cin);
         }
       }
     }
-    tile[k][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = kq + 4 * j;
+    if (k < a.KHW) {
+#pragma unroll
+      for (int c = 0; c < WR_CO; ++c) tile[c][k][cl] = acc[c][j];
+    }
   }
   __syncthreads();
   const int nci = min(WR_CI, a.Cin - c0);
-  float* o = a.dw + ((size_t)co * a.Cin + c0) * a.KHW;
-  for (int e = threadIdx.x; e < nci * a.KHW; e += blockDim.x) o[e] = tile[e % a.KHW][e / a.KHW];
+#pragma unroll
+  for (int c = 0; c < WR_CO; ++c) {
+    if (co0 + c >= a.Cout) break;
+    float* o = a.dw + ((size_t)(co0 + c) * a.Cin + c0) * a.KHW;
+    for (int e = threadIdx.x; e < nci * a.KHW; e += blockDim.x) o[e] = tile[c][e % a.KHW][e / a.KHW];
+  }
 }
 
 }  // namespace tc
@@ -582,7 +603,7 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
   for (int k = 0; k < d.KH * d.KW; ++k) max_src = pl.nsrc[k] > max_src ? pl.nsrc[k] : max_src;
   if (p.splits * max_src <= 8) {
     // few partials, large tensors (the deep discriminator layers): the pass is a layout change -> coalesced OIHW runs
-    wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div(d.Cin, WR_CI), (unsigned)d.Cout), 256, 0, st>>>(ra);
+    wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div(d.Cin, WR_CI), (unsigned)ceil_div(d.Cout, WR_CO)), 256, 0, st>>>(ra, p.splits * max_src);
   } else {
     const size_t total = (size_t)d.Cin * d.Cout;
     wgrad_halo_reduce_split_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 128), (unsigned)(d.KH * d.KW)), 128, 0, st>>>(ra);

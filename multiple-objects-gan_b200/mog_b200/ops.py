@@ -311,6 +311,133 @@ def split_planes(x: torch.Tensor, precision: int):
     return planes
 
 
+def _split_dy(dy, y, act, precision, need_db, needed):
+    """Output gradient of a conv whose epilogue applied ``act``: (fp32 dz or None, planes or None).  In the tcgen05 precisions
+    the activation backward is fused into the plane split (dz never exists in fp32) unless the bias gradient needs it."""
+    dyp = None
+    if act != ACT_NONE and precision != PREC_FP32 and not need_db and needed:
+        Cc = dy.shape[-1]
+        rows = dy.numel() // Cc
+        dyp = torch.empty((_planes_bytes(rows, Cc, precision) + 3) // 4, device=dy.device, dtype=torch.float32)
+        call("mog_split_planes_act", dy.data_ptr(), y.data_ptr(), act, rows, Cc, precision, dyp.data_ptr(), _stream())
+        dy = None
+    elif act != ACT_NONE:
+        dz = torch.empty_like(dy)
+        call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, _stream())
+        dy = dz
+    if dyp is None and precision != PREC_FP32 and needed:
+        dyp = planes_of(dy, precision)     # emitted by the BatchNorm backward that produced dy, else a split pass
+    return dy, dyp
+
+
+# ---- thin ends of the networks: 3-channel inputs / outputs on the tensor cores through the patch (im2col) matrix ----------
+# A conv with C <= 4 input channels spends one K = 16 MMA step and one TMA box per filter tap on 3 real channels (D_NET256's
+# first layer: forward 0.42 ms, weight gradient 0.87 ms at B = 32 for 0.01 TFLOP).  Its patch matrix [pixels][KH*KW*C -> KP]
+# is small (KP = 48 for 4x4x3); on it the conv is a 1x1 conv with KP channels and the weight gradient a plain GEMM.  The same
+# holds for the BACKWARD of a conv with <= 4 output channels (GET_IMAGE_G): its data gradient is a conv of the 3-channel dz,
+# its weight gradient the GEMM x^T . patches(dz).
+def _patch_planes(x, KH, KW, stride, pad, precision):
+    N, H, W, Cc = x.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    KP = (KH * KW * Cc + 7) // 8 * 8
+    planes = torch.empty((_planes_bytes(N * Ho * Wo, KP, precision) + 3) // 4, device=x.device, dtype=torch.float32)
+    call("mog_patch_planes", x.data_ptr(), N, H, W, Cc, KH, KW, stride, pad, precision, planes.data_ptr(), _stream())
+    return planes, Ho, Wo, KP
+
+
+def _pack_matrix(w2, d1):
+    """Packed forward operand of a temporary 1x1 weight [Cout][KP] (not cached: rebuilt from the live parameter every call,
+    so it is never stale -- inside a captured step the rebuild is part of the graph)."""
+    n = _lib.lib().mog_packed_weight_bytes(C.byref(d1), 0)
+    out = torch.empty((n + 3) // 4, device=w2.device, dtype=torch.float32)
+    call("mog_pack_weight", C.byref(d1), 0, w2.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def _padded_matrix(m2, KP):
+    """[R][K] -> contiguous [R][KP], zero pad columns."""
+    if m2.shape[1] == KP:
+        return m2.contiguous()
+    out = torch.zeros(m2.shape[0], KP, device=m2.device, dtype=torch.float32)
+    out[:, :m2.shape[1]] = m2
+    return out
+
+
+def _thin_cin(x, weight, stride, pad, up2x, precision):
+    if precision == PREC_FP32 or up2x or weight.dim() != 4 or x.dim() != 4 or isinstance(pad, (tuple, list)):
+        return False
+    Co, Ci, KH, KW = weight.shape
+    return Ci <= 4 and KH * KW > 1 and KH * KW * Ci <= 64
+
+
+def _thin_cout_bwd(w_shape, stride, pad, up2x, precision, has_bias):
+    if precision == PREC_FP32 or up2x or stride != 1 or has_bias or isinstance(pad, (tuple, list)):
+        return False
+    Co, Ci, KH, KW = w_shape
+    return Co <= 4 and Ci > 4 and KH == KW and KH == 2 * pad + 1 and KH > 1 and KH * KW * Co <= 64
+
+
+class PatchConv2dFn(torch.autograd.Function):
+    """Conv2dFn for <= 4 input channels: forward and weight gradient on the patch matrix (see above); the data gradient is the
+    ordinary one.  replaces nn.Conv2d(3, ndf, 4, 2, 1) (model.py:598) and Inception's Conv2d_1a_3x3 (model.py:258)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act, precision):
+        _chk(x, "conv input")
+        Co, Ci, KH, KW = weight.shape
+        N, H, W, Cx = x.shape
+        if Cx != Ci:
+            raise RuntimeError("conv: input has %d channels, weight expects %d" % (Cx, Ci))
+        xP, Ho, Wo, KP = _patch_planes(x, KH, KW, stride, pad, precision)
+        d1, _, _, dkey1 = _desc((N, Ho, Wo, KP), (Co, KP, 1, 1), 1, 0, False, act, precision)
+        frozen = not weight.requires_grad
+        ent = getattr(weight, "_mog_patch_pack", None) if frozen else None
+        ver = _weight_version(weight)
+        if ent is None or ent[0] != (ver, KP, precision):
+            w2 = _padded_matrix(weight.detach().permute(0, 2, 3, 1).reshape(Co, KH * KW * Ci), KP)
+            ent = ((ver, KP, precision), _pack_matrix(w2, d1))
+            if frozen:
+                weight._mog_patch_pack = ent
+        y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+        ws, nws = _workspace(d1, 0, x.device, dkey1)
+        b = None if bias is None else bias.detach().contiguous()
+        call("mog_conv2d_fwd", C.byref(d1), None, xP.data_ptr(), ent[1].data_ptr(), _ptr(b), y.data_ptr(), _ptr(ws), nws, _stream())
+        ctx.cfg = (stride, pad, act, precision, tuple(x.shape), (Ho, Wo, KP))
+        ctx.has_bias = bias is not None
+        need_w = weight.requires_grad or (bias is not None and bias.requires_grad)
+        ctx.save_for_backward(xP if need_w else None, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xP, weight, y = ctx.saved_tensors
+        stride, pad, act, precision, xshape, (Ho, Wo, KP) = ctx.cfg
+        dy = dy.contiguous()
+        Co, Ci, KH, KW = weight.shape
+        N = xshape[0]
+        st, dev = _stream(), dy.device
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dy, dyp = _split_dy(dy, y, act, precision, need_db, need_dx or need_dw)
+        dx = dw = db = None
+        if need_dx:
+            d, _, _, dkey = _desc(xshape, weight.shape, stride, pad, False, ACT_NONE, precision)
+            dx = torch.empty(xshape, device=dev, dtype=torch.float32)
+            ws, nws = _workspace(d, 1, dev, dkey)
+            call("mog_conv2d_dgrad", C.byref(d), _ptr(dy), _ptr(dyp), _packed(weight, "dgrad", d, dkey).data_ptr(),
+                 dx.data_ptr(), _ptr(ws), nws, st)
+        if need_dw:
+            d1, _, _, dkey1 = _desc((N, Ho, Wo, KP), (Co, KP, 1, 1), 1, 0, False, ACT_NONE, precision)
+            dw1 = torch.empty((Co, KP), device=dev, dtype=torch.float32)
+            if ctx.has_bias:
+                db = torch.empty(Co, device=dev, dtype=torch.float32)
+            ws, nws = _workspace(d1, 2, dev, dkey1)
+            call("mog_conv2d_wgrad", C.byref(d1), None, xP.data_ptr(), _ptr(dy), _ptr(dyp), dw1.data_ptr(), _ptr(db), _ptr(ws), nws, st)
+            dw = dw1[:, :KH * KW * Ci].reshape(Co, KH, KW, Ci).permute(0, 3, 1, 2).contiguous()
+        return dx, dw, db, None, None, None, None
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = act(conv(up2x?(x), w) + b), NHWC.  replaces nn.Conv2d (+ nn.Upsample) of model.py.
     In the tcgen05 precisions the input is split once into bf16 planes (kept for the weight
@@ -348,20 +475,9 @@ class Conv2dFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
-        dyp = None
-        if act != ACT_NONE and precision != PREC_FP32 and not need_db and (need_dx or need_dw):
-            # backward of the epilogue activation fused into the plane split: dz = dy * act'(y) never exists in fp32
-            Cc = dy.shape[-1]
-            rows = dy.numel() // Cc
-            dyp = torch.empty((_planes_bytes(rows, Cc, precision) + 3) // 4, device=dev, dtype=torch.float32)
-            call("mog_split_planes_act", dy.data_ptr(), y.data_ptr(), act, rows, Cc, precision, dyp.data_ptr(), st)
-            dy = None
-        elif act != ACT_NONE:
-            dz = torch.empty_like(dy)
-            call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, st)
-            dy = dz
-        if dyp is None and precision != PREC_FP32 and (need_dx or need_dw):
-            dyp = planes_of(dy, precision)     # emitted by the BatchNorm backward that produced dy, else a split pass
+        if _thin_cout_bwd(w4.shape, stride, pad, up2x, precision, ctx.has_bias) and (need_dx or need_dw):
+            return Conv2dFn._backward_thin_cout(dy, y, xp, weight, act, precision, xshape, need_dx, need_dw)
+        dy, dyp = _split_dy(dy, y, act, precision, need_db, need_dx or need_dw)
         dx = dw = db = None
         if need_dx:
             dx = torch.empty(xshape, device=dev, dtype=torch.float32)
@@ -377,6 +493,36 @@ class Conv2dFn(torch.autograd.Function):
                  _ptr(ws), nws, st)
             dw = dw.reshape(weight.shape)
         return dx, dw, db, None, None, None, None, None
+
+    @staticmethod
+    def _backward_thin_cout(dy, y, xp, weight, act, precision, xshape, need_dx, need_dw):
+        """Backward of a 'same' conv with <= 4 output channels (GET_IMAGE_G, model.py:464-474) through the patch matrix of
+        dz = dy * act'(y), dzP[p][(a, b, co)] = dz[p + (a - pad, b - pad)][co]:
+          dx[p][ci]          = sum_k dzP[p][k] * w[co][ci][KH-1-a][KW-1-b]        (1x1 conv, KP -> Cin)
+          dW[co][ci][kh][kw] = sum_p x[p][ci] * dzP[p][(KH-1-kh, KW-1-kw, co)]    (1x1 weight gradient: dzP input, x 'gradient')"""
+        Co, Ci, KH, KW = weight.shape
+        N, H, W, _ = xshape
+        st, dev = _stream(), dy.device
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("mog_act_bwd", dy.data_ptr(), y.data_ptr(), dz.data_ptr(), dy.numel(), act, st)
+        else:
+            dz = dy
+        dzP, _, _, KP = _patch_planes(dz, KH, KW, 1, (KH - 1) // 2, precision)
+        K = KH * KW * Co
+        d1, _, _, dkey1 = _desc((N, H, W, KP), (Ci, KP, 1, 1), 1, 0, False, ACT_NONE, precision)
+        dx = dw = None
+        if need_dx:
+            w2 = _padded_matrix(weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, K), KP)
+            dx = torch.empty(xshape, device=dev, dtype=torch.float32)
+            ws, nws = _workspace(d1, 0, dev, dkey1)
+            call("mog_conv2d_fwd", C.byref(d1), None, dzP.data_ptr(), _pack_matrix(w2, d1).data_ptr(), None, dx.data_ptr(), _ptr(ws), nws, st)
+        if need_dw:
+            g = torch.empty((Ci, KP), device=dev, dtype=torch.float32)
+            ws, nws = _workspace(d1, 2, dev, dkey1)
+            call("mog_conv2d_wgrad", C.byref(d1), None, dzP.data_ptr(), None, xp.data_ptr(), g.data_ptr(), None, _ptr(ws), nws, st)
+            dw = g[:, :K].reshape(Ci, KH, KW, Co).flip(1, 2).permute(3, 0, 1, 2).contiguous()
+        return dx, dw, None, None, None, None, None, None
 
 
 def _tile_eff(H, W):
@@ -412,6 +558,8 @@ def _retile(x, weight, stride, pad, up2x, precision):
 def conv2d(x, weight, bias=None, stride=1, pad=0, up2x=False, act=ACT_NONE, precision=None):
     if precision is None:
         precision = _default_precision
+    if _thin_cin(x, weight, stride, pad, up2x, precision):
+        return PatchConv2dFn.apply(x, weight, bias, stride, pad, act, precision)
     shape = _retile(x, weight, stride, pad, up2x, precision)
     if shape is not None:
         N, H, W, _ = x.shape

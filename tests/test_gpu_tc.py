@@ -62,6 +62,12 @@ TC_CASES = [
     (6, 8, 8, 192, 320, 1, 1, 0, False, False, 1),    # 1x1 on 8x8 (Inception 8x8 stage), ReLU, two N tiles of 160
     (5, 7, 7, 64, 64, 3, 1, 1, False, False, 0),      # 7x7 grid: sub-tile rows / columns beyond the image clip
     (40, 4, 4, 64, 64, 4, 2, 1, False, False, 0),     # 4 -> 2 grid
+    # thin ends through the patch matrix (mog_patch_planes): <= 4 input channels forward / weight gradient, <= 4 output
+    # channels backward (the Cin=3 / Cout=3 cases above take these paths too)
+    (2, 21, 21, 3, 8, 3, 2, 0, False, True, 1),       # Inception Conv2d_1a_3x3: 3x3/s2 no pad, odd size, bias + ReLU; K = 27 -> 32
+    (3, 16, 16, 1, 16, 4, 2, 1, False, False, 2),     # 1-channel images (Multi-MNIST discriminator): K = 16
+    (2, 16, 24, 4, 24, 3, 1, 1, False, False, 0),     # Cin = 4: K = 36 -> 40
+    (2, 16, 16, 24, 2, 3, 1, 1, False, False, 4),     # Cout = 2 + tanh: backward on patches of dz, K = 18 -> 24
 ]
 
 
