@@ -382,7 +382,11 @@ struct V4Geom { int Cv, GB, R, nxb, rpb, nyb; };
 // Same-address fp64 atomics serialise in L2 at ~55 ns each (measured: 6554 blocks -> 320 us for a pass that streams in
 // 125 us), so those kernels run a fixed, small number of blocks (about two per SM over all column groups and segments),
 // each looping over its row chunks with the sums kept in registers.
-static V4Geom v4_geom(int width, int M, int S = 1, bool reduce = false) {
+// which (reducing kernels only): 0 = forward statistics, 1 = backward reduce.  The grid of a reducing kernel is capped at the
+// number of blocks that are RESIDENT at once (each block strides over the rows and leaves one partial): bn_stats_v4_kernel
+// holds 3 blocks per SM (80 registers), and a grid of 4 per SM ran as one full wave plus a one-third wave -- 4.3 TB/s instead
+// of the ~6 TB/s of the two-wave-exact backward reduce (ncu r2j).
+static V4Geom v4_geom(int width, int M, int S = 1, bool reduce = false, int which = 1) {
   V4Geom g;
   g.Cv = width / 4;
   g.nxb = ceil_div(g.Cv, 32);
@@ -393,13 +397,16 @@ static V4Geom v4_geom(int width, int M, int S = 1, bool reduce = false) {
   while (ceil_div(M, g.rpb) > 65535) g.rpb *= 2;
   g.nyb = ceil_div(M, g.rpb);
   if (reduce) {
-    static int per_sm = -1;
-    if (per_sm < 0) {
-      const char* e = getenv("MOG_BN_BLOCKS_PER_SM");   // tuning knob: resident reducing blocks per SM (each leaves one partial)
-      per_sm = e ? atoi(e) : 4;
-      if (per_sm < 1) per_sm = 1;
+    static int per_sm[2] = {-1, -1};
+    if (per_sm[0] < 0) {
+      const char* e0 = getenv("MOG_BN_STATS_BLOCKS_PER_SM");   // tuning knobs: reducing blocks per SM
+      const char* e1 = getenv("MOG_BN_BLOCKS_PER_SM");
+      per_sm[0] = e0 ? atoi(e0) : 3;
+      per_sm[1] = e1 ? atoi(e1) : 4;
+      if (per_sm[0] < 1) per_sm[0] = 1;
+      if (per_sm[1] < 1) per_sm[1] = 1;
     }
-    int cap = (per_sm * kNumSMs) / (g.nxb * (S > 0 ? S : 1));
+    int cap = (per_sm[which ? 1 : 0] * kNumSMs) / (g.nxb * (S > 0 ? S : 1));
     if (cap < 1) cap = 1;
     if (g.nyb > cap) g.nyb = cap;
   }
@@ -702,7 +709,7 @@ using namespace mog;
 // number of partial slots P of the reducing kernels for a problem (which = 0: forward statistics, 1: backward sums)
 static int bn_parts_of(int S, int M, int C, int act, int which) {
   const int width = (which == 1 && act == MOG_ACT_GLU) ? C / 2 : C;
-  if ((C & 3) == 0 && (width & 3) == 0 && S <= 65535) return v4_geom(width, M, S, true).nyb;
+  if ((C & 3) == 0 && (width & 3) == 0 && S <= 65535) return v4_geom(width, M, S, true, which).nyb;
   const int chunks = ceil_div(M, rows_per_block(M));
   return chunks < 64 ? chunks : 64;
 }
@@ -718,7 +725,7 @@ extern "C" int mog_bn_stats(const float* x, int S, int M, int C, double* part, i
   cudaStream_t st = as_stream(stream);
   MOG_REQUIRE(S <= 65535, "mog_bn_stats: too many segments");
   if ((C & 3) == 0) {
-    const V4Geom g = v4_geom(C, M, S, true);
+    const V4Geom g = v4_geom(C, M, S, true, 0);
     bn_stats_v4_kernel<<<dim3(g.nxb, g.nyb, S), g.GB * g.R, 0, st>>>(x, M, C, g, part, S);
     return check_launch("bn_stats_v4_kernel");
   }

@@ -619,7 +619,7 @@ __device__ __forceinline__ void pack_multi_store(const MogPackEntry& a, int bx, 
   }
 }
 
-__global__ void __launch_bounds__(256) pack_multi_kernel(const MogPackEntry* __restrict__ T, const MogPackGroup* __restrict__ G, int ng) {
+__global__ void __launch_bounds__(256, 4) pack_multi_kernel(const MogPackEntry* __restrict__ T, const MogPackGroup* __restrict__ G, int ng) {
   __shared__ float tile[PK_N * PM_ROW];
   __shared__ MogPackEntry ent;
   int lo = 0, hi = ng - 1;

@@ -43,7 +43,10 @@ __device__ __forceinline__ void stv(float* p, const Vec<V>& r) {
   else *p = r.v[0];
 }
 
-template <int V>
+// K: compile-time window edge (3 = every pooling layer of Inception-v3 but the final 8x8 average; 0 = run-time a.k).  With K known the
+// K*K taps are loaded up front -- nine independent 128-bit loads in flight per thread; the run-time loop issued one load per
+// iteration and waited for it (ncu r2j: 2.6 TB/s on the 147^2 x 64 max pool, a pure latency bound).
+template <int V, int K>
 __global__ void pool_fwd_kernel(PoolArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // element index / V
   if (i >= a.total) return;
@@ -59,19 +62,44 @@ __global__ void pool_fwd_kernel(PoolArgs a) {
   int best[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) { acc.v[j] = a.mode == 0 ? -FLT_MAX : 0.f; best[j] = -1; }
-  for (int kh = 0; kh < a.k; ++kh) {
-    const int h = ho * a.s - a.p + kh;
-    if (h < 0 || h >= a.H) continue;
-    for (int kw = 0; kw < a.k; ++kw) {
-      const int w = wo * a.s - a.p + kw;
-      if (w < 0 || w >= a.W) continue;
-      const Vec<V> v = ldv<V>(xn + ((size_t)h * a.W + w) * a.C);
+  if (K > 0) {
+    constexpr int KK = K > 0 ? K * K : 1;
+    Vec<V> v[KK];
+    bool ok[KK];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      const int h = ho * a.s - a.p + t / (K > 0 ? K : 1), w = wo * a.s - a.p + t % (K > 0 ? K : 1);
+      ok[t] = h >= 0 && h < a.H && w >= 0 && w < a.W;
+      if (ok[t]) v[t] = ldv<V>(xn + ((size_t)h * a.W + w) * a.C);
+      else v[t] = Vec<V>{};
+    }
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      if (!ok[t]) continue;
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         if (a.mode == 0) {
-          if (v.v[j] > acc.v[j] || v.v[j] != v.v[j] || best[j] < 0) { acc.v[j] = v.v[j]; best[j] = kh * a.k + kw; }   // first maximum wins (torch)
+          if (v[t].v[j] > acc.v[j] || v[t].v[j] != v[t].v[j] || best[j] < 0) { acc.v[j] = v[t].v[j]; best[j] = t; }   // first maximum wins (torch)
         } else {
-          acc.v[j] += v.v[j];
+          acc.v[j] += v[t].v[j];
+        }
+      }
+    }
+  } else {
+    for (int kh = 0; kh < a.k; ++kh) {
+      const int h = ho * a.s - a.p + kh;
+      if (h < 0 || h >= a.H) continue;
+      for (int kw = 0; kw < a.k; ++kw) {
+        const int w = wo * a.s - a.p + kw;
+        if (w < 0 || w >= a.W) continue;
+        const Vec<V> v = ldv<V>(xn + ((size_t)h * a.W + w) * a.C);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if (a.mode == 0) {
+            if (v.v[j] > acc.v[j] || v.v[j] != v.v[j] || best[j] < 0) { acc.v[j] = v.v[j]; best[j] = kh * a.k + kw; }   // first maximum wins (torch)
+          } else {
+            acc.v[j] += v.v[j];
+          }
         }
       }
     }
@@ -93,7 +121,9 @@ __global__ void pool_fwd_kernel(PoolArgs a) {
 
 __device__ __forceinline__ int fdiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
-template <int V>
+// WM: compile-time bound of the covering windows per axis (3 for k = 3; 0 = run-time loops).  As in the forward kernel the
+// window gradients (and recorded arg-max positions) are loaded up front, WM*WM independent loads in flight.
+template <int V, int WM>
 __global__ void pool_bwd_kernel(PoolArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) return;
@@ -114,46 +144,77 @@ __global__ void pool_bwd_kernel(PoolArgs a) {
   Vec<V> acc;
 #pragma unroll
   for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
-  for (int ho = ho_lo; ho <= ho_hi; ++ho)
-    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-      const Vec<V> g = ldv<V>(dyn + ((size_t)ho * a.Wo + wo) * a.C);
-      if (a.mode == 1) {
+  if (WM > 0 && (a.mode == 1 || a.idx)) {
+    constexpr int WW = WM > 0 ? WM * WM : 1;
+    Vec<V> g[WW];
+    unsigned int pos[WW];
+    bool ok[WW];
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc.v[j] += g.v[j];
-      } else if (a.idx) {
-        // the forward recorded each window's arg-max position
-        const unsigned char* ip = a.idx + ((size_t)n * a.Ho * a.Wo + (size_t)ho * a.Wo + wo) * a.C + c;
-        unsigned char pos[V];
-        if (V == 4) {
-          const uchar4 t = *reinterpret_cast<const uchar4*>(ip);
-          pos[0] = t.x; pos[1 % V] = t.y; pos[2 % V] = t.z; pos[3 % V] = t.w;
-        } else {
-          pos[0] = *ip;
+    for (int t = 0; t < WW; ++t) {
+      const int ho = ho_lo + t / (WM > 0 ? WM : 1), wo = wo_lo + t % (WM > 0 ? WM : 1);
+      ok[t] = ho <= ho_hi && wo <= wo_hi;
+      pos[t] = 0u;
+      if (ok[t]) {
+        g[t] = ldv<V>(dyn + ((size_t)ho * a.Wo + wo) * a.C);
+        if (a.mode == 0) {
+          const unsigned char* ip = a.idx + ((size_t)n * a.Ho * a.Wo + (size_t)ho * a.Wo + wo) * a.C + c;
+          pos[t] = V == 4 ? *reinterpret_cast<const unsigned int*>(ip) : (unsigned int)*ip;
         }
-        const int me = (h - (ho * a.s - a.p)) * a.k + (w - (wo * a.s - a.p));   // this pixel's position inside the window
-#pragma unroll
-        for (int j = 0; j < V; ++j)
-          if ((int)pos[j] == me) acc.v[j] += g.v[j];
       } else {
-        // arg-max of this window recomputed from x, first maximum wins (torch: `val > maxval || isnan(val)`)
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          float best = -FLT_MAX;
-          int bh = -1, bw = -1;
-          for (int kh = 0; kh < a.k; ++kh) {
-            const int hh = ho * a.s - a.p + kh;
-            if (hh < 0 || hh >= a.H) continue;
-            for (int kw = 0; kw < a.k; ++kw) {
-              const int ww = wo * a.s - a.p + kw;
-              if (ww < 0 || ww >= a.W) continue;
-              const float v = __ldg(xn + ((size_t)hh * a.W + ww) * a.C + j);
-              if (v > best || v != v || bh < 0) { best = v; bh = hh; bw = ww; }
-            }
-          }
-          if (bh == h && bw == w) acc.v[j] += g.v[j];
-        }
+        g[t] = Vec<V>{};
       }
     }
+#pragma unroll
+    for (int t = 0; t < WW; ++t) {
+      if (!ok[t]) continue;
+      const int ho = ho_lo + t / (WM > 0 ? WM : 1), wo = wo_lo + t % (WM > 0 ? WM : 1);
+      const int me = (h - (ho * a.s - a.p)) * a.k + (w - (wo * a.s - a.p));   // this pixel's position inside the window
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (a.mode == 1 || (int)((pos[t] >> (8 * j)) & 0xffu) == me) acc.v[j] += g[t].v[j];
+    }
+  } else {
+    for (int ho = ho_lo; ho <= ho_hi; ++ho)
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const Vec<V> g = ldv<V>(dyn + ((size_t)ho * a.Wo + wo) * a.C);
+        if (a.mode == 1) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc.v[j] += g.v[j];
+        } else if (a.idx) {
+          // the forward recorded each window's arg-max position
+          const unsigned char* ip = a.idx + ((size_t)n * a.Ho * a.Wo + (size_t)ho * a.Wo + wo) * a.C + c;
+          unsigned char pos[V];
+          if (V == 4) {
+            const uchar4 t = *reinterpret_cast<const uchar4*>(ip);
+            pos[0] = t.x; pos[1 % V] = t.y; pos[2 % V] = t.z; pos[3 % V] = t.w;
+          } else {
+            pos[0] = *ip;
+          }
+          const int me = (h - (ho * a.s - a.p)) * a.k + (w - (wo * a.s - a.p));   // this pixel's position inside the window
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if ((int)pos[j] == me) acc.v[j] += g.v[j];
+        } else {
+          // arg-max of this window recomputed from x, first maximum wins (torch: `val > maxval || isnan(val)`)
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float best = -FLT_MAX;
+            int bh = -1, bw = -1;
+            for (int kh = 0; kh < a.k; ++kh) {
+              const int hh = ho * a.s - a.p + kh;
+              if (hh < 0 || hh >= a.H) continue;
+              for (int kw = 0; kw < a.k; ++kw) {
+                const int ww = wo * a.s - a.p + kw;
+                if (ww < 0 || ww >= a.W) continue;
+                const float v = __ldg(xn + ((size_t)hh * a.W + ww) * a.C + j);
+                if (v > best || v != v || bh < 0) { best = v; bh = hh; bw = ww; }
+              }
+            }
+            if (bh == h && bw == w) acc.v[j] += g.v[j];
+          }
+        }
+      }
+  }
   if (a.mode == 1) {
 #pragma unroll
     for (int j = 0; j < V; ++j) acc.v[j] = acc.v[j] / (float)(a.k * a.k);
@@ -265,8 +326,10 @@ extern "C" int mog_pool2d_fwd(const float* x, float* y, unsigned char* argmax, i
   if (rc) return rc;
   const int V = (C & 3) == 0 ? 4 : 1;
   PoolArgs a{x, nullptr, y, argmax, N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * Ho * Wo * C / V};
-  if (V == 4) pool_fwd_kernel<4><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
-  else pool_fwd_kernel<1><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  const unsigned grid = (unsigned)ceil_div_ll(a.total, 256);
+  if (V == 4 && k == 3) pool_fwd_kernel<4, 3><<<grid, 256, 0, as_stream(stream)>>>(a);
+  else if (V == 4) pool_fwd_kernel<4, 0><<<grid, 256, 0, as_stream(stream)>>>(a);
+  else pool_fwd_kernel<1, 0><<<grid, 256, 0, as_stream(stream)>>>(a);
   return check_launch("pool_fwd_kernel");
 }
 
@@ -279,8 +342,10 @@ extern "C" int mog_pool2d_bwd(const float* x, const unsigned char* argmax, const
   if (rc) return rc;
   const int V = (C & 3) == 0 ? 4 : 1;
   PoolArgs a{x, dy, dx, const_cast<unsigned char*>(argmax), N, H, W, C, Ho, Wo, k, stride, pad, mode, (long long)N * H * W * C / V};
-  if (V == 4) pool_bwd_kernel<4><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
-  else pool_bwd_kernel<1><<<(unsigned)ceil_div_ll(a.total, 256), 256, 0, as_stream(stream)>>>(a);
+  const unsigned grid = (unsigned)ceil_div_ll(a.total, 256);
+  if (V == 4 && k == 3) pool_bwd_kernel<4, 3><<<grid, 256, 0, as_stream(stream)>>>(a);   // <= 3 covering windows per axis (stride >= 1)
+  else if (V == 4) pool_bwd_kernel<4, 0><<<grid, 256, 0, as_stream(stream)>>>(a);
+  else pool_bwd_kernel<1, 0><<<grid, 256, 0, as_stream(stream)>>>(a);
   return check_launch("pool_bwd_kernel");
 }
 

@@ -280,6 +280,43 @@ __global__ void wgrad_halo_reduce_split_kernel(const WHReduceArgs a) {
 }
 
 
+// Many splits, FEW outputs (the patch-matrix GEMMs of the thin layers: 32 x 48 outputs, 296 partials each; 1x1 layers): the
+// thread-per-output kernel above would run a dozen blocks, each thread walking ~300 partials 8 at a time (~110 us of pure
+// latency, measured).  Here 8 split lanes share an output: lane l sums partials l, l + 8, ... (ascending), the 8 lane sums are
+// combined in lane order through shared memory -- a fixed order, deterministic.  Block = 32 outputs x 8 lanes.
+constexpr int WRS_LANES = 8;
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_lanes_kernel(const WHReduceArgs a) {
+  __shared__ float part[WRS_LANES][33];
+  const size_t per_tap = (size_t)a.Cin * a.Cout;
+  const int ol = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const size_t idx = (size_t)blockIdx.x * 32 + ol;   // co * Cin + ci
+  const int k = blockIdx.y;
+  const size_t per_split = (size_t)a.nent * per_tap;
+  const int ns = a.nsrc[k];
+  const int total = a.splits * ns;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (idx < per_tap) {
+    for (int i0 = sl; i0 < total; i0 += 4 * WRS_LANES) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * WRS_LANES;
+        if (i < total) {
+          const int z = i / ns, u = i - z * ns;
+          acc[j] += __ldg(a.ws + (size_t)z * per_split + (size_t)a.src[k][u] * per_tap + idx);
+        }
+      }
+    }
+  }
+  part[sl][ol] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (sl == 0 && idx < per_tap) {
+    float r = part[0][ol];
+#pragma unroll
+    for (int l = 1; l < WRS_LANES; ++l) r += part[l][ol];
+    a.dw[idx * a.KHW + k] = r;
+  }
+}
+
 // One block per (WR_CO output channels, 64-channel chunk of ci): the KHW x 64 sums of each co are formed with reads coalesced
 // along ci (partials added in ascending order: deterministic), staged in shared memory and written as ONE contiguous
 // 64 * KHW float run of the OIHW tensor per co.  A thread owns up to 4 taps x WR_CO channels and issues their loads together:
@@ -606,7 +643,10 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
     wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div(d.Cin, WR_CI), (unsigned)ceil_div(d.Cout, WR_CO)), 256, 0, st>>>(ra, p.splits * max_src);
   } else {
     const size_t total = (size_t)d.Cin * d.Cout;
-    wgrad_halo_reduce_split_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 128), (unsigned)(d.KH * d.KW)), 128, 0, st>>>(ra);
+    if (total * (size_t)(d.KH * d.KW) < (size_t)64 * 1024)
+      wgrad_halo_reduce_lanes_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 32), (unsigned)(d.KH * d.KW)), 256, 0, st>>>(ra);
+    else
+      wgrad_halo_reduce_split_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 128), (unsigned)(d.KH * d.KW)), 128, 0, st>>>(ra);
   }
   return check_launch("wgrad_halo_reduce_kernel");
 }
