@@ -40,7 +40,7 @@ struct DamsmArgs {
 
 // shared state of one (b, i) pair
 struct PairSmem {
-  float* w;    // [D][TMAXW+1]
+  float* w;    // [D][NT+2]   (pitch 2 x odd: see pair_scores)
   float* S;    // [R][TMAXW+1]  scores -> a1
   float* A2;   // [TMAXW][R+1]
   float* red;  // [3][TMAXW][DT/32 + 1]
@@ -54,16 +54,73 @@ __host__ __device__ __forceinline__ size_t al4(size_t n) { return (n + 3) & ~siz
 __device__ __forceinline__ PairSmem carve(float* sm, int R, int D, int tp) {
   PairSmem p;
   p.w = sm;
-  p.S = p.w + al4((size_t)D * (tp + 1));
+  p.S = p.w + al4((size_t)D * (tp + 2));
   p.A2 = p.S + al4((size_t)R * (tp + 1));
   p.red = p.A2 + (size_t)tp * lda_of(R);
   p.cosv = p.red + al4(3 * tp * (DT / 32 + 1));
   return p;
 }
 static size_t pair_smem_bytes(int R, int D, int tp, bool bwd) {
-  size_t f = al4((size_t)D * (tp + 1)) + al4((size_t)R * (tp + 1)) + (size_t)tp * lda_of(R) + al4(3 * tp * (DT / 32 + 1)) + 4 * tp;
+  size_t f = al4((size_t)D * (tp + 2)) + al4((size_t)R * (tp + 1)) + (size_t)tp * lda_of(R) + al4(3 * tp * (DT / 32 + 1)) + 4 * tp;
   if (bwd) f += (size_t)tp * lda_of(R);   // dA (dv reuses the word-vector buffer)
   return sizeof(float) * f;
+}
+
+// out(r, t) = sum_c ctx[r][c] * m[c][t]  for all regions r and words t < n; m = word vectors (scores) or dv (d a2) in shared
+// memory, pitch NT + 2.  One warp per FOUR regions; the two half-warps take the even / the odd words and 16 channels each per
+// step, so a word-vector element read from shared memory feeds four FMAs (the loop was bound by shared-memory loads at one
+// load per two FMAs: 24 wavefronts against 12 issue cycles per step).  Pitch NT + 2 = 2 x odd: the 16 channels of a half land
+// in 16 distinct even banks, the other half (word + 1) in the odd ones -- conflict free.  The 16-lane sums are formed by
+// shuffles (4 steps instead of 5).  transposed: store to out[t * ld + r] (d a2) instead of out[r * ld + t] (scores).
+template <int NT, bool TRANSPOSED>
+__device__ __forceinline__ void pair_scores(const float* __restrict__ ctx, const float* m, int R, int D, int n, float* out, int ld) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int half = lane >> 4, hl = lane & 15;
+  constexpr int NU = NT / 2;
+  const int ldw = NT + 2;
+  for (int r = 4 * wrp; r < R; r += 4 * (DT / 32)) {
+    float acc[4][NU];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int u = 0; u < NU; ++u) acc[q][u] = 0.f;
+    const float* c0 = ctx + (size_t)r * D;
+    const bool h1 = r + 1 < R, h2 = r + 2 < R, h3 = r + 3 < R;
+#pragma unroll 2
+    for (int c = hl; c < D; c += 16) {
+      float x[4];
+      x[0] = __ldg(c0 + c);
+      x[1] = h1 ? __ldg(c0 + D + c) : 0.f;
+      x[2] = h2 ? __ldg(c0 + 2 * D + c) : 0.f;
+      x[3] = h3 ? __ldg(c0 + 3 * D + c) : 0.f;
+      const float* mr = m + c * ldw + half;
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+        if (2 * u < n) {        // (word 2u + half; a word n <= t < NT of the odd half multiplies stale data that is never stored)
+          const float wv = mr[2 * u];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q][u] = fmaf(x[q], wv, acc[q][u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      if (2 * u < n) {
+        const int t = 2 * u + half;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float z = acc[q][u];
+          z += __shfl_xor_sync(0xffffffffu, z, 8);
+          z += __shfl_xor_sync(0xffffffffu, z, 4);
+          z += __shfl_xor_sync(0xffffffffu, z, 2);
+          z += __shfl_xor_sync(0xffffffffu, z, 1);
+          if (hl == 0 && t < n && r + q < R) {
+            if (TRANSPOSED) out[t * ld + r + q] = z;
+            else out[(r + q) * ld + t] = z;
+          }
+        }
+      }
+    }
+  }
 }
 
 // forward of one pair up to v (kept in registers: v[k][t] for channel c = tid + k*DT) and cos/|w|/|v|/wv in smem
@@ -74,66 +131,36 @@ template <int CPT, int NT>
 __device__ void pair_forward(const DamsmArgs& a, const PairSmem& s, const float* ctx, const float* wi, int n,
                              float (&v)[CPT][NT]) {
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int ldw = NT + 1, ldA = lda_of(a.R);
+  const int ldw = NT + 2, ldS = NT + 1, ldA = lda_of(a.R);
   for (int i = tid; i < a.D * n; i += DT) {
     int c = i / n, t = i - c * n;
     s.w[c * ldw + t] = __ldg(wi + (size_t)c * a.Tw + t);
   }
   __syncthreads();
-  // scores: one warp per PAIR of regions, lanes over channels: every word vector element read from shared memory feeds
-  // two FMAs (the loop is bound by shared-memory loads, one per FMA before)
-  for (int r = wrp; r < a.R; r += 2 * (DT / 32)) {
-    const int r1 = r + DT / 32;
-    const bool has1 = r1 < a.R;
-    float acc0[NT], acc1[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
-#pragma unroll 4
-    for (int c = lane; c < a.D; c += 32) {
-      const float x0 = __ldg(ctx + (size_t)r * a.D + c);
-      const float x1 = has1 ? __ldg(ctx + (size_t)r1 * a.D + c) : 0.f;
-#pragma unroll
-      for (int t = 0; t < NT; ++t)
-        if (t < n) {
-          const float wv = s.w[c * ldw + t];
-          acc0[t] = fmaf(x0, wv, acc0[t]);
-          acc1[t] = fmaf(x1, wv, acc1[t]);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      if (t < n) {
-        const float z0 = warp_sum(acc0[t]), z1 = warp_sum(acc1[t]);
-        if (lane == 0) {
-          s.S[r * ldw + t] = z0;
-          if (has1) s.S[r1 * ldw + t] = z1;
-        }
-      }
-    }
-  }
+  pair_scores<NT, false>(ctx, s.w, a.R, a.D, n, s.S, ldS);
   __syncthreads();
   // a1 = softmax over words (per region)
   for (int r = tid; r < a.R; r += DT) {
     float mx = -INFINITY;
-    for (int t = 0; t < n; ++t) mx = fmaxf(mx, s.S[r * ldw + t]);
+    for (int t = 0; t < n; ++t) mx = fmaxf(mx, s.S[r * ldS + t]);
     float sum = 0.f;
     for (int t = 0; t < n; ++t) {
-      float e = expf(s.S[r * ldw + t] - mx);
-      s.S[r * ldw + t] = e;
+      float e = expf(s.S[r * ldS + t] - mx);
+      s.S[r * ldS + t] = e;
       sum += e;
     }
     const float inv = 1.f / sum;
-    for (int t = 0; t < n; ++t) s.S[r * ldw + t] *= inv;
+    for (int t = 0; t < n; ++t) s.S[r * ldS + t] *= inv;
   }
   __syncthreads();
   // a2 = softmax over regions of gamma1 * a1 (per word): one warp per word
   for (int t = wrp; t < n; t += DT / 32) {
     float mx = -INFINITY;
-    for (int r = lane; r < a.R; r += 32) mx = fmaxf(mx, a.g1 * s.S[r * ldw + t]);
+    for (int r = lane; r < a.R; r += 32) mx = fmaxf(mx, a.g1 * s.S[r * ldS + t]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int r = lane; r < a.R; r += 32) {
-      float e = expf(a.g1 * s.S[r * ldw + t] - mx);
+      float e = expf(a.g1 * s.S[r * ldS + t] - mx);
       s.A2[t * ldA + r] = e;
       sum += e;
     }
@@ -253,7 +280,7 @@ __global__ void __launch_bounds__(DT, CPT == 1 && NT <= 24 ? 2 : 1) damsm_bwd_ke
   float* dA = s.cosv + 4 * NT;   // [NT][R+1]: d a2 -> d(gamma1*a1) -> reused
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const float* ctx = a.ctx + (size_t)b * a.R * a.D;
-  const int ldw = NT + 1, ldA = lda_of(a.R);
+  const int ldw = NT + 2, ldS = NT + 1, ldA = lda_of(a.R);
   {
     const int i = blockIdx.y;
     float* dctx = a.dctx + ((size_t)i * a.B + b) * a.R * a.D;
@@ -300,35 +327,7 @@ __global__ void __launch_bounds__(DT, CPT == 1 && NT <= 24 ? 2 : 1) damsm_bwd_ke
       }
     }
     __syncthreads();
-    for (int r = wrp; r < a.R; r += 2 * (DT / 32)) {
-      const int r1 = r + DT / 32;
-      const bool has1 = r1 < a.R;
-      float acc0[NT], acc1[NT];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
-#pragma unroll 4
-      for (int c = lane; c < a.D; c += 32) {
-        const float x0 = __ldg(ctx + (size_t)r * a.D + c);
-        const float x1 = has1 ? __ldg(ctx + (size_t)r1 * a.D + c) : 0.f;
-#pragma unroll
-        for (int t = 0; t < NT; ++t)
-          if (t < n) {
-            const float dvv = dvs[c * ldw + t];
-            acc0[t] = fmaf(x0, dvv, acc0[t]);
-            acc1[t] = fmaf(x1, dvv, acc1[t]);
-          }
-      }
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        if (t < n) {
-          const float z0 = warp_sum(acc0[t]), z1 = warp_sum(acc1[t]);
-          if (lane == 0) {
-            dA[t * ldA + r] = z0;   // d a2[t][r]
-            if (has1) dA[t * ldA + r1] = z1;
-          }
-        }
-      }
-    }
+    pair_scores<NT, true>(ctx, dvs, a.R, a.D, n, dA, ldA);   // d a2[t][r] = sum_c dv_t[c] ctx[r][c]
     __syncthreads();
     // softmax-over-regions backward: d(gamma1 a1[r][t]) = a2 (da2 - <a2, da2>)  -> da1 = gamma1 * that
     for (int t = wrp; t < n; t += DT / 32) {
@@ -342,8 +341,8 @@ __global__ void __launch_bounds__(DT, CPT == 1 && NT <= 24 ? 2 : 1) damsm_bwd_ke
     // softmax-over-words backward (per region): dS[r][t] = a1 (da1 - <a1, da1>), stored back into dA[t][r]
     for (int r = tid; r < a.R; r += DT) {
       float dot = 0.f;
-      for (int t = 0; t < n; ++t) dot = fmaf(s.S[r * ldw + t], dA[t * ldA + r], dot);
-      for (int t = 0; t < n; ++t) dA[t * ldA + r] = s.S[r * ldw + t] * (dA[t * ldA + r] - dot);
+      for (int t = 0; t < n; ++t) dot = fmaf(s.S[r * ldS + t], dA[t * ldA + r], dot);
+      for (int t = 0; t < n; ++t) dA[t * ldA + r] = s.S[r * ldS + t] * (dA[t * ldA + r] - dot);
     }
     __syncthreads();
     // d ctx[r][c] = sum_t dv_t[c] a2[t][r] + dS[r][t] w[c][t]: four regions per step (128-bit loads of a2 / dS), the

@@ -84,7 +84,10 @@ def test_libmog_encoder_matches_reference(prec):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [(0, 3, 2, 0, 35, 35, 24), (0, 3, 2, 0, 147, 147, 24), (1, 3, 1, 1, 17, 17, 24), (1, 8, 8, 0, 8, 8, 24),
-                                  (0, 3, 2, 1, 9, 12, 24), (1, 2, 2, 0, 7, 9, 24), (0, 3, 2, 0, 13, 11, 6), (1, 3, 1, 1, 5, 7, 3)])
+                                  (0, 3, 2, 1, 9, 12, 24), (1, 2, 2, 0, 7, 9, 24), (0, 3, 2, 0, 13, 11, 6), (1, 3, 1, 1, 5, 7, 3),
+                                  # wider channel counts (several 128-byte lines per pixel)
+                                  (0, 3, 2, 0, 35, 35, 64), (1, 3, 1, 1, 17, 17, 96), (0, 3, 2, 1, 9, 12, 32), (1, 2, 2, 0, 7, 9, 64),
+                                  (0, 3, 1, 1, 6, 21, 32)])
 def test_pool2d_matches_torch(case):
     from mog_b200 import ops
     mode, k, s, p, H, W, Cc = case
