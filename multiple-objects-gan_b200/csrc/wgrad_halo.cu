@@ -252,38 +252,11 @@ struct WHReduceArgs {
   int nsrc[16];
   int src[16][4];
 };
-// many splits (the big generator layers: up to ~100 partials per element): one thread per (tap, co, ci), 8 loads in flight
-__global__ void wgrad_halo_reduce_split_kernel(const WHReduceArgs a) {
-  // one thread per (filter tap k, co, ci): reads coalesced along ci, fixed summation order (deterministic),
-  // 8 independent partial sums in flight to cover the L2 latency
-  const size_t per_tap = (size_t)a.Cin * a.Cout;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // co * Cin + ci
-  const int k = blockIdx.y;
-  if (idx >= per_tap) return;
-  const size_t per_split = (size_t)a.nent * per_tap;
-  const int ns = a.nsrc[k];
-  const int total = a.splits * ns;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int i0 = 0; i0 < total; i0 += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = i0 + j;
-      if (i < total) {
-        const int z = i / ns, u = i - z * ns;
-        acc[j] += __ldg(a.ws + (size_t)z * per_split + (size_t)a.src[k][u] * per_tap + idx);
-      }
-    }
-  }
-  a.dw[idx * a.KHW + k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-}
-
-
-// Many splits, FEW outputs (the patch-matrix GEMMs of the thin layers: 32 x 48 outputs, 296 partials each; 1x1 layers): the
-// thread-per-output kernel above would run a dozen blocks, each thread walking ~300 partials 8 at a time (~110 us of pure
-// latency, measured).  Here 8 split lanes share an output: lane l sums partials l, l + 8, ... (ascending), the 8 lane sums are
-// combined in lane order through shared memory -- a fixed order, deterministic.  Block = 32 outputs x 8 lanes.
+// Many splits (the generator's layers: up to ~300 partials per element; the patch-matrix GEMMs of the thin layers: 32 x 48
+// outputs, 296 partials each).  A thread per output walking its partials 8 at a time was pure latency: a dozen blocks and
+// ~110 us for the thin GEMMs, 60 - 75 us for the 96 x 96 x 9 layers (ncu r2q).  Here 8 split lanes share an output: lane l
+// sums partials l, l + 8, ... (ascending), the 8 lane sums are combined in lane order through shared memory -- a fixed order,
+// deterministic.  Block = 32 outputs x 8 lanes.
 constexpr int WRS_LANES = 8;
 __global__ void __launch_bounds__(256) wgrad_halo_reduce_lanes_kernel(const WHReduceArgs a) {
   __shared__ float part[WRS_LANES][33];
@@ -643,10 +616,7 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
     wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div(d.Cin, WR_CI), (unsigned)ceil_div(d.Cout, WR_CO)), 256, 0, st>>>(ra, p.splits * max_src);
   } else {
     const size_t total = (size_t)d.Cin * d.Cout;
-    if (total * (size_t)(d.KH * d.KW) < (size_t)64 * 1024)
-      wgrad_halo_reduce_lanes_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 32), (unsigned)(d.KH * d.KW)), 256, 0, st>>>(ra);
-    else
-      wgrad_halo_reduce_split_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 128), (unsigned)(d.KH * d.KW)), 128, 0, st>>>(ra);
+    wgrad_halo_reduce_lanes_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 32), (unsigned)(d.KH * d.KW)), 256, 0, st>>>(ra);
   }
   return check_launch("wgrad_halo_reduce_kernel");
 }
