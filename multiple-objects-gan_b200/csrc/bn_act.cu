@@ -2,7 +2,7 @@
 // LeakyReLU / none, optional residual) forward, and the two-pass backward.  HBM-bound streaming
 // kernels over [S*M][C] row-major (NHWC) tensors: per-channel reductions run over rows with
 // 32 consecutive channels per warp row (128-byte coalesced), partials are combined with
-// warp/smem reductions and one double atomicAdd per (block, channel).
+// warp/smem reductions into one fp64 partial per (block, channel); a second kernel adds the partials in a fixed order.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -378,10 +378,10 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 // The scalar kernels above remain for odd channel counts.
 // ---------------------------------------------------------------------------------------------
 struct V4Geom { int Cv, GB, R, nxb, rpb, nyb; };
-// reduce = true: the reducing kernels (statistics, backward sums) end in one double atomicAdd per channel per block.
-// Same-address fp64 atomics serialise in L2 at ~55 ns each (measured: 6554 blocks -> 320 us for a pass that streams in
-// 125 us), so those kernels run a fixed, small number of blocks (about two per SM over all column groups and segments),
-// each looping over its row chunks with the sums kept in registers.
+// reduce = true: the reducing kernels (statistics, backward sums) leave one fp64 partial per channel per block, so they run a
+// fixed, small number of blocks (a few per SM over all column groups and segments), each looping over its row chunks with the
+// sums kept in registers.  (History: the first version ended in fp64 atomics, which serialise in L2 at ~55 ns each -- 6554
+// blocks -> 320 us for a pass that streams in 125 us -- and are not bit-reproducible.)
 // which (reducing kernels only): 0 = forward statistics, 1 = backward reduce.  The grid of a reducing kernel is capped at the
 // number of blocks that are RESIDENT at once (each block strides over the rows and leaves one partial): bn_stats_v4_kernel
 // holds 3 blocks per SM (80 registers), and a grid of 4 per SM ran as one full wave plus a one-third wave -- 4.3 TB/s instead

@@ -476,6 +476,10 @@ int launch_wgrad_reduce(const float* ws, float* dw, int splits, int K, int Cout,
                         cudaStream_t st) {
   dim3 grid(ceil_div(Cin, RCI), ceil_div(Cout, RCO));
   const size_t smem = sizeof(float) * RCO * (RCI * KHW + 1);
+  if (smem > 48 * 1024) {   // 5x5 filters: 51 KB (found by tests/test_gpu_fullsize.py: the launch failed with "invalid argument")
+    cudaError_t e = cudaFuncSetAttribute(wgrad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(MOG_ERR_UNSUPPORTED, "wgrad_reduce_kernel: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+  }
   wgrad_reduce_kernel<<<grid, 256, smem, st>>>(ws, dw, splits, K, Cout, Cin, CinP, KHW);
   return check_launch("wgrad_reduce_kernel");
 }

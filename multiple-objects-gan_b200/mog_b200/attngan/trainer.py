@@ -561,6 +561,13 @@ class GraphedStep:
                 for bf, v in saved:
                     bf.copy_(v)
         torch.cuda.current_stream().wait_stream(side)
+        # the multi-tensor repacking tables of the optimisers (ops.repack) are (re)built on the host whenever a weight gained a
+        # packed layout since the last optimiser step -- e.g. the data-gradient layouts of the discriminators, first needed by
+        # the generator step AFTER their own Adam step.  Build them now, eagerly: a rebuild inside the capture would be a
+        # pageable host-to-device copy (an error under capture).  Repacking the current weights changes nothing.
+        from .. import ops as _ops
+        for o in self.opts:
+            _ops.repack([p for g in o.param_groups for p in g["params"] if p.grad is not None])
         torch.cuda.synchronize()
         from .. import _lib
         n0 = _lib.launch_count()

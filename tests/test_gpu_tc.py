@@ -68,6 +68,7 @@ TC_CASES = [
     (3, 16, 16, 1, 16, 4, 2, 1, False, False, 2),     # 1-channel images (Multi-MNIST discriminator): K = 16
     (2, 16, 24, 4, 24, 3, 1, 1, False, False, 0),     # Cin = 4: K = 36 -> 40
     (2, 16, 16, 24, 2, 3, 1, 1, False, False, 4),     # Cout = 2 + tanh: backward on patches of dz, K = 18 -> 24
+    (2, 12, 12, 48, 64, 5, 1, 2, False, False, 1),    # Inception 5x5 (25 taps: the generic weight-gradient reduce needs 51 KB of smem)
 ]
 
 
