@@ -249,8 +249,8 @@ def test_graphed_step_equals_eager_steps():
                     gs = tr2.graphed_step(st2, *args, warmup=1, noise=noises[k], eps=epss[k], dry_warmup=True)
                 losses2.append([t.clone() for t in gs(*args, noise=noises[k], eps=epss[k])])
         torch.cuda.synchronize()
-        # (the BatchNorm reductions end in fp64 atomics, so two runs agree to rounding, not bit for bit; Adam then moves
-        # near-zero-gradient entries by +-lr either way -- same gates as the reference comparison)
+        # (gates as in the reference comparison; at the benchmark's size the same comparison is made bit for bit:
+        # tests/test_gpu_fullsize.py)
         rel = lambda a, r: float((a.double() - r.double()).norm() / r.double().norm().clamp_min(1e-30))   # noqa: E731
         for k in range(K):
             for a, r in zip(losses2[k], losses1[k]):
