@@ -254,11 +254,11 @@ struct WHReduceArgs {
 };
 // Many splits (the generator's layers: up to ~300 partials per element; the patch-matrix GEMMs of the thin layers: 32 x 48
 // outputs, 296 partials each).  A thread per output walking its partials 8 at a time was pure latency: a dozen blocks and
-// ~110 us for the thin GEMMs, 60 - 75 us for the 96 x 96 x 9 layers (ncu r2q).  Here 8 split lanes share an output: lane l
-// sums partials l, l + 8, ... (ascending), the 8 lane sums are combined in lane order through shared memory -- a fixed order,
-// deterministic.  Block = 32 outputs x 8 lanes.
-constexpr int WRS_LANES = 8;
-__global__ void __launch_bounds__(256) wgrad_halo_reduce_lanes_kernel(const WHReduceArgs a) {
+// ~110 us for the thin GEMMs, 60 - 75 us for the 96 x 96 x 9 layers (ncu r2q).  Here 16 split lanes share an output: lane l
+// sums partials l, l + 16, ... (ascending, 4 loads in flight), the 16 lane sums are combined in lane order through shared
+// memory -- a fixed order, deterministic.  Block = 32 outputs x 16 lanes.
+constexpr int WRS_LANES = 16;
+__global__ void __launch_bounds__(32 * WRS_LANES) wgrad_halo_reduce_lanes_kernel(const WHReduceArgs a) {
   __shared__ float part[WRS_LANES][33];
   const size_t per_tap = (size_t)a.Cin * a.Cout;
   const int ol = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -316,18 +316,26 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WHReduceAr
     for (int c = 0; c < WR_CO; ++c) acc[c][j] = 0.f;
   }
   if (ci < a.Cin) {
-    for (int i = 0; i < maxtotal; ++i) {
+    for (int i0 = 0; i0 < maxtotal; i0 += 2) {     // two partials per step: up to 16 loads in flight per thread
+      float v[2][WR_CO][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (i < tot[j]) {
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + h;
+          const bool on = i < tot[j];
           const int k = kq + 4 * j;
-          const int z = i / ns[j], u = i - z * ns[j];
-          const float* src = a.ws + (size_t)z * per_split + (size_t)a.src[k][u] * per_tap + ci;
+          const int z = on ? i / ns[j] : 0, u = on ? i - z * ns[j] : 0;
+          const float* src = a.ws + (size_t)z * per_split + (size_t)a.src[on ? k : 0][u] * per_tap + ci;
 #pragma unroll
-          for (int c = 0; c < WR_CO; ++c)
-            if (co0 + c < a.Cout) acc[c][j] += __ldg(src + (size_t)(co0 + c) * a.Cin);
+          for (int c = 0; c < WR_CO; ++c) v[h][c][j] = (on && co0 + c < a.Cout) ? __ldg(src + (size_t)(co0 + c) * a.Cin) : 0.f;
         }
-      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)      // ascending partial index: the summation order is fixed
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < WR_CO; ++c) acc[c][j] += v[h][c][j];
     }
   }
 #pragma unroll
@@ -616,7 +624,7 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
     wgrad_halo_reduce_kernel<<<dim3((unsigned)ceil_div(d.Cin, WR_CI), (unsigned)ceil_div(d.Cout, WR_CO)), 256, 0, st>>>(ra, p.splits * max_src);
   } else {
     const size_t total = (size_t)d.Cin * d.Cout;
-    wgrad_halo_reduce_lanes_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 32), (unsigned)(d.KH * d.KW)), 256, 0, st>>>(ra);
+    wgrad_halo_reduce_lanes_kernel<<<dim3((unsigned)ceil_div_ll((long long)total, 32), (unsigned)(d.KH * d.KW)), 32 * WRS_LANES, 0, st>>>(ra);
   }
   return check_launch("wgrad_halo_reduce_kernel");
 }
