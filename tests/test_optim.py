@@ -96,3 +96,55 @@ def test_adam_update_reaches_the_next_forward(prec):
         w_before = w.detach().clone()
         opt.step()
         assert float((w.detach() - w_before).abs().max()) > 1e-3
+
+
+REPACK_CASES = [
+    # Cout, Cin, k, stride, pad, up2x, H      (x is [2, H, H, Cin])
+    (192, 96, 3, 1, 1, False, 16),    # ResBlock conv: fwd + dgrad (transposed) packs
+    (96, 96, 3, 1, 1, True, 16),      # upBlock: 4 sub-pixel phase packs with pre-summed 2x2 taps, dgrad through parity views
+    (192, 96, 4, 2, 1, False, 16),    # downBlock 4x4/s2: parity-view forward, 4 stride-phase dgrad packs
+    (40, 88, 4, 1, 1, False, 16),     # ragged channel counts (Cout 40 -> N tile 48, Cin 88)
+    (64, 48, 1, 1, 0, False, 12),     # 1x1
+    (1536, 768, 4, 2, 1, False, 8),   # deep discriminator layer: several N tiles, K = 12288
+    (96, 3, 4, 2, 1, False, 16),      # 3 input channels: only the dgrad pack is cached (forward runs on the patch matrix)
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", REPACK_CASES, ids=lambda c: "x".join(str(int(v)) for v in c))
+def test_multi_tensor_repack_equals_per_problem_pack(case):
+    """ops.repack (ONE mog_pack_multi launch over all cached layouts of the updated weights -- what runs after every fused Adam
+    step) must leave exactly the bytes mog_pack_weight (the lazy per-problem pack) writes."""
+    from mog_b200 import ops
+    Co, Ci, k, s, p, up, H = case
+    P = ops.PREC_NAMES["bf16x3"]
+    torch.manual_seed(5)
+    w = (torch.randn(Co, Ci, k, k, device="cuda") * 0.05).requires_grad_(True)
+    x = torch.randn(2, H, H, Ci, device="cuda", requires_grad=True)
+
+    def fwd_bwd():
+        y = ops.conv2d(x, w, None, s, p, up, ops.ACT_NONE, P)
+        y.sum().backward()
+        x.grad = None
+        w.grad = None
+
+    fwd_bwd()                                    # creates the packed layouts (lazy mog_pack_weight)
+    cache = w._mog_pack
+    assert len(cache) >= 1
+    with torch.no_grad():
+        w.mul_(1.7).add_(0.01)                   # new values
+    ops.invalidate_packed([w])
+    for ent in cache.values():                   # (alignment gaps between phase blocks are written by neither kernel)
+        ent["out"].zero_()
+    ops.repack([w])                              # multi-tensor kernel
+    torch.cuda.synchronize()
+    multi = {key: ent["out"].clone() for key, ent in cache.items()}
+    covered = [key for key, ent in cache.items() if ent["ver"] == ops._weight_version(w)]
+    assert covered, "no layout of this weight went through mog_pack_multi"
+    for ent in cache.values():                   # force the lazy path to rewrite every layout
+        ent["ver"] = None
+        ent["out"].zero_()
+    fwd_bwd()
+    torch.cuda.synchronize()
+    for key in covered:
+        assert torch.equal(multi[key].view(torch.int32), cache[key]["out"].view(torch.int32)), key
