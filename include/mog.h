@@ -127,6 +127,14 @@ int mog_split_planes_act(const float* dy, const float* y, int act, long long row
 int mog_patch_planes(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int precision,
                      void* planes, void* stream);
 
+/* The adjoint of mog_patch_planes with the conv epilogue (col2im): z is the fp32 output [N*Ho*Wo][ldz] of a 1x1 problem whose
+ * column k = (kh*KW + kw)*C + c is the contribution of tap (kh, kw) to channel c;
+ *   y[n,h,w,c] = act(bias[c] + sum of z[(n,ho,wo)][k] over the taps with (h + pad - kh, w + pad - kw) = stride * (ho, wo)).
+ * C <= 4, KH*KW <= 16; Ho, Wo are the conv's output size for an H x W input.  Used for the data gradient of convs with <= 4
+ * input channels (z = dy . w) and the forward of 'same' convs with <= 4 output channels (GET_IMAGE_G, model.py:464-474). */
+int mog_col2im_act(const float* z, int ldz, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                   const float* bias, int act, float* y, void* stream);
+
 /* replaces: nn.Conv2d forward incl. a preceding nn.Upsample(2,'nearest') (model.py:41-55,
  * 587-609,626,664-677; GlobalAttention.py:25-28) and nn.Linear (H=W=KH=KW=1; model.py:324,
  * 365,371).  y: [N,Ho,Wo,Cout]; bias may be NULL. */

@@ -378,6 +378,19 @@ extern "C" int mog_patch_planes(const float* x, int N, int H, int W, int C, int 
   return launch_patch_planes(x, N, H, W, C, KH, KW, stride, pad, Ho, Wo, planes, precision == MOG_PREC_BF16X3 ? 2 : 1, as_stream(stream));
 }
 
+extern "C" int mog_col2im_act(const float* z, int ldz, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                             const float* bias, int act, float* y, void* stream) {
+  MOG_REQUIRE(z && y && N > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "mog_col2im_act: bad argument");
+  MOG_REQUIRE(C <= 4 && KH * KW <= 16, "mog_col2im_act: implemented for C <= 4 channels and filters of at most 16 taps (C=%d, %dx%d)", C, KH, KW);
+  MOG_REQUIRE(ldz >= KH * KW * C && (ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0,
+              "mog_col2im_act: row pitch %d must be >= KH*KW*C and a multiple of 4, z 16-byte aligned", ldz);
+  MOG_REQUIRE(H + 2 * pad >= KH && W + 2 * pad >= KW, "mog_col2im_act: filter larger than the padded image");
+  MOG_REQUIRE(act == MOG_ACT_NONE || act == MOG_ACT_RELU || act == MOG_ACT_LRELU || act == MOG_ACT_TANH || act == MOG_ACT_SIGMOID,
+              "mog_col2im_act: activation %d", act);
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  return launch_col2im_act(z, ldz, N, H, W, C, KH, KW, stride, pad, Ho, Wo, bias, act, y, as_stream(stream));
+}
+
 static int build(const MogConvDesc* d, int which, Problem* probs, int* hires) {
   *hires = 0;
   return which == 0 ? build_fwd(d, probs) : build_dgrad(d, probs, hires);

@@ -73,6 +73,8 @@ int launch_wgrad_halo(const MogConvDesc& d, int Ho, int Wo, const void* x_planes
                       int passes, cudaStream_t st);
 int launch_patch_planes(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
                         void* planes, int nplanes, cudaStream_t st);
+int launch_col2im_act(const float* z, int ldz, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                      const float* bias, int act, float* y, cudaStream_t st);
 int launch_split_planes(const float* x, long long rows, int C, int CP, void* planes, int nplanes, cudaStream_t st,
                         const float* y = nullptr, int act = 0);
 

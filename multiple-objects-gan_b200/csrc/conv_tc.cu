@@ -779,6 +779,95 @@ __global__ void patch_planes_kernel(const float* __restrict__ x, int N, int H, i
   if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// The adjoint of patch extraction (col2im) with the conv epilogue:
+//   y[n, h, w, c] = act(bias[c] + sum over taps (kh, kw) with (h + pad - kh, w + pad - kw) = stride * (ho, wo), (ho, wo) inside
+//                       the Ho x Wo grid, of z[(n, ho, wo)][(kh*KW + kw)*C + c])
+// z = the output of a 1x1 problem with KP >= KH*KW*C columns (row pitch ldz).  Two uses, both for C <= 4:
+//   * the data gradient of a conv with <= 4 INPUT channels: z = dy . W2, W2[(kh, kw, ci)][co] = w[co][ci][kh][kw] -- instead of
+//     KH*KW/stride^2-tap stride phases whose N tile holds 3 real columns (D_NET256 layer 1: 4 x 89 us at 9.6 % tensor pipe);
+//   * the FORWARD of a 'same' conv with <= 4 output channels (GET_IMAGE_G): z[q][(a, b, co)] = sum_ci x[q][ci] w[co][ci][KH-1-a][KW-1-b]
+//     (0.42 ms at 12 % tensor pipe as a 9-tap conv with a 16-column N tile).
+// One thread per output pixel, all C channels; the <= 16 taps are loaded up front (fixed summation order: tap ascending).
+struct Col2imArgs {
+  const float* z;
+  const float* bias;
+  float* y;
+  int N, H, W, C, KH, KW, s, p, Ho, Wo, ldz, act;
+  int nh, nw, pitch;   // rows / columns of z rows staged per tile, shared-memory pitch of a staged row (odd)
+};
+constexpr int C2I_TH = 8, C2I_TW = 32;   // output tile: 8 x 32 pixels, one per thread
+// first / last patch-grid index along one axis that touches output positions [o0, o0 + T): (o + p - k) = s * g, 0 <= k < K
+__host__ __device__ __forceinline__ int c2i_lo(int o0, int p, int K, int s) {
+  const int v = o0 + p - (K - 1);
+  return v <= 0 ? 0 : (v + s - 1) / s;
+}
+// One block per 8 x 32 tile of output pixels: the z rows the tile gathers from (a (8 + KH - 1)/s x (32 + KW - 1)/s patch of the
+// Ho x Wo grid; consecutive grid columns are consecutive rows of z, so every staged line is one contiguous run) are loaded with
+// 128-bit accesses into shared memory, then every thread sums the taps of its pixel from there (odd pitch: conflict free).
+// (A first version gathered straight from global memory: 12-byte pieces of 9 different 128-byte rows per pixel -- 0.76 ms per
+// step, no faster than the convolutions it replaced.)
+__global__ void __launch_bounds__(C2I_TH * C2I_TW) col2im_act_kernel(const Col2imArgs a) {
+  extern __shared__ float c2i_sm[];
+  const int w0 = blockIdx.x * C2I_TW, h0 = blockIdx.y * C2I_TH, n = blockIdx.z;
+  const int K = a.KH * a.KW * a.C;
+  const int gh0 = c2i_lo(h0, a.p, a.KH, a.s), gw0 = c2i_lo(w0, a.p, a.KW, a.s);
+  const float* zn = a.z + (size_t)n * a.Ho * a.Wo * a.ldz;
+  // ---- stage: lines gh0 .. gh0 + nh - 1, columns gw0 .. gw0 + nw - 1 (clipped to the grid)
+  const int f4_per_row = a.ldz >> 2;
+  const int cols = min(a.nw, a.Wo - gw0), lines = min(a.nh, a.Ho - gh0);
+  const int per_line = cols * f4_per_row, total = lines > 0 && cols > 0 ? lines * per_line : 0;
+  const float4* zb = reinterpret_cast<const float4*>(zn);
+  constexpr int NT = C2I_TH * C2I_TW;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * NT) {     // four 128-bit loads in flight per thread
+    float4 v[4];
+    int line[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * NT;
+      line[u] = i / per_line;
+      r[u] = i - line[u] * per_line;
+      if (i < total) v[u] = __ldg(zb + ((size_t)(gh0 + line[u]) * a.Wo + gw0) * f4_per_row + r[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * NT >= total) break;
+      const int col = r[u] / f4_per_row, k = (r[u] - col * f4_per_row) * 4;
+      float* d = c2i_sm + ((size_t)line[u] * a.nw + col) * a.pitch + k;
+      if (k < K) d[0] = v[u].x;
+      if (k + 1 < K) d[1] = v[u].y;
+      if (k + 2 < K) d[2] = v[u].z;
+      if (k + 3 < K) d[3] = v[u].w;
+    }
+  }
+  __syncthreads();
+  // ---- gather
+  const int tw = threadIdx.x % C2I_TW, th = threadIdx.x / C2I_TW;
+  const int h = h0 + th, w = w0 + tw;
+  if (h >= a.H || w >= a.W) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < a.KH; ++kh) {
+    const int hh = h + a.p - kh;
+    if (hh < 0) break;
+    const int gh = a.s == 1 ? hh : (a.s == 2 ? hh >> 1 : hh / a.s);     // (no integer division for the strides that occur)
+    if (gh * a.s != hh || gh >= a.Ho) continue;
+    const float* line = c2i_sm + (size_t)(gh - gh0) * a.nw * a.pitch;
+    for (int kw = 0; kw < a.KW; ++kw) {
+      const int ww = w + a.p - kw;
+      if (ww < 0) break;
+      const int gw = a.s == 1 ? ww : (a.s == 2 ? ww >> 1 : ww / a.s);
+      if (gw * a.s != ww || gw >= a.Wo) continue;
+      const float* e = line + (gw - gw0) * a.pitch + (kh * a.KW + kw) * a.C;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < a.C) acc[c] += e[c];
+    }
+  }
+  float* yp = a.y + (((size_t)n * a.H + h) * a.W + w) * a.C;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c < a.C) yp[c] = epi_act(acc[c] + (a.bias ? __ldg(a.bias + c) : 0.f), a.act);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -804,6 +893,26 @@ int launch_patch_planes(const float* x, int N, int H, int W, int C, int KH, int 
   const long long n = rows * (KP / 8);
   tc::patch_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, N, H, W, C, KH, KW, stride, pad, Ho, Wo, K, KP, hi, lo);
   return check_launch("patch_planes_kernel");
+}
+
+int launch_col2im_act(const float* z, int ldz, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                      const float* bias, int act, float* y, cudaStream_t st) {
+  tc::Col2imArgs a{z, bias, y, N, H, W, C, KH, KW, stride, pad, Ho, Wo, ldz, act, 0, 0, 0};
+  // staged patch of the grid per tile: indices g with s*g in [o0 + p - (K-1), o0 + T - 1 + p]
+  a.nh = (tc::C2I_TH - 1 + KH - 1) / stride + 2;
+  a.nw = (tc::C2I_TW - 1 + KW - 1) / stride + 2;
+  const int K = KH * KW * C;
+  a.pitch = K | 1;
+  const size_t smem = sizeof(float) * (size_t)a.nh * a.nw * a.pitch;
+  if (smem > 200 * 1024) return fail(MOG_ERR_UNSUPPORTED, "mog_col2im_act: %zu bytes of shared memory", smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(tc::col2im_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(MOG_ERR_UNSUPPORTED, "mog_col2im_act: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+  }
+  if (N > 65535) return fail(MOG_ERR_UNSUPPORTED, "mog_col2im_act: batch too large");
+  dim3 grid((unsigned)ceil_div(W, tc::C2I_TW), (unsigned)ceil_div(H, tc::C2I_TH), (unsigned)N);
+  tc::col2im_act_kernel<<<grid, tc::C2I_TH * tc::C2I_TW, smem, st>>>(a);
+  return check_launch("col2im_act_kernel");
 }
 
 int tc_bn_for(int Cd) {

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mog_split_planes": (_i, [_p, C.c_longlong, _i, _i, _p, _p]),
     "mog_split_planes_act": (_i, [_p, _p, _i, C.c_longlong, _i, _i, _p, _p]),
     "mog_patch_planes": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "mog_col2im_act": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "mog_conv2d_fwd": (_i, [_dp, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mog_conv2d_dgrad": (_i, [_dp, _p, _p, _p, _p, _p, _sz, _p]),
     "mog_conv2d_wgrad": (_i, [_dp, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -371,6 +371,30 @@ def _gemm_grid(N, H, W):
     return (1, M // 8, 8) if M % 8 == 0 else (N, H, W)
 
 
+def _padded_rows(m2, KP):
+    """[K][C] -> contiguous [KP][C], zero pad rows."""
+    if m2.shape[0] == KP:
+        return m2.contiguous()
+    out = torch.zeros(KP, m2.shape[1], device=m2.device, dtype=torch.float32)
+    out[:m2.shape[0]] = m2
+    return out
+
+
+def _gemm_then_col2im(src, src_planes, w2, N, Hs, Ws, out_shape, Cc, KH, KW, stride, pad, bias, act, precision):
+    """out = col2im_act(z), z = the 1x1 problem src [N*Hs*Ws][Cs] . w2^T [Cs][KP] (fp32, [N*Hs*Ws][KP]); see mog_col2im_act."""
+    KP, Cs = w2.shape
+    d1, _, _, dkey1 = _desc(_gemm_grid(N, Hs, Ws) + (Cs,), (KP, Cs, 1, 1), 1, 0, False, ACT_NONE, precision)
+    dev = w2.device
+    z = torch.empty((N * Hs * Ws, KP), device=dev, dtype=torch.float32)
+    ws, nws = _workspace(d1, 0, dev, dkey1)
+    call("mog_conv2d_fwd", C.byref(d1), _ptr(src), _ptr(src_planes), _pack_matrix(w2, d1).data_ptr(), None, z.data_ptr(), _ptr(ws), nws,
+         _stream())
+    out = torch.empty(out_shape, device=dev, dtype=torch.float32)
+    _, H, W, _ = out_shape
+    call("mog_col2im_act", z.data_ptr(), KP, N, H, W, Cc, KH, KW, stride, pad, _ptr(bias), act, out.data_ptr(), _stream())
+    return out
+
+
 def _thin_cin(x, weight, stride, pad, up2x, precision):
     if precision == PREC_FP32 or up2x or weight.dim() != 4 or x.dim() != 4 or isinstance(pad, (tuple, list)):
         return False
@@ -429,7 +453,12 @@ class PatchConv2dFn(torch.autograd.Function):
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
         dy, dyp = _split_dy(dy, y, act, precision, need_db, need_dx or need_dw)
         dx = dw = db = None
-        if need_dx:
+        if need_dx and KH * KW <= 16:
+            # dx = col2im(dy . W2), W2[(kh, kw, ci)][co] = w[co][ci][kh][kw]: one GEMM over the output pixels + a gather, instead
+            # of stride^2 phase problems whose N tile holds 3 real columns
+            w2 = _padded_rows(weight.detach().permute(2, 3, 1, 0).reshape(KH * KW * Ci, Co), KP)
+            dx = _gemm_then_col2im(dy, dyp, w2, N, Ho, Wo, xshape, Ci, KH, KW, stride, pad, None, ACT_NONE, precision)
+        elif need_dx:
             d, _, _, dkey = _desc(xshape, weight.shape, stride, pad, False, ACT_NONE, precision)
             dx = torch.empty(xshape, device=dev, dtype=torch.float32)
             ws, nws = _workspace(d, 1, dev, dkey)
@@ -457,12 +486,20 @@ class Conv2dFn(torch.autograd.Function):
         _chk(x, "conv input")
         w4 = weight if weight.dim() == 4 else weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
         d, Ho, Wo, dkey = _desc(x.shape, w4.shape, stride, pad, up2x, act, precision)
-        y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
-        ws, nws = _workspace(d, 0, x.device, dkey)
         b = None if bias is None else bias.detach().contiguous()
         xp = planes_of(x, precision) if precision != PREC_FP32 else None
-        call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _ptr(xp), _packed(weight, "fwd", d, dkey).data_ptr(), _ptr(b),
-             y.data_ptr(), _ptr(ws), nws, _stream())
+        if _thin_cout_bwd(w4.shape, stride, pad, up2x, precision, False) and w4.shape[2] * w4.shape[3] <= 16:
+            # <= 4 output channels ('same' conv: GET_IMAGE_G): z[q][(a, b, co)] = sum_ci x[q][ci] w[co][ci][KH-1-a][KW-1-b] is one
+            # GEMM over the pixels with KP = KH*KW*Cout -> 8 columns; y = col2im(z) + bias, activation (mog_col2im_act)
+            Co, Ci, KH, KW = w4.shape
+            KP = (KH * KW * Co + 7) // 8 * 8
+            w2 = _padded_rows(w4.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(KH * KW * Co, Ci), KP)
+            y = _gemm_then_col2im(x, xp, w2, d.N, d.H, d.W, (d.N, Ho, Wo, Co), Co, KH, KW, 1, pad, b, act, precision)
+        else:
+            y = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32)
+            ws, nws = _workspace(d, 0, x.device, dkey)
+            call("mog_conv2d_fwd", C.byref(d), x.data_ptr(), _ptr(xp), _packed(weight, "fwd", d, dkey).data_ptr(), _ptr(b),
+                 y.data_ptr(), _ptr(ws), nws, _stream())
         ctx.cfg = (stride, pad, up2x, act, precision, tuple(x.shape))
         ctx.has_bias = bias is not None
         # the input is only needed again for the weight / bias gradient: a frozen conv (image encoder) keeps nothing of it

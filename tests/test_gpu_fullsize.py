@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 ADJ_TOL = 2e-4
 
 FULL_SIZE_LAYERS = [
-    # N, H, W, Cin, Cout, KH, KW, stride, pad, up2x     (shapes of profiles/r2r_shape_profile.txt)
+    # N, H, W, Cin, Cout, KH, KW, stride, pad, up2x     (shapes of profiles/r2z_shape_profile.txt)
     (32, 128, 128, 96, 192, 3, 3, 1, 1, False),   # ResBlock conv C -> 2C @128^2 (halo form)
     (32, 128, 128, 96, 96, 3, 3, 1, 1, True),     # G.h_net3.upsample: up2x + 3x3 -> 256^2 (sub-pixel phases) -- the roofline conv
     (64, 128, 128, 96, 192, 4, 4, 2, 1, False),   # D_NET256 layer 2, real+fake pair pass (parity views)

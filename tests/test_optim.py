@@ -106,7 +106,6 @@ REPACK_CASES = [
     (40, 88, 4, 1, 1, False, 16),     # ragged channel counts (Cout 40 -> N tile 48, Cin 88)
     (64, 48, 1, 1, 0, False, 12),     # 1x1
     (1536, 768, 4, 2, 1, False, 8),   # deep discriminator layer: several N tiles, K = 12288
-    (96, 3, 4, 2, 1, False, 16),      # 3 input channels: only the dgrad pack is cached (forward runs on the patch matrix)
 ]
 
 
