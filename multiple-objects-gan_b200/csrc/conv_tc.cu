@@ -740,16 +740,16 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
 // on the patch matrix the same conv is a 1x1 conv with KP channels.  One thread per 8-column chunk of a patch row.
 __global__ void patch_planes_kernel(const float* __restrict__ x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
                                     int Ho, int Wo, int K, int KP, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  // grid: x = image row of the patch grid (n * Ho + ho), y = blocks over (wo, 8-column chunk): 32-bit index arithmetic only
+  // (the flat 64-bit decomposition idx -> (n, ho, wo, chunk) cost four 64-bit divisions per thread: the kernel was
+  // instruction bound at 1.7 TB/s of plane writes, ncu r2u)
   const int cpr = KP >> 3;
-  const long long rows = (long long)N * Ho * Wo;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cpr) return;
-  const long long r = idx / cpr;
-  const int k0 = (int)(idx - r * cpr) * 8;
-  const int wo = (int)(r % Wo);
-  const long long q = r / Wo;
-  const int ho = (int)(q % Ho);
-  const int n = (int)(q / Ho);
+  const int item = blockIdx.y * blockDim.x + threadIdx.x;     // wo * cpr + chunk
+  if (item >= Wo * cpr) return;
+  const int wo = item / cpr;
+  const int k0 = (item - wo * cpr) * 8;
+  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
+  const long long r = (long long)blockIdx.x * Wo + wo;
   const int h0 = ho * stride - pad, w0 = wo * stride - pad;
   const float* xn = x + (size_t)n * H * W * C;
   float f[8];
@@ -890,8 +890,10 @@ int launch_patch_planes(const float* x, int N, int H, int W, int C, int KH, int 
   const long long rows = (long long)N * Ho * Wo;
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(planes);
   __nv_bfloat16* lo = nplanes == 2 ? hi + (size_t)rows * KP : nullptr;
-  const long long n = rows * (KP / 8);
-  tc::patch_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, N, H, W, C, KH, KW, stride, pad, Ho, Wo, K, KP, hi, lo);
+  const int per_line = Wo * (KP / 8);
+  if ((long long)N * Ho > 0x7fffffffLL || ceil_div(per_line, 256) > 65535) return fail(MOG_ERR_UNSUPPORTED, "mog_patch_planes: problem too large");
+  tc::patch_planes_kernel<<<dim3((unsigned)(N * Ho), (unsigned)ceil_div(per_line, 256)), 256, 0, st>>>(x, N, H, W, C, KH, KW, stride, pad, Ho,
+                                                                                                       Wo, K, KP, hi, lo);
   return check_launch("patch_planes_kernel");
 }
 
