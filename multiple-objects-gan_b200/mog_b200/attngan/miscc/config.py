@@ -47,7 +47,7 @@ def _defaults():
     c.GAN = edict(DF_DIM=64, GF_DIM=128, Z_DIM=100, CONDITION_DIM=100, R_NUM=2, B_ATTENTION=True, B_DCGAN=False)
     c.TEXT = edict(CAPTIONS_PER_IMAGE=10, EMBEDDING_DIM=256, WORDS_NUM=18)
     # libmog extensions (not in the reference): conv operand precision and STN convention
-    c.MOG = edict(PRECISION='bf16x3', ALIGN_CORNERS=False, MASK_QUIRK=True, CUDA_GRAPH=True)
+    c.MOG = edict(PRECISION='bf16x3', ALIGN_CORNERS=False, MASK_QUIRK=True, CUDA_GRAPH=True, STREAMS=True)
     return c
 
 

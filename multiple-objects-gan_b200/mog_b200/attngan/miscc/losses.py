@@ -64,37 +64,63 @@ def discriminator_loss(netD, real_imgs, fake_imgs, conditions, real_labels, fake
 
 def generator_loss(netsD, image_encoder, fake_imgs, real_labels, words_embs, sent_emb, match_labels,
                    cap_lens, class_ids, gpus=None, local_labels=None, transf_matrices=None,
-                   transf_matrices_inv=None):
+                   transf_matrices_inv=None, streams=None):
     """losses.py:177-226.  ``logs`` is returned as a list of (name, 0-d tensor) pairs instead of a
     formatted string so that no ``.item()`` host sync happens inside the step (the reference forces
     4-5 syncs per step, losses.py:204,225); ``format_logs`` renders the reference's string.
     With ``image_encoder is None`` the DAMSM terms (losses.py:205-224) are skipped (G+D-only step)."""
     numDs = len(netsD)
-    logs = []
-    errG_total = 0
-    for i in range(numDs):
+    batch_size = real_labels.size(0)
+
+    def d_branch(i):
         if i == 0:
             features = netsD[i](fake_imgs[i], local_labels, transf_matrices, transf_matrices_inv)
         else:
             features = netsD[i](fake_imgs[i])
         cond_errG = ops.sigmoid_bce(netsD[i].COND_DNET.logits(features, sent_emb), real_labels)
         if netsD[i].UNCOND_DNET is not None:
-            errG = ops.sigmoid_bce(netsD[i].UNCOND_DNET.logits(features), real_labels)
-            g_loss = errG + cond_errG
-        else:
-            g_loss = cond_errG
-        errG_total = errG_total + g_loss
-        logs.append(('g_loss%d' % i, g_loss.detach()))
-        if i == (numDs - 1) and image_encoder is not None:
-            region_features, cnn_code = image_encoder(fake_imgs[i])
-            batch_size = real_labels.size(0)
-            w_loss0, w_loss1, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size)
-            w_loss = (w_loss0 + w_loss1) * cfg.TRAIN.SMOOTH.LAMBDA
-            s_loss0, s_loss1 = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
-            s_loss = (s_loss0 + s_loss1) * cfg.TRAIN.SMOOTH.LAMBDA
-            errG_total = errG_total + w_loss + s_loss
-            logs.append(('w_loss', w_loss.detach()))
-            logs.append(('s_loss', s_loss.detach()))
+            return ops.sigmoid_bce(netsD[i].UNCOND_DNET.logits(features), real_labels) + cond_errG
+        return cond_errG
+
+    def damsm_branch():
+        region_features, cnn_code = image_encoder(fake_imgs[numDs - 1])
+        w_loss0, w_loss1, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size)
+        s_loss0, s_loss1 = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
+        return (w_loss0 + w_loss1) * cfg.TRAIN.SMOOTH.LAMBDA, (s_loss0 + s_loss1) * cfg.TRAIN.SMOOTH.LAMBDA
+
+    # The branches (one per discriminator, one through the image encoder) are independent until the final sum.  With
+    # ``streams`` they are enqueued on separate CUDA streams (forked from / joined to the current one): the many small kernels
+    # of the encoder and of the low-resolution discriminators fill the SMs / the HBM bandwidth the big tensor-core kernels
+    # of D_NET256 leave idle, in the forward and -- autograd runs every node on its forward's stream -- in the backward.
+    # Same kernels, same summation order: the result is bit-identical to the single-stream order.
+    g_losses, damsm = [None] * numDs, None
+    if streams is None:
+        for i in range(numDs):
+            g_losses[i] = d_branch(i)
+        if image_encoder is not None:
+            damsm = damsm_branch()
+    else:
+        cur = torch.cuda.current_stream()
+        for s in streams[:numDs + 1]:
+            s.wait_stream(cur)
+        if image_encoder is not None:       # the longest chain of small kernels first
+            with torch.cuda.stream(streams[numDs]):
+                damsm = damsm_branch()
+        for i in reversed(range(numDs)):
+            with torch.cuda.stream(streams[i]):
+                g_losses[i] = d_branch(i)
+        for s in streams[:numDs + 1]:
+            cur.wait_stream(s)
+    logs = []
+    errG_total = 0
+    for i in range(numDs):
+        errG_total = errG_total + g_losses[i]
+        logs.append(('g_loss%d' % i, g_losses[i].detach()))
+    if damsm is not None:
+        w_loss, s_loss = damsm
+        errG_total = errG_total + w_loss + s_loss
+        logs.append(('w_loss', w_loss.detach()))
+        logs.append(('s_loss', s_loss.detach()))
     return errG_total, logs
 
 

@@ -20,6 +20,7 @@ collages of ``save_img_results`` / ``build_super_images`` (host-side PIL drawing
 """
 from __future__ import annotations
 
+import contextlib
 import glob
 import os
 import time
@@ -180,6 +181,15 @@ class condGANTrainer(object):
             for p in m.parameters():
                 p.requires_grad = brequires
 
+    def _branch_streams(self, n, device):
+        """Side streams for the independent branches of a step (``cfg.MOG.STREAMS``; None = everything on one stream)."""
+        if not cfg.MOG.STREAMS or device.type != "cuda":
+            return None
+        have = getattr(self, "_side_streams", None)
+        if have is None or len(have) < n:
+            have = self._side_streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+        return have
+
     @staticmethod
     def _opt_step(opt, grad_scale=1.0):
         if isinstance(opt, mog_optim.Adam):
@@ -215,22 +225,36 @@ class condGANTrainer(object):
         # multi-GPU: the discriminators are independent, so the one with the largest gradient bucket (D_NET256, 643 MB)
         # goes first and its all-reduce travels while the smaller ones compute; single GPU keeps the reference's order
         order = sorted(range(len(netsD)), key=lambda j: -st["bucketDs"][j].flat.numel()) if multi else range(len(netsD))
+        # cfg.MOG.STREAMS: the (independent) discriminator steps run on separate CUDA streams, forked from and joined to the
+        # current one (inside a captured step: parallel branches of the graph) -- the small, bandwidth- or latency-bound
+        # kernels of one discriminator run next to the tensor-core kernels of another.  Same kernels and sums: bit-identical.
+        streams = self._branch_streams(len(netsD) + 1, sent_emb.device)
+        cur = torch.cuda.current_stream() if streams is not None else None
+        errDs = [None] * len(netsD)
         for i in order:
             netD = netsD[i]
-            netD.zero_grad(set_to_none=True)
-            if i == 0:
-                errD = discriminator_loss(netD, imgs[i], fake_imgs[i], sent_emb, st["real_labels"],
-                                          st["fake_labels"], self.gpus, local_labels=label_one_hot,
-                                          transf_matrices=transf_matrices, transf_matrices_inv=transf_matrices_inv)
-            else:
-                errD = discriminator_loss(netD, imgs[i], fake_imgs[i], sent_emb, st["real_labels"],
-                                          st["fake_labels"], self.gpus)
-            errD.backward()
-            if multi:
-                st["bucketDs"][i].launch()       # async all-reduce; next D computes meanwhile
-            elif optimize:
-                self._opt_step(st["optDs"][i])
-            errD_total = errD_total + errD.detach()
+            if streams is not None:
+                streams[i].wait_stream(cur)
+            with (torch.cuda.stream(streams[i]) if streams is not None else contextlib.nullcontext()):
+                netD.zero_grad(set_to_none=True)
+                if i == 0:
+                    errD = discriminator_loss(netD, imgs[i], fake_imgs[i], sent_emb, st["real_labels"],
+                                              st["fake_labels"], self.gpus, local_labels=label_one_hot,
+                                              transf_matrices=transf_matrices, transf_matrices_inv=transf_matrices_inv)
+                else:
+                    errD = discriminator_loss(netD, imgs[i], fake_imgs[i], sent_emb, st["real_labels"],
+                                              st["fake_labels"], self.gpus)
+                errD.backward()
+                if multi:
+                    st["bucketDs"][i].launch()       # async all-reduce; next D computes meanwhile
+                elif optimize:
+                    self._opt_step(st["optDs"][i])
+                errDs[i] = errD.detach()
+        if streams is not None:
+            for i in order:
+                cur.wait_stream(streams[i])
+        for i in range(len(netsD)):
+            errD_total = errD_total + errDs[i]
         if multi:
             for i in range(len(netsD)):
                 fused = isinstance(st["optDs"][i], mog_optim.Adam)
@@ -244,7 +268,7 @@ class condGANTrainer(object):
         errG_total, logs = generator_loss(netsD, self.image_encoder, fake_imgs, st["real_labels"], words_embs,
                                           sent_emb, st["match_labels"], cap_lens, class_ids, self.gpus,
                                           local_labels=label_one_hot, transf_matrices=transf_matrices,
-                                          transf_matrices_inv=transf_matrices_inv)
+                                          transf_matrices_inv=transf_matrices_inv, streams=streams)
         kl_loss = KL_loss(mu, logvar)
         errG_total = errG_total + kl_loss
         errG_total.backward()

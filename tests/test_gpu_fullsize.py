@@ -7,7 +7,8 @@
   them against each other at full size; the forward itself is pinned element-wise at small sizes (test_gpu_tc.py) and at
   config-5 widths with B = 4 (test_gpu_config5.py).
 * the full training step is bit-reproducible run to run, and its CUDA-graph form (what bench.py times) leaves bit-identical
-  parameters, EMA copy, Adam moments and BatchNorm buffers as the eager step.
+  parameters, EMA copy, Adam moments and BatchNorm buffers as the eager step -- with the independent branches of the step on
+  separate CUDA streams (cfg.MOG.STREAMS, the default) and on one stream.
 
 Run on the B200 box: -m gpu."""
 import numpy as np
@@ -120,10 +121,11 @@ def test_full_size_step_is_reproducible_and_graph_equals_eager():
 
     try:
         runs = []
-        for mode in ("eager", "eager", "graph"):
+        for mode in ("eager", "eager", "graph", "one-stream"):
+            cfg.MOG.STREAMS = mode != "one-stream"     # default: the independent branches of the step on separate streams
             tr, st = make()
             losses = []
-            if mode == "eager":
+            if mode in ("eager", "one-stream"):
                 for k in range(K):
                     losses.append([float(t) for t in tr.train_step(st, *args, noise=noises[k], eps=epss[k])])
             else:   # one eager step (creates the optimiser state), capture without training, then replays
@@ -135,12 +137,14 @@ def test_full_size_step_is_reproducible_and_graph_equals_eager():
             runs.append((losses, _snapshot(st)))
             del tr, st
             torch.cuda.empty_cache()
-        (l0, s0), (l1, s1), (l2, s2) = runs
+        (l0, s0), (l1, s1), (l2, s2), (l3, s3) = runs
         assert all(np.isfinite(v) for step in l0 for v in step)
         assert l0 == l1, "two eager runs of the same step differ"
         assert all(torch.equal(a, b) for a, b in zip(s0, s1)), "the eager step is not bit-reproducible"
         assert l0 == l2, ("graph vs eager losses", l0, l2)
         bad = [i for i, (a, b) in enumerate(zip(s0, s2)) if not torch.equal(a, b)]
         assert not bad, "graph replay differs from the eager step in %d of %d state tensors" % (len(bad), len(s0))
+        assert l0 == l3 and all(torch.equal(a, b) for a, b in zip(s0, s3)), "multi-stream step differs from the single-stream step"
     finally:
+        cfg.MOG.STREAMS = True
         ops.set_precision("fp32")
