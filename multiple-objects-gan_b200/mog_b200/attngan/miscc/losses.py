@@ -62,9 +62,19 @@ def discriminator_loss(netD, real_imgs, fake_imgs, conditions, real_labels, fake
     return errD
 
 
+def damsm_terms(image_encoder, fake_img, words_embs, sent_emb, match_labels, cap_lens, class_ids, batch_size):
+    """The DAMSM part of the generator objective (losses.py:205-224): (w_loss, s_loss), each already times LAMBDA.  It depends
+    on the generated image and the frozen encoders only -- not on the discriminators -- so a trainer may evaluate it on a side
+    stream while the discriminator steps run and hand it to :func:`generator_loss` (``damsm=``)."""
+    region_features, cnn_code = image_encoder(fake_img)
+    w_loss0, w_loss1, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size)
+    s_loss0, s_loss1 = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
+    return (w_loss0 + w_loss1) * cfg.TRAIN.SMOOTH.LAMBDA, (s_loss0 + s_loss1) * cfg.TRAIN.SMOOTH.LAMBDA
+
+
 def generator_loss(netsD, image_encoder, fake_imgs, real_labels, words_embs, sent_emb, match_labels,
                    cap_lens, class_ids, gpus=None, local_labels=None, transf_matrices=None,
-                   transf_matrices_inv=None, streams=None):
+                   transf_matrices_inv=None, streams=None, damsm=None):
     """losses.py:177-226.  ``logs`` is returned as a list of (name, 0-d tensor) pairs instead of a
     formatted string so that no ``.item()`` host sync happens inside the step (the reference forces
     4-5 syncs per step, losses.py:204,225); ``format_logs`` renders the reference's string.
@@ -83,27 +93,26 @@ def generator_loss(netsD, image_encoder, fake_imgs, real_labels, words_embs, sen
         return cond_errG
 
     def damsm_branch():
-        region_features, cnn_code = image_encoder(fake_imgs[numDs - 1])
-        w_loss0, w_loss1, _ = words_loss(region_features, words_embs, match_labels, cap_lens, class_ids, batch_size)
-        s_loss0, s_loss1 = sent_loss(cnn_code, sent_emb, match_labels, class_ids, batch_size)
-        return (w_loss0 + w_loss1) * cfg.TRAIN.SMOOTH.LAMBDA, (s_loss0 + s_loss1) * cfg.TRAIN.SMOOTH.LAMBDA
+        return damsm_terms(image_encoder, fake_imgs[numDs - 1], words_embs, sent_emb, match_labels, cap_lens, class_ids, batch_size)
 
     # The branches (one per discriminator, one through the image encoder) are independent until the final sum.  With
     # ``streams`` they are enqueued on separate CUDA streams (forked from / joined to the current one): the many small kernels
     # of the encoder and of the low-resolution discriminators fill the SMs / the HBM bandwidth the big tensor-core kernels
     # of D_NET256 leave idle, in the forward and -- autograd runs every node on its forward's stream -- in the backward.
     # Same kernels, same summation order: the result is bit-identical to the single-stream order.
-    g_losses, damsm = [None] * numDs, None
+    # ``damsm``: the terms already evaluated by the caller (on streams[numDs], joined below)
+    g_losses = [None] * numDs
     if streams is None:
         for i in range(numDs):
             g_losses[i] = d_branch(i)
-        if image_encoder is not None:
+        if image_encoder is not None and damsm is None:
             damsm = damsm_branch()
     else:
         cur = torch.cuda.current_stream()
-        for s in streams[:numDs + 1]:
+        for s in streams[:numDs]:
             s.wait_stream(cur)
-        if image_encoder is not None:       # the longest chain of small kernels first
+        if image_encoder is not None and damsm is None:       # the longest chain of small kernels first
+            streams[numDs].wait_stream(cur)
             with torch.cuda.stream(streams[numDs]):
                 damsm = damsm_branch()
         for i in reversed(range(numDs)):
