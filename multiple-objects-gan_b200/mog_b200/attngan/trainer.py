@@ -212,8 +212,15 @@ class condGANTrainer(object):
             st["bucketDs"] = [parallel.GradBucket(d.parameters()) for d in netsD]
         return st
 
-    def train_step(self, st, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv,
-                   label_one_hot, cap_lens=None, class_ids=None, noise=None, optimize=True, eps=None):
+    def train_step(self, *args, **kwargs):
+        """One iteration of trainer.py:294-342 (see :meth:`_train_step`); with ``cfg.MOG.STREAMS`` the weight gradients run on
+        side streams (``ops.async_wgrad``)."""
+        from .. import ops
+        with ops.async_wgrad(bool(cfg.MOG.STREAMS)):
+            return self._train_step(*args, **kwargs)
+
+    def _train_step(self, st, imgs, sent_emb, words_embs, mask, transf_matrices, transf_matrices_inv,
+                    label_one_hot, cap_lens=None, class_ids=None, noise=None, optimize=True, eps=None):
         """One iteration of trainer.py:294-342: G forward; per D: zero_grad, loss, backward, Adam;
         then G: zero_grad, adversarial (+DAMSM if an image encoder is attached) + KL loss, backward,
         Adam, EMA.  Returns (errD_total, errG_total, kl_loss) as device scalars (no host sync)."""

@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import (ACT_GLU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, MogConvDesc,
                    PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_NAMES, call)
 
+import contextlib
 import ctypes as C
 
 # Product default: bf16x3 (tcgen05, fp32-equivalent: meets the 1e-3 end-to-end bound).  MOG_PRECISION / cfg.MOG.PRECISION
@@ -311,6 +312,63 @@ def split_planes(x: torch.Tensor, precision: int):
     return planes
 
 
+# ---- weight gradients on a side stream -----------------------------------------------------------------------------------
+# Inside ``with async_wgrad():`` (the trainers wrap their step in it) the weight gradient of a convolution is enqueued on a
+# side stream of the stream its backward runs on, and is handed to ``weight.grad`` when the whole backward pass has finished
+# (autograd's end-of-pass callback) instead of being returned through autograd: the data-gradient chain -- BatchNorm backward
+# (HBM bound) -> dgrad (tensor bound) -> ... -- does not wait for the weight gradients, which fill the tensor pipe while the
+# bandwidth-bound kernels of the next layer run.  Same kernels, same accumulation order for weights used more than once:
+# bit-identical to the synchronous order.  Only ``loss.backward()`` style passes (gradients accumulated into leaves) may use
+# it -- ``torch.autograd.grad(..., weight)`` would see no gradient -- hence opt-in.
+_async = {"on": False, "pending": [], "sides": {}, "used": [], "cb": False}
+
+
+@contextlib.contextmanager
+def async_wgrad(enabled=True):
+    prev = _async["on"]
+    _async["on"] = bool(enabled)
+    try:
+        yield
+    finally:
+        _async["on"] = prev
+        if _async["pending"]:      # a backward pass that did not complete: drop what it left
+            _async["pending"].clear()
+            _async["used"].clear()
+            _async["cb"] = False
+
+
+def _async_side(cur):
+    s = _async["sides"].get(cur.cuda_stream)
+    if s is None:
+        s = _async["sides"][cur.cuda_stream] = torch.cuda.Stream(device=cur.device)
+    return s
+
+
+def _async_defer(weight, dw, keep, side):
+    _async["pending"].append((weight, dw, keep))
+    if side not in _async["used"]:
+        _async["used"].append(side)
+    if not _async["cb"]:
+        _async["cb"] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_async_flush)
+
+
+def _async_flush():
+    """End of the backward pass (runs with the caller's current stream set): join the side streams, hand the gradients over."""
+    cur = torch.cuda.current_stream()
+    for s in _async["used"]:
+        cur.wait_stream(s)
+    with torch.no_grad():
+        for weight, dw, _keep in _async["pending"]:
+            if weight.grad is None:
+                weight.grad = dw
+            else:
+                weight.grad.add_(dw)
+    _async["pending"].clear()
+    _async["used"].clear()
+    _async["cb"] = False
+
+
 def _split_dy(dy, y, act, precision, need_db, needed):
     """Output gradient of a conv whose epilogue applied ``act``: (fp32 dz or None, planes or None).  In the tcgen05 precisions
     the activation backward is fused into the plane split (dz never exists in fp32) unless the bias gradient needs it."""
@@ -530,13 +588,23 @@ class Conv2dFn(torch.autograd.Function):
             call("mog_conv2d_dgrad", C.byref(d), _ptr(dy), _ptr(dyp), _packed(weight, "dgrad", d, dkey).data_ptr(),
                  dx.data_ptr(), _ptr(ws), nws, st)
         if need_dw:
-            dw = torch.empty(w4.shape, device=dev, dtype=torch.float32)
-            if ctx.has_bias:
-                db = torch.empty(d.Cout, device=dev, dtype=torch.float32)
-            ws, nws = _workspace(d, 2, dev, dkey)
-            call("mog_conv2d_wgrad", C.byref(d), _ptr(x), _ptr(xp), _ptr(dy), _ptr(dyp), dw.data_ptr(), _ptr(db),
-                 _ptr(ws), nws, st)
-            dw = dw.reshape(weight.shape)
+            side = None
+            if _async["on"] and not ctx.has_bias and weight.is_leaf and dev.type == "cuda":
+                cur = torch.cuda.current_stream()
+                side = _async_side(cur)
+                side.wait_stream(cur)          # the operands (planes of x and dy) are ready on cur
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                dw = torch.empty(w4.shape, device=dev, dtype=torch.float32)
+                if ctx.has_bias:
+                    db = torch.empty(d.Cout, device=dev, dtype=torch.float32)
+                ws, nws = _workspace(d, 2, dev, dkey)
+                call("mog_conv2d_wgrad", C.byref(d), _ptr(x), _ptr(xp), _ptr(dy), _ptr(dyp), dw.data_ptr(), _ptr(db),
+                     _ptr(ws), nws, _stream())
+                dw = dw.reshape(weight.shape)
+            if side is not None:
+                # (the operands stay referenced until the end of the pass: their memory must not be reused on cur meanwhile)
+                _async_defer(weight, dw, (x, xp, dy, dyp, ws), side)
+                dw = None
         return dx, dw, db, None, None, None, None, None
 
     @staticmethod
