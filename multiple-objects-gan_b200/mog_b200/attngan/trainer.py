@@ -190,7 +190,8 @@ class condGANTrainer(object):
             # (MOG_STREAM_PRIO, default on: the branches of many small kernels -- stream 0 = D_NET64, the last = image encoder --
             # at a higher priority than the stream of the big tensor-core kernels)
             prio = os.environ.get("MOG_STREAM_PRIO", "1") == "1"     # (measured: 55.3 -> 54.6 ms)
-            have = self._side_streams = [torch.cuda.Stream(device=device, priority=-1 if prio and i in (0, n - 1) else 0)
+            lvl = int(os.environ.get("MOG_STREAM_PRIO_LEVELS", "1"))      # (2: big branches above the weight-gradient side streams too)
+            have = self._side_streams = [torch.cuda.Stream(device=device, priority=(-lvl if i in (0, n - 1) else -(lvl - 1)) if prio else 0)
                                          for i in range(n)]
         return have
 
