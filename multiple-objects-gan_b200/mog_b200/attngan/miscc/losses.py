@@ -118,7 +118,8 @@ def generator_loss(netsD, image_encoder, fake_imgs, real_labels, words_embs, sen
         for i in reversed(range(numDs)):
             with torch.cuda.stream(streams[i]):
                 g_losses[i] = d_branch(i)
-        for s in streams[:numDs + 1]:
+        # (join what was forked: the encoder stream only if the DAMSM terms ran on it, here or in the caller)
+        for s in streams[:numDs] + ([streams[numDs]] if damsm is not None else []):
             cur.wait_stream(s)
     logs = []
     errG_total = 0

@@ -275,3 +275,24 @@ def test_graphed_step_equals_eager_steps():
                 assert float(slot[0]) == K and slot[1] == K
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+
+
+def test_graphed_step_without_damsm_captures():
+    """The G+D-only step (no image encoder: ``bench.py --no-damsm``) as a CUDA graph with the branch streams on: every forked
+    stream is joined and no un-forked one is waited on (a capture error otherwise)."""
+    from mog_b200.attngan.trainer import condGANTrainer
+    c = dict(GF_DIM=8, DF_DIM=8, Z_DIM=20, R_NUM=1, EMBEDDING_DIM=32, T=6, B=4)
+    cfg = _set_cfg(c)
+    cfg.MOG.PRECISION = "bf16x3"
+    netG, netsD = _build(c, 31)
+    tr = condGANTrainer("", None, 0, None)
+    tr.image_encoder = None
+    optG, optDs = tr.define_optimizers(netG, netsD)
+    st = tr.make_step_state(netG, netsD, optG, optDs)
+    b = _dev(synth.attngan_batch(c["B"], T=c["T"], nef=c["EMBEDDING_DIM"], nz=c["Z_DIM"], seed=31))
+    args = (b["imgs"], b["sent_emb"], b["words_embs"], b["mask"], b["transf_matrices"], b["transf_matrices_inv"], b["label_one_hot"],
+            b["cap_lens"], b["class_ids"])
+    gs = tr.graphed_step(st, *args, warmup=2)
+    out = [float(t) for t in gs(*args)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for v in out)
